@@ -1,0 +1,288 @@
+"""URDF -> model descriptor (plain dict, JSON-serialisable).
+
+This replaces the reference's `p.loadURDF(path, useFixedBase, globalScaling)` call
+(`diy_gym/model.py:65`).  Semantics reproduced from the physics engine the reference drives
+([RECALLED-UNVERIFIED] - see DESIGN.md "parity unpinned"):
+
+* root = the link that is no joint's child; links are numbered by pre-order DFS with children in the
+  order their joints appear in the file, joint i connects link i to its parent, base = -1;
+  fixed joints are kept as 0-DoF links;
+* a link named `world` without `<inertial>` has mass 0 (=> fixed base); any other link without
+  `<inertial>` gets mass 1;
+* inertia tensors in the XML are ignored: the diagonal is recomputed from the collision geometry
+  (exact formula for a lone primitive coincident with the inertial frame, otherwise the box formula on
+  the collision AABB taken in the inertial frame, zero when there is no collision geometry);
+* mesh collision geometry is replaced by a fitted capsule/box proxy (`mesh.fit_proxy`).
+"""
+import json
+import os
+import xml.etree.ElementTree as ET
+
+import numpy as np
+
+from . import mesh as meshlib
+from .mathutil import Transform, quat_from_euler, quat_to_mat, mat_to_quat, quat_mul
+
+HULL_MARGIN = 0.001  # collision margin the reference engine gives hull / box children (Appendix A.1)
+
+
+def _floats(text, n=None, default=None):
+    if text is None:
+        return list(default)
+    vals = [float(t) for t in text.split()]
+    if n is not None and len(vals) != n:
+        raise ValueError('expected %d floats, got %r' % (n, text))
+    return vals
+
+
+def _origin(elem):
+    o = elem.find('origin') if elem is not None else None
+    if o is None:
+        return [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+    return _floats(o.get('xyz'), 3, (0, 0, 0)), _floats(o.get('rpy'), 3, (0, 0, 0))
+
+
+_AXIS_TO_Z = {
+    0: mat_to_quat(np.array([[0.0, 0, 1], [0, 1, 0], [-1, 0, 0]])),  # local z -> geometry x
+    1: mat_to_quat(np.array([[1.0, 0, 0], [0, 0, 1], [0, -1, 0]])),  # local z -> geometry y
+    2: np.array([0.0, 0, 0, 1]),
+}
+
+
+def _geometry(geom_elem, origin_xyz, origin_rpy, urdf_dir, cache):
+    """Return (shape dict in link frame, local aabb (center, half) in shape frame) or None."""
+    T_link_geom = Transform.from_xyz_rpy(origin_xyz, origin_rpy)
+    child = None
+    for tag in ('box', 'sphere', 'cylinder', 'capsule', 'mesh'):
+        child = geom_elem.find(tag)
+        if child is not None:
+            break
+    if child is None:
+        return None
+    if child.tag == 'box':
+        size = _floats(child.get('size'), 3)
+        shape = dict(type='box', dims=[0.5 * s for s in size] + [0.0])
+    elif child.tag == 'sphere':
+        shape = dict(type='sphere', dims=[float(child.get('radius')), 0.0, 0.0, 0.0])
+    elif child.tag in ('cylinder', 'capsule'):
+        r, l = float(child.get('radius')), float(child.get('length'))
+        shape = dict(type=child.tag, dims=[r, 0.5 * l, 0.0, 0.0])
+    else:
+        fname = child.get('filename')
+        if fname.startswith('package://'):
+            fname = fname[len('package://'):]
+        path = os.path.join(urdf_dir, fname)
+        scale = _floats(child.get('scale'), 3, (1, 1, 1))
+        key = (path, tuple(scale))
+        if key not in cache:
+            if not os.path.isfile(path):
+                cache[key] = None
+            else:
+                verts = meshlib.load_vertices(path) * np.asarray(scale)
+                cache[key] = meshlib.fit_proxy(verts) if len(verts) else None
+        fit = cache[key]
+        if fit is None:
+            return None
+        shape = dict(type=fit['type'], dims=list(fit['dims']) + [0.0] * (4 - len(fit['dims'])), mesh=os.path.basename(fname))
+        T_aabb = T_link_geom * Transform(fit['center'])
+        shape['aabb'] = dict(xyz=T_aabb.p.tolist(), quat=T_aabb.q.tolist(), half=list(fit['half']))
+        T_link_geom = T_link_geom * Transform(fit['center'], _AXIS_TO_Z[fit['axis']])
+    shape['xyz'] = T_link_geom.p.tolist()
+    shape['quat'] = T_link_geom.q.tolist()
+    return shape
+
+
+def shape_half_extents(shape):
+    """Half extents of the shape's own-frame bounding box (no margin)."""
+    t, d = shape['type'], shape['dims']
+    if t == 'box':
+        return np.array(d[:3])
+    if t == 'sphere':
+        return np.array([d[0]] * 3)
+    if t == 'cylinder':
+        return np.array([d[0], d[0], d[1]])
+    if t == 'capsule':
+        return np.array([d[0], d[0], d[1] + d[0]])
+    raise ValueError(t)
+
+
+def _inertia_rule(collisions, inertial_xyz, inertial_rpy, has_mesh_flags):
+    """Decide how the inertia diagonal is derived (evaluated at scale 1; lengths scale linearly)."""
+    if not collisions:
+        return dict(kind='zero')
+    T_link_inertial = Transform.from_xyz_rpy(inertial_xyz, inertial_rpy)
+    Ti = T_link_inertial.inverse()
+    if len(collisions) == 1:
+        c = collisions[0]
+        rel = Ti * Transform(c['xyz'], c['quat'])
+        if np.allclose(rel.p, 0, atol=1e-9) and abs(abs(rel.q[3]) - 1) < 1e-9 and not has_mesh_flags[0]:
+            return dict(kind=c['type'], dims=list(c['dims']))
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for c in collisions:
+        if 'aabb' in c:  # true mesh bounding box, not the proxy's
+            rel = Ti * Transform(c['aabb']['xyz'], c['aabb']['quat'])
+            h = np.abs(quat_to_mat(rel.q)) @ np.asarray(c['aabb']['half'])
+        else:
+            rel = Ti * Transform(c['xyz'], c['quat'])
+            h = np.abs(quat_to_mat(rel.q)) @ shape_half_extents(c)
+        margin = 0.0 if c['type'] in ('sphere', ) else HULL_MARGIN
+        lo = np.minimum(lo, rel.p - h - margin)
+        hi = np.maximum(hi, rel.p + h + margin)
+    return dict(kind='aabb', extent=(hi - lo).tolist())
+
+
+def inertia_from_rule(rule, mass, scale, xml_diag):
+    """Inertia diagonal in the inertial frame for `mass` at global `scale`."""
+    k = rule['kind']
+    if mass <= 0:
+        return np.zeros(3)
+    if k == 'zero':
+        return np.zeros(3)
+    if k == 'xml':
+        return np.asarray(xml_diag, dtype=float) * scale * scale
+    if k == 'aabb':
+        lx, ly, lz = np.asarray(rule['extent']) * scale
+        return mass / 12.0 * np.array([ly * ly + lz * lz, lx * lx + lz * lz, lx * lx + ly * ly])
+    d = np.asarray(rule['dims'], dtype=float) * scale
+    if k == 'box':
+        lx, ly, lz = 2 * (d[:3] + 0.0)
+        return mass / 12.0 * np.array([ly * ly + lz * lz, lx * lx + lz * lz, lx * lx + ly * ly])
+    if k == 'sphere':
+        return np.full(3, 0.4 * mass * d[0] * d[0])
+    if k == 'cylinder':
+        r2, h2 = d[0] * d[0], 4 * d[1] * d[1]
+        t1 = mass / 12.0 * h2 + mass / 4.0 * r2
+        return np.array([t1, t1, mass / 2.0 * r2])
+    if k == 'capsule':
+        hx, hy, hz = d[0], d[0], d[1] + d[0]
+        lx, ly, lz = 2 * hx, 2 * hy, 2 * hz
+        return mass / 12.0 * np.array([ly * ly + lz * lz, lx * lx + lz * lz, lx * lx + ly * ly])
+    raise ValueError(k)
+
+
+def compile_urdf(path, rel_name=None):
+    """Parse a URDF file into a model descriptor."""
+    tree = ET.parse(path)
+    robot = tree.getroot()
+    urdf_dir = os.path.dirname(os.path.abspath(path))
+    cache = {}
+
+    materials = {}
+    for m in robot.findall('material'):
+        c = m.find('color')
+        if c is not None:
+            materials[m.get('name')] = _floats(c.get('rgba'), 4)
+    for link in robot.findall('link'):
+        for vis in link.findall('visual'):
+            m = vis.find('material')
+            if m is not None and m.find('color') is not None and m.get('name'):
+                materials.setdefault(m.get('name'), _floats(m.find('color').get('rgba'), 4))
+
+    link_elems = {l.get('name'): l for l in robot.findall('link')}
+    joints = []
+    for j in robot.findall('joint'):
+        if j.find('parent') is None or j.find('child') is None:
+            continue
+        joints.append(j)
+    children_of = {name: [] for name in link_elems}
+    child_names = set()
+    for j in joints:
+        children_of[j.find('parent').get('link')].append(j)
+        child_names.add(j.find('child').get('link'))
+    roots = [n for n in link_elems if n not in child_names]
+    if len(roots) != 1:
+        raise ValueError('URDF must have exactly one root link, found %r' % roots)
+
+    links = []
+
+    def add_link(name, parent_idx, joint_elem):
+        le = link_elems[name]
+        inertial = le.find('inertial')
+        if inertial is not None:
+            mass = float(inertial.find('mass').get('value')) if inertial.find('mass') is not None else 0.0
+            ixyz, irpy = _origin(inertial)
+            ie = inertial.find('inertia')
+            xml_diag = [float(ie.get(k, 0)) for k in ('ixx', 'iyy', 'izz')] if ie is not None else [0.0, 0.0, 0.0]
+        else:
+            mass = 0.0 if name == 'world' else 1.0
+            ixyz, irpy = [0.0, 0.0, 0.0], [0.0, 0.0, 0.0]
+            xml_diag = [0.0, 0.0, 0.0] if name == 'world' else [1.0, 1.0, 1.0]
+        contact = le.find('contact')
+        lat = None
+        if contact is not None and contact.find('lateral_friction') is not None:
+            lat = float(contact.find('lateral_friction').get('value'))
+
+        collisions, mesh_flags = [], []
+        for col in le.findall('collision'):
+            g = col.find('geometry')
+            if g is None:
+                continue
+            xyz, rpy = _origin(col)
+            s = _geometry(g, xyz, rpy, urdf_dir, cache)
+            if s is not None:
+                collisions.append(s)
+                mesh_flags.append('mesh' in s)
+        visuals = []
+        for vis in le.findall('visual'):
+            g = vis.find('geometry')
+            if g is None:
+                continue
+            xyz, rpy = _origin(vis)
+            s = _geometry(g, xyz, rpy, urdf_dir, cache)
+            if s is None:
+                continue
+            rgba = [1.0, 1.0, 1.0, 1.0]
+            m = vis.find('material')
+            if m is not None:
+                if m.find('color') is not None:
+                    rgba = _floats(m.find('color').get('rgba'), 4)
+                elif m.get('name') in materials:
+                    rgba = materials[m.get('name')]
+            s['rgba'] = rgba
+            visuals.append(s)
+        if not visuals:  # fall back to the collision proxies so the body is visible to the camera
+            for c in collisions:
+                v = dict(c)
+                v['rgba'] = [1.0, 1.0, 1.0, 1.0]
+                visuals.append(v)
+
+        rule = _inertia_rule(collisions, ixyz, irpy, mesh_flags if mesh_flags else [False])
+
+        jd = None
+        if joint_elem is not None:
+            jtype = joint_elem.get('type')
+            jxyz, jrpy = _origin(joint_elem)
+            axis_e = joint_elem.find('axis')
+            axis = _floats(axis_e.get('xyz'), 3) if axis_e is not None else [1.0, 0.0, 0.0]
+            lim = joint_elem.find('limit')
+            dyn = joint_elem.find('dynamics')
+            jd = dict(name=joint_elem.get('name'), type=jtype, xyz=jxyz, rpy=jrpy, axis=axis,
+                      lower=float(lim.get('lower', 0)) if lim is not None else 0.0,
+                      upper=float(lim.get('upper', -1 if lim.get('lower') is None else 0)) if lim is not None else -1.0,
+                      effort=float(lim.get('effort', 0)) if lim is not None else 0.0,
+                      velocity=float(lim.get('velocity', 0)) if lim is not None else 0.0,
+                      damping=float(dyn.get('damping', 0)) if dyn is not None else 0.0,
+                      friction=float(dyn.get('friction', 0)) if dyn is not None else 0.0)
+            if jtype not in ('fixed', 'revolute', 'continuous', 'prismatic'):
+                raise ValueError('Unsupported joint type %r on joint %s' % (jtype, jd['name']))
+            if jtype in ('revolute', 'continuous', 'prismatic') and rule['kind'] == 'zero' and mass > 0:
+                rule = dict(kind='xml')
+        idx = len(links)
+        links.append(dict(name=name, parent=parent_idx, joint=jd, mass=mass, inertia_xml=xml_diag, inertial_xyz=ixyz,
+                          inertial_rpy=irpy, has_inertial=inertial is not None, lateral_friction=lat,
+                          collisions=collisions, visuals=visuals, inertia_rule=rule))
+        for j in children_of[name]:
+            add_link(j.find('child').get('link'), idx, j)
+
+    add_link(roots[0], -1, None)
+    return dict(name=robot.get('name'), source=rel_name or os.path.basename(path), links=links)
+
+
+def save_model(desc, path):
+    with open(path, 'w') as f:
+        json.dump(desc, f, indent=None, separators=(',', ':'))
+
+
+def load_model(path):
+    with open(path, 'r') as f:
+        return json.load(f)
