@@ -32,7 +32,7 @@ MAGIC = 0x44594742  # 'DYGB'
 
 HDR_I_FIELDS = [
     'nb', 'nl', 'nd', 'ns', 'nv', 'npair', 'ncam', 'nop', 'n_act', 'n_obs', 'n_rew', 'n_term', 'substeps', 'iterations',
-    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters',
+    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn',
     # state offsets
     'S_BPOS', 'S_BQUAT', 'S_BVEL', 'S_BOMEGA', 'S_Q', 'S_QD', 'S_MKP', 'S_MKD', 'S_MTPOS', 'S_MTVEL', 'S_MMAXF',
     'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_STEP', 'S_RESETS',
@@ -43,10 +43,10 @@ HDR_I_FIELDS = [
 HDR_F_FIELDS = ['dt', 'gx', 'gy', 'gz', 'erp', 'contact_erp', 'linear_slop', 'contact_margin', 'ik_damping',
                 'ik_threshold', 'max_joint_vel', 'default_motor_impulse', 'limit_max_impulse', 'ik_null_lambda_sq']
 
-BODY_I_W, BODY_F_W = 6, 8
+BODY_I_W, BODY_F_W = 8, 8
 LINK_I_W, LINK_F_W = 6, 28
-SHAPE_I_W, SHAPE_F_W = 4, 12
-VIS_I_W, VIS_F_W = 4, 16
+SHAPE_I_W, SHAPE_F_W = 4, 20
+VIS_I_W, VIS_F_W = 4, 24
 OP_I_W = 8
 CAM_I_W, CAM_F_W = 8, 16
 
@@ -67,6 +67,7 @@ class BodyInfo:
         self.fixed_base = fixed_base
         self.base_pos, self.base_quat = np.asarray(base_pos, float), np.asarray(base_quat, float)
         self.mass_override, self.color = mass_override, color
+        self.per_env_pose = False  # set by add-ons (respawn) that move the base per environment
         self.links = desc['links']
         self.n_links = len(self.links) - 1
         self.link_start = self.dof_start = self.frame_base = None  # set by SceneBuilder
@@ -183,11 +184,16 @@ class SceneBuilder:
         shapes, visuals = [], []
         frame_movable = np.zeros(nframes, bool)
 
+        dyn_index, ndyn = {}, 0
+        for b in B:
+            dyn_index[b.index] = ndyn if b.kind != 0 else -1
+            ndyn += int(b.kind != 0)
         for b in B:
             s = b.scale
             L = b.links
             LI = [Transform.from_xyz_rpy(np.asarray(l['inertial_xyz']) * s, l['inertial_rpy']) for l in L]
-            body_i[b.index] = [b.kind, b.link_start, b.n_links, b.dof_start, b.n_dofs, b.frame_link0]
+            baked = int(b.kind == 0 and not b.per_env_pose)
+            body_i[b.index] = [b.kind, b.link_start, b.n_links, b.dof_start, b.n_dofs, b.frame_link0, dyn_index[b.index], baked]
             body_f[b.index, 0:3] = LI[0].p
             body_f[b.index, 3:7] = LI[0].q
             init_pose[b.index, 0:3] = b.base_pos
@@ -235,22 +241,26 @@ class SceneBuilder:
                 for c in l['collisions']:
                     T = Tci * Transform(np.asarray(c['xyz']) * s, c['quat'])
                     dims = np.asarray(c['dims'], float) * s
+                    Tw = Transform(b.base_pos, b.base_quat) * T
                     shapes.append(dict(body=b.index, frame=fr, type=SHAPE_TYPES[c['type']], pos=T.p, quat=T.q, dims=dims,
-                                       friction=fric))
+                                       friction=fric, baked=int(b.kind == 0 and not b.per_env_pose), wpos=Tw.p, wquat=Tw.q))
                 for v in l['visuals']:
                     T = Tci * Transform(np.asarray(v['xyz']) * s, v['quat'])
                     dims = np.asarray(v['dims'], float) * s
                     rgba = list(v.get('rgba', [1, 1, 1, 1]))
                     if b.color is not None and k == 0:
                         rgba = [float(x) for x in b.color]
-                    visuals.append(dict(frame=fr, type=SHAPE_TYPES[v['type']], pos=T.p, quat=T.q, dims=dims, rgba=rgba))
+                    Tw = Transform(b.base_pos, b.base_quat) * T
+                    visuals.append(dict(frame=fr, type=SHAPE_TYPES[v['type']], pos=T.p, quat=T.q, dims=dims, rgba=rgba,
+                                        baked=int(b.kind == 0 and not b.per_env_pose), wpos=Tw.p, wquat=Tw.q))
 
         ns, nv = len(shapes), len(visuals)
         shape_i = np.zeros((ns, SHAPE_I_W), np.int32)
         shape_f = np.zeros((ns, SHAPE_F_W))
         friction = np.zeros(ns)
         for i, sh in enumerate(shapes):
-            shape_i[i] = [sh['body'], sh['frame'], sh['type'], 0]
+            shape_i[i] = [sh['body'], sh['frame'], sh['type'], sh['baked']]
+            shape_f[i, 12:15], shape_f[i, 15:19] = sh['wpos'], sh['wquat']
             shape_f[i, 0:3], shape_f[i, 3:7], shape_f[i, 7:11] = sh['pos'], sh['quat'], sh['dims']
             d = sh['dims']
             shape_f[i, 11] = {0: d[0], 1: float(np.linalg.norm(d[:3])), 2: d[0] + d[1], 3: float(np.hypot(d[0], d[1]))}[sh['type']]
@@ -258,7 +268,8 @@ class SceneBuilder:
         vis_i = np.zeros((nv, VIS_I_W), np.int32)
         vis_f = np.zeros((nv, VIS_F_W))
         for i, v in enumerate(visuals):
-            vis_i[i] = [v['frame'], v['type'], 0, 0]
+            vis_i[i] = [v['frame'], v['type'], v['baked'], 0]
+            vis_f[i, 16:19], vis_f[i, 19:23] = v['wpos'], v['wquat']
             vis_f[i, 0:3], vis_f[i, 3:7], vis_f[i, 7:11], vis_f[i, 11:15] = v['pos'], v['quat'], v['dims'], v['rgba']
             d = v['dims']
             vis_f[i, 15] = {0: d[0], 1: float(np.linalg.norm(d[:3])), 2: d[0] + d[1], 3: float(np.hypot(d[0], d[1]))}[v['type']]
@@ -336,7 +347,7 @@ class SceneBuilder:
 
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
-                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20)
+                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn)
         hdr.update(lay)
         hdr_i = np.array([hdr[k] for k in HDR_I_FIELDS], np.int32)
         hf = dict(dt=self.timestep, gx=self.gravity[0], gy=self.gravity[1], gz=self.gravity[2], erp=0.2, contact_erp=0.2,
