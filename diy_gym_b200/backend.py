@@ -1,0 +1,147 @@
+"""ctypes binding of the C ABI (include/diygym_b200.h) + the torch-owned device buffers of one world.
+
+There is no CPU fallback: a missing library or a missing CUDA device raises.  PyTorch is used for device
+memory and streams only; the arithmetic is in csrc/dg_kernels.cu.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from .build import LIB
+
+_lib = None
+
+
+class DgBufferTable(ctypes.Structure):
+    _fields_ = [('state', ctypes.c_void_p), ('param', ctypes.c_void_p), ('action', ctypes.c_void_p), ('obs', ctypes.c_void_p),
+                ('reward', ctypes.c_void_p), ('term', ctypes.c_void_p)]
+
+
+Q = dict(STATE_SIZE=0, PARAM_SIZE=1, N_ACT=2, N_OBS=3, N_REW=4, N_TERM=5, N_ENVS=6, TEAM=7, BLOCK_THREADS=8, GRID_BLOCKS=9,
+         SMEM_BYTES=10, WS_FLOATS=11, N_CAMERAS=12, LAUNCHES=13)
+
+
+def load_library():
+    """dlopen libdiygym_b200.so (built in-tree by `python -m diy_gym_b200.build`); raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB):
+        raise RuntimeError('libdiygym_b200.so is missing: run `python -m diy_gym_b200.build` (there is no CPU fallback)')
+    L = ctypes.CDLL(LIB)
+    vp, ip, dp = ctypes.c_void_p, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double)
+    L.dg_world_create.restype = ctypes.c_int
+    L.dg_world_create.argtypes = [ip, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]
+    L.dg_world_destroy.restype = None
+    L.dg_world_destroy.argtypes = [vp]
+    L.dg_last_error.restype = ctypes.c_char_p
+    L.dg_last_error.argtypes = [vp]
+    L.dg_query.restype = ctypes.c_int64
+    L.dg_query.argtypes = [vp, ctypes.c_int]
+    L.dg_bind_buffers.restype = ctypes.c_int
+    L.dg_bind_buffers.argtypes = [vp, ctypes.POINTER(DgBufferTable)]
+    L.dg_set_seed.restype = ctypes.c_int
+    L.dg_set_seed.argtypes = [vp, ctypes.c_uint32, ctypes.c_int]
+    for f in ('dg_init_state', 'dg_step'):
+        getattr(L, f).restype = ctypes.c_int
+        getattr(L, f).argtypes = [vp, vp]
+    L.dg_reset.restype = ctypes.c_int
+    L.dg_reset.argtypes = [vp, vp, vp]
+    L.dg_render.restype = ctypes.c_int
+    L.dg_render.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    L.dg_step_host.restype = ctypes.c_int
+    L.dg_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    _lib = L
+    return L
+
+
+class World:
+    """N lock-stepped environments of one compiled scene on one GPU."""
+    def __init__(self, scene, n_envs, device=0, team=0, seed=1234, env_id_offset=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError('diy_gym_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        L = load_library()
+        self.L, self.scene, self.n_envs = L, scene, int(n_envs)
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        ib = np.ascontiguousarray(scene.ibuf, np.int32)
+        fb = np.ascontiguousarray(scene.fbuf, np.float64)
+        h = ctypes.c_void_p()
+        rc = L.dg_world_create(ib.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ib.size, fb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                               fb.size, self.n_envs, self.device.index, int(team), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError('dg_world_create failed (%d): %s' % (rc, L.dg_last_error(None).decode()))
+        self._h = h
+        q = lambda k: int(L.dg_query(h, Q[k]))
+        self.S, self.P, self.n_act, self.n_obs, self.n_rew, self.n_term = q('STATE_SIZE'), q('PARAM_SIZE'), q('N_ACT'), q('N_OBS'), q('N_REW'), q('N_TERM')
+        self.team, self.block_threads, self.grid_blocks, self.smem_bytes, self.ws_floats = q('TEAM'), q('BLOCK_THREADS'), q('GRID_BLOCKS'), q('SMEM_BYTES'), q('WS_FLOATS')
+        N, dev = self.n_envs, self.device
+        self.state = torch.zeros((N, self.S), dtype=torch.float32, device=dev)
+        self.param = torch.zeros((N, self.P), dtype=torch.float32, device=dev)
+        self.action = torch.zeros((N, max(self.n_act, 1)), dtype=torch.float32, device=dev)[:, :self.n_act].contiguous() if self.n_act else torch.zeros((N, 0), dtype=torch.float32, device=dev)
+        self.obs = torch.zeros((N, self.n_obs), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((N, self.n_rew), dtype=torch.float32, device=dev)
+        self.term = torch.zeros((N, self.n_term), dtype=torch.uint8, device=dev)
+        self._keep = [torch.zeros(4, device=dev) for _ in range(4)]   # non-null stand-ins for zero-width buffers
+        ptr = lambda t, i: t.data_ptr() if t.numel() else self._keep[i].data_ptr()
+        tab = DgBufferTable(self.state.data_ptr(), self.param.data_ptr(), ptr(self.action, 0), ptr(self.obs, 1), ptr(self.reward, 2), ptr(self.term, 3))
+        self._check(L.dg_bind_buffers(h, ctypes.byref(tab)))
+        self._check(L.dg_set_seed(h, int(seed) & 0xffffffff, int(env_id_offset)))
+        self._check(L.dg_init_state(h, self._stream()))
+        self.cams = [(int(c[1]), int(c[2])) for c in scene.sec['CAM_I']]
+        self._img = {}
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError('diygym_b200 error %d: %s' % (rc, self.L.dg_last_error(self._h).decode()))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            torch.cuda.synchronize(self.device)
+            self.L.dg_world_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.L.dg_query(self._h, Q['LAUNCHES']))
+
+    def step(self):
+        self._check(self.L.dg_step(self._h, self._stream()))
+
+    def reset(self, mask=None):
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        self._check(self.L.dg_reset(self._h, ctypes.c_void_p(mask.data_ptr()) if mask is not None else None, self._stream()))
+
+    def render(self, cam=0):
+        w, hgt = self.cams[cam]
+        if cam not in self._img:
+            self._img[cam] = (torch.empty((self.n_envs, hgt, w, 3), dtype=torch.float32, device=self.device),
+                              torch.empty((self.n_envs, hgt, w), dtype=torch.float32, device=self.device))
+        rgb, depth = self._img[cam]
+        self._check(self.L.dg_render(self._h, cam, ctypes.c_void_p(rgb.data_ptr()), ctypes.c_void_p(depth.data_ptr()), self._stream()))
+        return rgb, depth
+
+    def step_host(self, action_host, obs_host, reward_host, term_host):
+        """Host-buffer step: numpy (ideally pinned) in, numpy out, synchronous."""
+        p = lambda a: ctypes.c_void_p(a.ctypes.data) if a is not None and a.size else None
+        self._check(self.L.dg_step_host(self._h, p(action_host), p(obs_host), p(reward_host), p(term_host), self._stream()))
+
+    # named views into the state / parameter rows (same names as csrc/scene_sections.h)
+    def s(self, name, n):
+        o = self.scene.hdr[name]
+        return self.state[:, o:o + n]
+
+    def p(self, name, n):
+        o = self.scene.hdr[name]
+        return self.param[:, o:o + n]

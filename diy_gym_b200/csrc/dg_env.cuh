@@ -1,0 +1,1086 @@
+// dg_env.cuh - the per-environment step, written once for a TEAM of `nt` cooperating lanes.
+//
+// One environment is advanced by a team of nt lanes (nt = 1,2,4,...,32, a sub-warp group).  The code is a
+// sequence of PHASES; inside a phase every lane works on its own items (bodies, M^-1 columns, shape pairs,
+// constraint rows, add-on ops) and never reads what another lane writes in the same phase; between phases the
+// team synchronises (__syncwarp on the team mask).  The test-only CPU emulation (tests/emul) runs the same
+// phases lane after lane, which is exactly the barrier semantics.
+//
+// What it computes replaces, for N environments at once, the reference's
+//   DIYGym.step  (/root/reference/diy_gym/diy_gym.py:187-209):  add-on update -> p.stepSimulation() -> observe/reward/terminal
+//   DIYGym.reset (/root/reference/diy_gym/diy_gym.py:130-148):  add-on reset -> hot-start steps -> observe
+// with p.stepSimulation() configured as at diy_gym.py:76-82 (fixedTimeStep 1/240, numSubSteps 2, 150 solver sweeps).
+// The physics is this repo's own fp32 engine (articulated-body forward dynamics, primitive contact generation,
+// projected Gauss-Seidel on motor / limit / contact rows); its fp64 checker is oracle/bullet_restatement.c.
+#pragma once
+#include "dg_math.cuh"
+#include "dg_scene.h"
+
+namespace dg {
+
+struct Env {
+  const DevScene* sc;
+  float* ws;          // team workspace (shared memory on the GPU)
+  float* st;          // this environment's state row  [S]
+  float* pr;          // this environment's parameter row [P]
+  const float* act;   // [n_act]
+  float* obs;         // [n_obs]
+  float* rew;         // [n_rew]
+  uint8_t* term;      // [n_term]
+  uint32_t seed;
+  int env_id;
+};
+
+#define SC (*C.sc)
+#define WSI(C) ((int*)(C).ws)
+#define KIN(s) (C.ws + SC.W_KIN + 18 * (s))
+#define LNK(gl) (C.ws + SC.W_LINK + 19 * (gl))
+#define ABA(s) (C.ws + SC.X_ABA + 39 * (s))
+#define LNX(gl) (C.ws + SC.X_LNK + 7 * (gl))
+#define DOF(k, d) (C.ws[SC.W_DOF + (k) * SC.nd + (d)])
+#define BST(di) (C.ws + SC.W_BST + 13 * (di))
+#define EXT(s) (C.ws + SC.W_EXT + 6 * (s))
+#define ST(name) (C.st + DG_SO(C.sc, name))
+#define PR(name) (C.pr + DG_PO(C.sc, name))
+
+DG_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+DG_HD int float_as_int(float f) { union { float f; int i; } u; u.f = f; return u.i; }
+DG_HD float int_as_float(int i) { union { float f; int i; } u; u.i = i; return u.f; }
+
+// ------------------------------------------------------------------ load / store -------------------------------
+// Copies the dynamic part of the state row into the workspace; static bodies that are not baked get their pose too.
+DG_FN void phase_load(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  for (int i = ln; i < 13 * sc.ndyn; i += nt) {
+    int di = i / 13, k = i - 13 * di, b = sc.dyn_body[di];
+    float v;
+    if (k < 3) v = ST(S_BPOS)[3 * b + k];
+    else if (k < 7) v = ST(S_BQUAT)[4 * b + k - 3];
+    else if (k < 10) v = ST(S_BVEL)[3 * b + k - 7];
+    else v = ST(S_BOMEGA)[3 * b + k - 10];
+    BST(di)[k] = v;
+  }
+  for (int d = ln; d < sc.nd; d += nt) {
+    float qd = ST(S_QD)[d];
+    DOF(D_Q, d) = ST(S_Q)[d]; DOF(D_QD, d) = qd; DOF(D_KP, d) = ST(S_MKP)[d]; DOF(D_KD, d) = ST(S_MKD)[d];
+    DOF(D_TPOS, d) = ST(S_MTPOS)[d]; DOF(D_TVEL, d) = ST(S_MTVEL)[d]; DOF(D_MAXF, d) = ST(S_MMAXF)[d];
+    DOF(D_APPLIED, d) = ST(S_MAPPLIED)[d]; DOF(D_JTQ, d) = ST(S_JTORQUE)[d];
+    DOF(D_TDAMP, d) = -PR(P_JDAMP)[d] * qd;   // joint damping torque, evaluated once per outer step
+    DOF(D_QDD, d) = 0.f;
+  }
+  for (int f = ln; f < sc.nframes; f += nt) {
+    int s = sc.frame_slot[f];
+    if (s < 0) continue;
+    float* e = EXT(s);
+    for (int i = 0; i < 3; i++) { e[i] = ST(S_EXTF)[3 * f + i]; e[3 + i] = ST(S_EXTT)[3 * f + i]; }
+    if (f < sc.nb && sc.body_i[DG_BODY_I_W * f] == 0) {   // static body with a per-environment pose
+      float* K = KIN(s);
+      q_to_mat(K, ST(S_BQUAT) + 4 * f); v_cpy(K + 9, ST(S_BPOS) + 3 * f);
+      v_set(K + 12, 0, 0, 0); v_set(K + 15, 0, 0, 0);
+    }
+  }
+  if (ln == 0) for (int i = 0; i < WH_COUNT; i++) WSI(C)[sc.W_HDR + i] = 0;
+}
+
+// ------------------------------------------------------------------ kinematics ---------------------------------
+// joint transform of link gl at coordinate q:  E = child_from_parent rotation, r = child COM in parent coordinates
+DG_FN void joint_xform(const DevScene& sc, int gl, float q, float* E, float* r) {
+  const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl; const float* R0 = sc.link_x + 16 * gl;
+  float Rrel[9], tmp[3];
+  if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
+  else if (li[2] == 2) { m_cpy(Rrel, R0); float dd[3] = {lf[7] + lf[10] * q, lf[8] + lf[11] * q, lf[9] + lf[12] * q}; m_vec(tmp, R0, dd); }
+  else { m_cpy(Rrel, R0); m_vec(tmp, R0, lf + 7); }
+  v_add(r, lf + 4, tmp);
+  E[0] = Rrel[0]; E[1] = Rrel[3]; E[2] = Rrel[6]; E[3] = Rrel[1]; E[4] = Rrel[4]; E[5] = Rrel[7]; E[6] = Rrel[2]; E[7] = Rrel[5]; E[8] = Rrel[8];
+}
+DG_HD int parent_slot(const int* li, int l0, int s0) { return li[1] < 0 ? s0 : s0 + 1 + (li[1] - l0); }
+
+// world pose and body-frame spatial velocity of every frame of dynamic body b
+DG_FN void fk_vel_body(const Env& C, int b) {
+  const DevScene& sc = SC;
+  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  int l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT];
+  const float* bs = BST(bp[BP_DI]);
+  float* K0 = KIN(s0);
+  q_to_mat(K0, bs + 3); v_cpy(K0 + 9, bs);
+  mT_vec(K0 + 12, K0, bs + 10); mT_vec(K0 + 15, K0, bs + 7);
+  for (int k = 0; k < nlb; k++) {
+    int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lx = sc.link_x + 16 * gl;
+    float* L = LNK(gl); float* K = KIN(s0 + 1 + k); const float* Kp = KIN(parent_slot(li, l0, s0));
+    int dof = li[3];
+    float E[9], r[3], t[3], t2[3];
+    joint_xform(sc, gl, dof >= 0 ? DOF(D_Q, dof) : 0.f, E, r);
+    m_cpy(L, E); v_cpy(L + 9, r);
+    float Rw[9]; m_mulT(Rw, Kp, E); m_cpy(K, Rw);
+    m_vec(t, Kp, r); v_add(K + 9, Kp + 9, t);
+    float w[3], v[3];
+    m_vec(w, E, Kp + 12);
+    v_cross(t, Kp + 12, r); v_add(t2, Kp + 15, t); m_vec(v, E, t2);
+    if (dof >= 0) { float qd = DOF(D_QD, dof); v_madd(w, lx + 9, qd); v_madd(v, lx + 12, qd); }
+    v_cpy(K + 12, w); v_cpy(K + 15, v);
+  }
+}
+
+// ------------------------------------------------------------------ articulated-body algorithm -----------------
+DG_HD void ia_mul(const float* A, const float* B, const float* Cm, const float* a, const float* l, float* n, float* f) {
+  float t[3]; m_vec(n, A, a); m_vec(t, B, l); v_add(n, n, t); mT_vec(f, B, a); m_vec(t, Cm, l); v_add(f, f, t);
+}
+// Gauss-Jordan inverse with partial pivoting of the n x n matrix M (destroyed); both live in the workspace
+DG_FN int invert_small(float* M, int n, float* inv) {
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = (i == j) ? 1.f : 0.f;
+  for (int c = 0; c < n; c++) {
+    int p = c;
+    for (int r2 = c + 1; r2 < n; r2++) if (fabsf(M[r2 * n + c]) > fabsf(M[p * n + c])) p = r2;
+    if (fabsf(M[p * n + c]) < 1e-30f) return -1;
+    if (p != c) for (int j = 0; j < n; j++) { float t = M[c * n + j]; M[c * n + j] = M[p * n + j]; M[p * n + j] = t; t = inv[c * n + j]; inv[c * n + j] = inv[p * n + j]; inv[p * n + j] = t; }
+    float d = 1.0f / M[c * n + c];
+    for (int j = 0; j < n; j++) { M[c * n + j] *= d; inv[c * n + j] *= d; }
+    for (int r2 = 0; r2 < n; r2++) if (r2 != c) {
+      float fct = M[r2 * n + c];
+      if (fct != 0.f) for (int j = 0; j < n; j++) { M[r2 * n + j] -= fct * M[c * n + j]; inv[r2 * n + j] -= fct * inv[c * n + j]; }
+    }
+  }
+  return 0;
+}
+
+// forward dynamics of dynamic body b, then the velocity half of the semi-implicit Euler step
+DG_FN void aba_body(const Env& C, int b, float h) {
+  const DevScene& sc = SC;
+  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  int kind = bi[0], l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT], di = bp[BP_DI];
+  const float *mass = PR(P_MASS), *inertia = PR(P_INERTIA);
+  float kl = PR(P_LINDAMP)[b], ka = PR(P_ANGDAMP)[b];
+  // pass 1: bias forces and rigid-body inertias
+  for (int k = -1; k < nlb; k++) {
+    int s = s0 + 1 + k, f = k < 0 ? b : sc.nb + l0 + k;
+    float* X = ABA(s);
+    if (k < 0 && kind != 2) { for (int i = 0; i < 33; i++) X[i] = 0.f; continue; }
+    const float* K = KIN(s); const float *w = K + 12, *v = K + 15; const float* e = EXT(s);
+    float m = mass[f]; const float* I = inertia + 3 * f;
+    float Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]}, t[3], fw[3], pa[3], pl[3];
+    v_cross(pa, w, Iw);
+    v_cross(t, w, v); v_scale(pl, t, m);
+    fw[0] = sc.g[0] * m + e[0]; fw[1] = sc.g[1] * m + e[1]; fw[2] = sc.g[2] * m + e[2];
+    mT_vec(t, K, fw); v_sub(pl, pl, t);
+    mT_vec(t, K, e + 3); v_sub(pa, pa, t);
+    float wn = v_len(w), vn = v_len(v);
+    v_madd(pa, Iw, ka + ka * wn);
+    float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, kl + kl * vn);
+    v_cpy(X, pa); v_cpy(X + 3, pl);
+    for (int i = 6; i < 33; i++) X[i] = 0.f;
+    X[6] = I[0]; X[10] = I[1]; X[14] = I[2]; X[24] = m; X[28] = m; X[32] = m;
+    if (k >= 0) {
+      int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; float* c = LNX(gl);
+      if (li[3] >= 0) {
+        const float* lx = sc.link_x + 16 * gl;
+        float qd = DOF(D_QD, li[3]), sa[3], sl[3], t2[3];
+        v_scale(sa, lx + 9, qd); v_scale(sl, lx + 12, qd);
+        v_cross(c, w, sa); v_cross(c + 3, w, sl); v_cross(t2, v, sa); v_add(c + 3, c + 3, t2);
+      } else for (int i = 0; i < 6; i++) c[i] = 0.f;
+    }
+  }
+  // pass 2: articulated inertias, leaves to root
+  for (int k = nlb - 1; k >= 0; k--) {
+    int gl = l0 + k, s = s0 + 1 + k; const int* li = sc.link_i + DG_LINK_I_W * gl;
+    int ps = parent_slot(li, l0, s0);
+    float* X = ABA(s); float* L = LNK(gl); float* cx = LNX(gl);
+    float Aa[9], Ba[9], Ca[9], pa[6], n[3], fo[3];
+    m_cpy(Aa, X + 6); m_cpy(Ba, X + 15); m_cpy(Ca, X + 24);
+    if (li[3] >= 0) {
+      const float* lx = sc.link_x + 16 * gl; const float *sa = lx + 9, *sl = lx + 12;
+      float U[6];
+      ia_mul(Aa, Ba, Ca, sa, sl, U, U + 3);
+      float D = v_dot(sa, U) + v_dot(sl, U + 3);
+      float tau = DOF(D_JTQ, li[3]) + DOF(D_TDAMP, li[3]);
+      float uu = tau - (v_dot(sa, X) + v_dot(sl, X + 3));
+      for (int i = 0; i < 6; i++) L[12 + i] = U[i];
+      L[18] = D; cx[6] = uu;
+      float Dinv = 1.0f / D;
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+        Aa[3 * i + j] -= U[i] * U[j] * Dinv; Ba[3 * i + j] -= U[i] * U[3 + j] * Dinv; Ca[3 * i + j] -= U[3 + i] * U[3 + j] * Dinv;
+      }
+      ia_mul(Aa, Ba, Ca, cx, cx + 3, n, fo);
+      for (int i = 0; i < 3; i++) { pa[i] = X[i] + n[i] + U[i] * uu * Dinv; pa[3 + i] = X[3 + i] + fo[i] + U[3 + i] * uu * Dinv; }
+    } else {
+      ia_mul(Aa, Ba, Ca, cx, cx + 3, n, fo);
+      for (int i = 0; i < 3; i++) { pa[i] = X[i] + n[i]; pa[3 + i] = X[3 + i] + fo[i]; }
+    }
+    // transform to the parent: rotate the blocks by E^T (.) E, then shift by r
+    const float* E = L; const float* r = L + 9;
+    float T1[9], Ar[9], Br[9], Cr[9];
+    mT_mul(T1, E, Aa); m_mul(Ar, T1, E); mT_mul(T1, E, Ba); m_mul(Br, T1, E); mT_mul(T1, E, Ca); m_mul(Cr, T1, E);
+    float Kx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+    float KC[9], BK[9], KBt[9], KCK[9];
+    m_mul(KC, Kx, Cr); m_mul(BK, Br, Kx); m_mulT(KBt, Kx, Br); m_mul(KCK, KC, Kx);
+    float* P = ABA(ps);
+    for (int i = 0; i < 9; i++) { P[6 + i] += Ar[i] - BK[i] + KBt[i] - KCK[i]; P[15 + i] += Br[i] + KC[i]; P[24 + i] += Cr[i]; }
+    float fp[3], np_[3], t[3];
+    mT_vec(fp, E, pa + 3); mT_vec(np_, E, pa); v_cross(t, r, fp); v_add(np_, np_, t);
+    v_add(P, P, np_); v_add(P + 3, P + 3, fp);
+  }
+  // base acceleration
+  float* X0 = ABA(s0); float* a0 = X0 + 33;
+  if (kind == 2) {
+    float* M = C.ws + sc.X_I0T + bp[BP_I0OFF]; float* Iv = C.ws + sc.W_I0 + bp[BP_I0OFF];
+    const float *A = X0 + 6, *B = X0 + 15, *Cm = X0 + 24;
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { M[6 * i + j] = A[3 * i + j]; M[6 * i + 3 + j] = B[3 * i + j]; M[6 * (3 + i) + j] = B[3 * j + i]; M[6 * (3 + i) + 3 + j] = Cm[3 * i + j]; }
+    invert_small(M, 6, Iv);
+    for (int i = 0; i < 6; i++) { float s = 0.f; for (int j = 0; j < 6; j++) s -= Iv[6 * i + j] * X0[j]; a0[i] = s; }
+  } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
+  // pass 3: accelerations, root to leaves
+  for (int k = 0; k < nlb; k++) {
+    int gl = l0 + k, s = s0 + 1 + k; const int* li = sc.link_i + DG_LINK_I_W * gl;
+    const float* L = LNK(gl); const float* cx = LNX(gl); const float* ap = ABA(parent_slot(li, l0, s0)) + 33;
+    float* a = ABA(s) + 33; float t[3], t2[3], aa[3], al[3];
+    m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
+    v_add(aa, aa, cx); v_add(al, al, cx + 3);
+    if (li[3] >= 0) {
+      const float* lx = sc.link_x + 16 * gl;
+      float qdd = (cx[6] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
+      DOF(D_QDD, li[3]) = qdd;
+      v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
+    }
+    v_cpy(a, aa); v_cpy(a + 3, al);
+  }
+  // velocity update
+  if (kind == 2) {
+    const float* K0 = KIN(s0); float* bs = BST(di); float t[3], lin[3], aw[3];
+    v_cross(t, K0 + 12, K0 + 15); v_add(lin, a0 + 3, t);
+    m_vec(aw, K0, a0); v_madd(bs + 10, aw, h);
+    m_vec(aw, K0, lin); v_madd(bs + 7, aw, h);
+  }
+  for (int i = 0; i < bi[4]; i++) DOF(D_QD, bi[3] + i) += h * DOF(D_QDD, bi[3] + i);
+}
+
+DG_FN void phase_dynamics(const Env& C, int ln, int nt, float h) {
+  for (int di = ln; di < SC.ndyn; di += nt) { int b = SC.dyn_body[di]; fk_vel_body(C, b); aba_body(C, b, h); }
+}
+
+// One column of M^-1 of body b: response of the generalized velocity to a unit generalized impulse at coordinate col.
+// Coordinates: floating bodies [torque_world(3), force_world(3), joints...], fixed-base bodies [joints...].
+DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
+  const DevScene& sc = SC;
+  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  int kind = bi[0], l0 = bi[1], nlb = bi[2], d0 = bi[3], s0 = bp[BP_SLOT], g = bp[BP_GDIM];
+  int jo = kind == 2 ? 6 : 0;
+  float* out = C.ws + sc.W_MINV + bp[BP_MINVOFF] + col * g;
+  float* uu = scr; float* ast = scr + sc.max_nlb;   // a-stack indexed by depth+1 (0 = base)
+  for (int k = 0; k < nlb; k++) uu[k] = 0.f;
+  float p[6] = {0, 0, 0, 0, 0, 0};
+  if (col >= jo) {
+    int k0 = -1;
+    for (int k = 0; k < nlb; k++) if (sc.link_i[DG_LINK_I_W * (l0 + k) + 3] == d0 + col - jo) { k0 = k; break; }
+    for (int k = k0; k >= 0;) {
+      int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* L = LNK(gl);
+      float pa[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
+      if (li[3] >= 0) {
+        const float* lx = sc.link_x + 16 * gl;
+        float u1 = (k == k0 ? 1.f : 0.f) - (v_dot(lx + 9, pa) + v_dot(lx + 12, pa + 3));
+        uu[k] = u1; float s = u1 / L[18];
+        for (int i = 0; i < 6; i++) pa[i] += L[12 + i] * s;
+      }
+      float fp[3], np_[3], t[3];
+      mT_vec(fp, L, pa + 3); mT_vec(np_, L, pa); v_cross(t, L + 9, fp); v_add(np_, np_, t);
+      v_cpy(p, np_); v_cpy(p + 3, fp);
+      k = li[1] < 0 ? -1 : li[1] - l0;
+    }
+  }
+  float* a0 = ast;
+  if (kind == 2) {
+    const float* K0 = KIN(s0); const float* Iv = C.ws + sc.W_I0 + bp[BP_I0OFF];
+    float gen[6] = {0, 0, 0, 0, 0, 0}, rhs[6], t[3];
+    if (col < 6) gen[col] = 1.f;
+    mT_vec(t, K0, gen); v_sub(rhs, t, p); mT_vec(t, K0, gen + 3); v_sub(rhs + 3, t, p + 3);
+    for (int i = 0; i < 6; i++) { float s = 0.f; for (int j = 0; j < 6; j++) s += Iv[6 * i + j] * rhs[j]; a0[i] = s; }
+    m_vec(out, K0, a0); m_vec(out + 3, K0, a0 + 3);
+  } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
+  for (int k = 0; k < nlb; k++) {
+    int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* L = LNK(gl);
+    int dep = sc.link_depth[gl];
+    const float* ap = ast + 6 * dep; float* ak = ast + 6 * (dep + 1);
+    float t[3], t2[3], aa[3], al[3];
+    m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
+    if (li[3] >= 0) {
+      const float* lx = sc.link_x + 16 * gl;
+      float qdd = (uu[k] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
+      out[jo + li[3] - d0] = qdd;
+      v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
+    }
+    v_cpy(ak, aa); v_cpy(ak + 3, al);
+  }
+}
+DG_FN void phase_minv(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  float* scr = C.ws + sc.X_MSCR + sc.mscr_stride * ln;
+  int item = 0;
+  for (int di = 0; di < sc.ndyn; di++) {
+    int b = sc.dyn_body[di], g = sc.body_plan[BP_W * b + BP_GDIM];
+    for (int col = 0; col < g; col++, item++) if (item % nt == ln) minv_column(C, b, col, scr);
+  }
+}
+
+// ------------------------------------------------------------------ collision ----------------------------------
+struct Ct { int fa, fb; float pa[3], pb[3], n[3], dist, mu; };
+
+DG_FN void shape_pose(const Env& C, int s, const float** R, const float** p) {
+  int sl = SC.shape_slot[s];
+  const float* w = sl >= 0 ? C.ws + SC.X_SHW + 12 * sl : SC.shape_wb + 12 * s;
+  *R = w; *p = w + 9;
+}
+DG_FN void phase_shape_world(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  for (int s = ln; s < sc.ns; s += nt) {
+    int sl = sc.shape_slot[s];
+    if (sl < 0) continue;
+    const float* sf = sc.shape_f + DG_SHAPE_F_W * s; const float* K = KIN(sc.frame_slot[sc.shape_i[DG_SHAPE_I_W * s + 1]]);
+    float* w = C.ws + sc.X_SHW + 12 * sl; float Rl[9], R[9], t[3];
+    q_to_mat(Rl, sf + 3); m_mul(R, K, Rl); m_cpy(w, R); m_vec(t, K, sf); v_add(w + 9, K + 9, t);
+  }
+  int nw = (sc.npair + 31) / 32;
+  for (int i = ln; i < nw; i += nt) WSI(C)[sc.X_SURV + i] = 0;
+  if (ln == 0) { WSI(C)[sc.W_HDR + WH_NCONTACT] = 0; }
+}
+DG_HD void ct_add(Ct* list, int* n, int cap, int fa, int fb, const float* pa, const float* pb, const float* nrm, float dist, float mu, float margin) {
+  if (dist > margin || *n >= cap) return;
+  Ct* c = &list[(*n)++]; c->fa = fa; c->fb = fb; v_cpy(c->pa, pa); v_cpy(c->pb, pb); v_cpy(c->n, nrm); c->dist = dist; c->mu = mu;
+}
+DG_FN int sphere_box(const float* c, float r, const float* Rb, const float* pb, const float* h, float* pa_out, float* pb_out, float* n, float* dist) {
+  float d[3], cl[3], q[3]; v_sub(d, c, pb); mT_vec(cl, Rb, d);
+  int inside = 1;
+  for (int i = 0; i < 3; i++) { q[i] = cl[i]; if (q[i] > h[i]) { q[i] = h[i]; inside = 0; } else if (q[i] < -h[i]) { q[i] = -h[i]; inside = 0; } }
+  float nl[3] = {0, 0, 0};
+  if (!inside) {
+    float dv[3]; v_sub(dv, cl, q); float len = v_len(dv);
+    if (len < 1e-12f) return 0;
+    v_scale(nl, dv, 1.0f / len); *dist = len - r;
+  } else {
+    int ax = 0; float best = 1e30f;
+    for (int i = 0; i < 3; i++) { float pen = h[i] - fabsf(cl[i]); if (pen < best) { best = pen; ax = i; } }
+    float sg = cl[ax] >= 0 ? 1.0f : -1.0f;
+    for (int i = 0; i < 3; i++) if (i == ax) { nl[i] = sg; q[i] = sg * h[i]; }
+    *dist = -best - r;
+  }
+  m_vec(n, Rb, nl); float t[3]; m_vec(t, Rb, q); v_add(pb_out, pb, t);
+  v_scale(t, n, -r); v_add(pa_out, c, t);
+  return 1;
+}
+DG_FN int point_box(const float* p, const float* Rb, const float* pb, const float* h, float margin, float* pb_out, float* n, float* dist) {
+  float d[3], pl[3]; v_sub(d, p, pb); mT_vec(pl, Rb, d);
+  int ax = 0; float best = 1e30f;
+  for (int i = 0; i < 3; i++) { float pen = h[i] - fabsf(pl[i]); if (pen < -margin) return 0; if (pen < best) { best = pen; ax = i; } }
+  float nl[3] = {0, 0, 0}, q[3] = {pl[0], pl[1], pl[2]};
+  float sg = pl[ax] >= 0 ? 1.0f : -1.0f;
+  for (int i = 0; i < 3; i++) if (i == ax) { nl[i] = sg; q[i] = sg * h[i]; }
+  m_vec(n, Rb, nl); float t[3]; m_vec(t, Rb, q); v_add(pb_out, pb, t); *dist = -best;
+  return 1;
+}
+DG_FN void seg_closest(const float* p1, const float* d1, const float* p2, const float* d2, float* s, float* t) {
+  float r[3]; v_sub(r, p1, p2);
+  float a = v_dot(d1, d1), e = v_dot(d2, d2), f = v_dot(d2, r);
+  if (a <= 1e-18f && e <= 1e-18f) { *s = *t = 0; return; }
+  if (a <= 1e-18f) { *s = 0; *t = clampf(f / e, 0.f, 1.f); return; }
+  float c = v_dot(d1, r);
+  if (e <= 1e-18f) { *t = 0; *s = clampf(-c / a, 0.f, 1.f); return; }
+  float b = v_dot(d1, d2), den = a * e - b * b;
+  *s = den > 1e-18f ? clampf((b * f - c * e) / den, 0.f, 1.f) : 0.0f;
+  *t = (b * (*s) + f) / e;
+  if (*t < 0) { *t = 0; *s = clampf(-c / a, 0.f, 1.f); } else if (*t > 1) { *t = 1; *s = clampf((b - c) / a, 0.f, 1.f); }
+}
+DG_FN void as_capsule(int type, const float* dims, const float* R, const float* p, float* e0, float* e1, float* rad) {
+  float half = 0; *rad = dims[0];
+  if (type == SHAPE_CAPSULE) half = dims[1];
+  else if (type == SHAPE_CYLINDER) half = dims[1] - dims[0] > 0 ? dims[1] - dims[0] : 0;
+  float ax[3] = {R[2] * half, R[5] * half, R[8] * half};
+  v_sub(e0, p, ax); v_add(e1, p, ax);
+}
+DG_HD bool pair_in_reach(const Env& C, int sa, int sb) {
+  const float *Ra, *pa, *Rb, *pb;
+  shape_pose(C, sa, &Ra, &pa); shape_pose(C, sb, &Rb, &pb);
+  float dc[3]; v_sub(dc, pa, pb);
+  float reach = SC.shape_f[DG_SHAPE_F_W * sa + 11] + SC.shape_f[DG_SHAPE_F_W * sb + 11] + SC.margin;
+  return v_dot(dc, dc) <= reach * reach;
+}
+// narrow phase of one shape pair; writes at most 4 contacts into out, returns the count
+DG_FN int collide_pair(const Env& C, int sa, int sb, Ct* out) {
+  const DevScene& sc = SC;
+  const int *ia = sc.shape_i + DG_SHAPE_I_W * sa, *ib = sc.shape_i + DG_SHAPE_I_W * sb;
+  const float *fa = sc.shape_f + DG_SHAPE_F_W * sa, *fb = sc.shape_f + DG_SHAPE_F_W * sb;
+  const float *Ra, *pa, *Rb, *pb;
+  shape_pose(C, sa, &Ra, &pa); shape_pose(C, sb, &Rb, &pb);
+  float margin = sc.margin;
+  int ta = ia[2], tb = ib[2];
+  float mu = PR(P_FRICTION)[sa] * PR(P_FRICTION)[sb];
+  int nt_ = 0;
+  float ca[3], cb[3], n[3], dist;
+  if (ta != SHAPE_BOX && tb != SHAPE_BOX) {
+    float a0[3], a1[3], b0[3], b1[3], ra, rb, d1[3], d2[3], s, t, c1[3], c2[3];
+    as_capsule(ta, fa + 7, Ra, pa, a0, a1, &ra); as_capsule(tb, fb + 7, Rb, pb, b0, b1, &rb);
+    v_sub(d1, a1, a0); v_sub(d2, b1, b0); seg_closest(a0, d1, b0, d2, &s, &t);
+    v_cpy(c1, a0); v_madd(c1, d1, s); v_cpy(c2, b0); v_madd(c2, d2, t);
+    float d[3]; v_sub(d, c1, c2); float len = v_len(d);
+    if (len < 1e-12f) v_set(n, 0, 0, 1); else v_scale(n, d, 1.0f / len);
+    dist = len - ra - rb; float tt[3]; v_scale(tt, n, -ra); v_add(ca, c1, tt); v_scale(tt, n, rb); v_add(cb, c2, tt);
+    ct_add(out, &nt_, 4, ia[1], ib[1], ca, cb, n, dist, mu, margin);
+    return nt_;
+  }
+  // at least one box: B is the reference box, X the other shape (flip at the end if we swapped)
+  int swap = (tb != SHAPE_BOX);
+  const float *Rx = swap ? Rb : Ra, *px = swap ? pb : pa, *dx = swap ? fb + 7 : fa + 7;
+  const float *Rbx = swap ? Ra : Rb, *pbx = swap ? pa : pb, *hb = swap ? fa + 7 : fb + 7;
+  int tx = swap ? tb : ta; int fx = swap ? ib[1] : ia[1], fbx = swap ? ia[1] : ib[1];
+  Ct loc[16]; int nloc = 0;
+  if (tx == SHAPE_SPHERE) {
+    if (sphere_box(px, dx[0], Rbx, pbx, hb, ca, cb, n, &dist)) ct_add(loc, &nloc, 16, fx, fbx, ca, cb, n, dist, mu, margin);
+  } else if (tx == SHAPE_CAPSULE) {
+    float e0[3], e1[3], rad, mid[3], dseg[3], rel[3];
+    as_capsule(tx, dx, Rx, px, e0, e1, &rad);
+    v_sub(dseg, e1, e0); v_sub(rel, pbx, e0);
+    float dd = v_dot(dseg, dseg), tt = dd > 1e-18f ? clampf(v_dot(rel, dseg) / dd, 0.f, 1.f) : 0.0f;
+    v_cpy(mid, e0); v_madd(mid, dseg, tt);
+    if (sphere_box(e0, rad, Rbx, pbx, hb, ca, cb, n, &dist)) ct_add(loc, &nloc, 16, fx, fbx, ca, cb, n, dist, mu, margin);
+    if (dd > 1e-18f && sphere_box(e1, rad, Rbx, pbx, hb, ca, cb, n, &dist)) ct_add(loc, &nloc, 16, fx, fbx, ca, cb, n, dist, mu, margin);
+    if (tt > 1e-6f && tt < 1 - 1e-6f && sphere_box(mid, rad, Rbx, pbx, hb, ca, cb, n, &dist)) ct_add(loc, &nloc, 16, fx, fbx, ca, cb, n, dist, mu, margin);
+  } else if (tx == SHAPE_CYLINDER) {
+    float zc[3] = {Rx[2], Rx[5], Rx[8]}, xc[3] = {Rx[0], Rx[3], Rx[6]}, yc[3] = {Rx[1], Rx[4], Rx[7]};
+    for (int cap = -1; cap <= 1; cap += 2) {
+      float cc[3]; v_cpy(cc, px); v_madd(cc, zc, cap * dx[1]);
+      for (int k = 0; k < 6; k++) {
+        float sg = k < 3 ? 1.f : -1.f; int a3 = k % 3;
+        float nk[3] = {-Rbx[a3] * sg, -Rbx[3 + a3] * sg, -Rbx[6 + a3] * sg};
+        float t[3]; v_cpy(t, nk); v_madd(t, zc, -v_dot(nk, zc));
+        float len = v_len(t), pt[3];
+        int npt = len < 1e-6f ? 4 : 1;   // cap parallel to this face: four rim points instead
+        for (int j4 = 0; j4 < npt; j4++) {
+          if (npt == 4) { const float* bx = (j4 & 1) ? yc : xc; float s2 = (j4 & 2) ? -1.0f : 1.0f; v_cpy(pt, cc); v_madd(pt, bx, s2 * dx[0]); }
+          else { v_cpy(pt, cc); v_madd(pt, t, dx[0] / len); }
+          if (point_box(pt, Rbx, pbx, hb, margin, cb, n, &dist)) {
+            int dup = 0;
+            for (int j = 0; j < nloc; j++) { float dd[3]; v_sub(dd, loc[j].pa, pt); if (v_dot(dd, dd) < 1e-12f) dup = 1; }
+            if (!dup) ct_add(loc, &nloc, 16, fx, fbx, pt, cb, n, dist, mu, margin);
+          }
+        }
+      }
+    }
+  } else {   // box X against box B: corners of X in B, then corners of B in X
+    for (int k = 0; k < 8; k++) {
+      float cl[3] = {(k & 1 ? 1 : -1) * dx[0], (k & 2 ? 1 : -1) * dx[1], (k & 4 ? 1 : -1) * dx[2]}, pt[3], t[3];
+      m_vec(t, Rx, cl); v_add(pt, px, t);
+      if (point_box(pt, Rbx, pbx, hb, margin, cb, n, &dist)) ct_add(loc, &nloc, 16, fx, fbx, pt, cb, n, dist, mu, margin);
+    }
+    for (int k = 0; k < 8; k++) {
+      float cl[3] = {(k & 1 ? 1 : -1) * hb[0], (k & 2 ? 1 : -1) * hb[1], (k & 4 ? 1 : -1) * hb[2]}, pt[3], t[3], nn[3], cx[3];
+      m_vec(t, Rbx, cl); v_add(pt, pbx, t);
+      if (point_box(pt, Rx, px, dx, margin, cx, nn, &dist)) { v_scale(nn, nn, -1.0f); ct_add(loc, &nloc, 16, fx, fbx, cx, pt, nn, dist, mu, margin); }
+    }
+  }
+  // keep the 4 deepest (stable selection, same order as a stable sort by depth)
+  for (int i = 0; i < nloc; i++) for (int j = i + 1; j < nloc; j++) if (loc[j].dist < loc[i].dist) { Ct t = loc[i]; loc[i] = loc[j]; loc[j] = t; }
+  if (nloc > 4) nloc = 4;
+  for (int i = 0; i < nloc; i++) {
+    Ct c = loc[i];
+    if (swap) { Ct s2 = c; s2.fa = c.fb; s2.fb = c.fa; v_cpy(s2.pa, c.pb); v_cpy(s2.pb, c.pa); v_scale(s2.n, c.n, -1.0f); c = s2; }
+    out[nt_++] = c;
+  }
+  return nt_;
+}
+DG_HD void surv_set(int* word, int bit) {
+#if defined(__CUDA_ARCH__)
+  atomicOr(word, 1 << bit);
+#else
+  *word |= 1 << bit;
+#endif
+}
+DG_HD int popc32(unsigned x) {
+#if defined(__CUDA_ARCH__)
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
+#endif
+}
+// broad phase: bounding-sphere test of every candidate pair, survivors marked in a bit set
+DG_FN void phase_broad(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  for (int k = ln; k < sc.npair; k += nt)
+    if (pair_in_reach(C, sc.pair_i[2 * k], sc.pair_i[2 * k + 1])) surv_set(WSI(C) + sc.X_SURV + (k >> 5), k & 31);
+}
+DG_FN void phase_count_survivors(const Env& C, int ln, int nt) {
+  if (ln != 0) return;
+  int nw = (SC.npair + 31) / 32, n = 0;
+  for (int i = 0; i < nw; i++) n += popc32((unsigned)WSI(C)[SC.X_SURV + i]);
+  WSI(C)[SC.W_HDR + WH_NSURV] = n;
+}
+// narrow phase, round `rnd`: lane ln takes survivor number rnd*nt + ln (in pair order) and parks its contacts
+DG_FN void phase_narrow(const Env& C, int ln, int nt, int rnd) {
+  const DevScene& sc = SC;
+  float* tmp = C.ws + sc.X_CTMP + sc.ctmp_stride * ln;
+  int want = rnd * nt + ln, nw = (sc.npair + 31) / 32, seen = 0, pair = -1;
+  for (int i = 0; i < nw && pair < 0; i++) {
+    unsigned wd = (unsigned)WSI(C)[sc.X_SURV + i]; int c = popc32(wd);
+    if (seen + c <= want) { seen += c; continue; }
+    for (int bit = 0; bit < 32; bit++) if (wd & (1u << bit)) { if (seen == want) { pair = 32 * i + bit; break; } seen++; }
+  }
+  int n = 0;
+  if (pair >= 0) {
+    Ct out[4];
+    n = collide_pair(C, sc.pair_i[2 * pair], sc.pair_i[2 * pair + 1], out);
+    for (int i = 0; i < n; i++) {
+      float* c = tmp + 1 + CT_W * i;
+      c[CT_FA] = int_as_float(out[i].fa); c[CT_FB] = int_as_float(out[i].fb);
+      v_cpy(c + CT_PA, out[i].pa); v_cpy(c + CT_PB, out[i].pb); v_cpy(c + CT_N, out[i].n); c[CT_DIST] = out[i].dist; c[CT_MU] = out[i].mu;
+    }
+  }
+  tmp[0] = int_as_float(n);
+}
+DG_FN void phase_append(const Env& C, int ln, int nt) {
+  if (ln != 0) return;
+  const DevScene& sc = SC;
+  int nc = WSI(C)[sc.W_HDR + WH_NCONTACT];
+  for (int l = 0; l < nt; l++) {
+    const float* tmp = C.ws + sc.X_CTMP + sc.ctmp_stride * l; int n = float_as_int(tmp[0]);
+    for (int i = 0; i < n && nc < sc.maxc; i++, nc++) { float* dst = C.ws + sc.X_CON + CT_W * nc; const float* src = tmp + 1 + CT_W * i; for (int j = 0; j < CT_W; j++) dst[j] = src[j]; }
+  }
+  WSI(C)[sc.W_HDR + WH_NCONTACT] = nc;
+}
+
+// ------------------------------------------------------------------ constraint rows ----------------------------
+DG_HD int body_of_frame(const DevScene& sc, int f) { return f < sc.nb ? f : sc.link_i[DG_LINK_I_W * (f - sc.nb)]; }
+// generalized force per unit force along dir at world point p on frame f (compact coordinates of its body)
+DG_FN void point_jacobian(const Env& C, int f, const float* p, const float* dir, float* J) {
+  const DevScene& sc = SC;
+  int b = body_of_frame(sc, f); const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  int g = bp[BP_GDIM], d0 = bi[3], s0 = bp[BP_SLOT], l0 = bi[1];
+  for (int i = 0; i < g; i++) J[i] = 0.f;
+  int jo = 0;
+  if (bi[0] == 2) { float rel[3]; v_sub(rel, p, KIN(s0) + 9); v_cross(J, rel, dir); v_cpy(J + 3, dir); jo = 6; }
+  int gl = f < sc.nb ? -1 : f - sc.nb;
+  while (gl >= 0) {
+    const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl; const float* K = KIN(s0 + 1 + gl - l0);
+    if (li[2] == 1) {
+      float aw[3], dw[3], o[3], rel[3], t[3];
+      m_vec(aw, K, lf + 10); m_vec(dw, K, lf + 7); v_sub(o, K + 9, dw);
+      v_sub(rel, p, o); v_cross(t, aw, rel); J[jo + li[3] - d0] = v_dot(dir, t);
+    } else if (li[2] == 2) { float aw[3]; m_vec(aw, K, lf + 10); J[jo + li[3] - d0] = v_dot(dir, aw); }
+    gl = li[1];
+  }
+}
+DG_FN void body_genvel(const Env& C, int b, float* gv) {
+  const int* bi = SC.body_i + DG_BODY_I_W * b; int jo = 0;
+  if (bi[0] == 2) { const float* bs = BST(SC.body_plan[BP_W * b + BP_DI]); v_cpy(gv, bs + 10); v_cpy(gv + 3, bs + 7); jo = 6; }
+  for (int i = 0; i < bi[4]; i++) gv[jo + i] = DOF(D_QD, bi[3] + i);
+}
+// joint-limit rows (only when violated) then motor rows of every dynamic body, lane per body
+DG_FN void phase_unit_rows(const Env& C, int ln, int nt, float h) {
+  const DevScene& sc = SC;
+  for (int di = ln; di < sc.ndyn; di += nt) {
+    int b = sc.dyn_body[di]; const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+    int l0 = bi[1], nlb = bi[2], d0 = bi[3], g = bp[BP_GDIM], jo = bi[0] == 2 ? 6 : 0;
+    const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
+    float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW]; int n = 0;
+    for (int k = 0; k < nlb; k++) {
+      const int* li = sc.link_i + DG_LINK_I_W * (l0 + k); const float* lf = sc.link_f + DG_LINK_F_W * (l0 + k);
+      int d = li[3];
+      if (d < 0 || !li[4]) continue;
+      for (int side = 0; side < 2; side++) {
+        float pen = side == 0 ? DOF(D_Q, d) - lf[20] : lf[21] - DOF(D_Q, d);
+        if (pen > 0) continue;
+        int col = jo + d - d0; float sg = side == 0 ? 1.f : -1.f;
+        float den = Minv[col * g + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, rel = sg * DOF(D_QD, d);
+        float* r = rows + UR_W * n++;
+        r[UR_RHS] = (-rel + (-pen) * sc.erp / h) * dinv; r[UR_DINV] = dinv; r[UR_LO] = 0.f; r[UR_HI] = sc.limit_max_impulse; r[UR_APPLIED] = 0.f;
+        r[UR_COL] = int_as_float(side == 0 ? col : -1 - col); r[UR_MOTOR] = int_as_float(-1);
+      }
+    }
+    for (int k = 0; k < nlb; k++) {
+      int d = sc.link_i[DG_LINK_I_W * (l0 + k) + 3];
+      if (d < 0) continue;
+      float maxf = DOF(D_MAXF, d);
+      DOF(D_APPLIED, d) = 0.f;
+      if (maxf <= 0) continue;
+      int col = jo + d - d0;
+      float den = Minv[col * g + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, qd = DOF(D_QD, d);
+      float desired = DOF(D_KP, d) * (DOF(D_TPOS, d) - DOF(D_Q, d)) / h + qd + DOF(D_KD, d) * (DOF(D_TVEL, d) - qd);
+      float* r = rows + UR_W * n++;
+      r[UR_RHS] = (desired - qd) * dinv; r[UR_DINV] = dinv; r[UR_LO] = -maxf * sc.dt; r[UR_HI] = maxf * sc.dt; r[UR_APPLIED] = 0.f;
+      r[UR_COL] = int_as_float(col); r[UR_MOTOR] = int_as_float(d);
+    }
+    WSI(C)[sc.W_UCNT + di] = n;
+    float* dv = C.ws + sc.W_DV + bp[BP_GVOFF];
+    for (int i = 0; i < g; i++) dv[i] = 0.f;
+  }
+  if (ln == 0) WSI(C)[sc.W_HDR + WH_NCROW] = 3 * WSI(C)[sc.W_HDR + WH_NCONTACT];
+}
+DG_FN void plane_space(const float* n, float* p, float* q) {
+  if (fabsf(n[2]) > 0.7071067811865475244f) { float a = n[1] * n[1] + n[2] * n[2], k = 1.0f / sqrtf(a); p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k; q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1]; }
+  else { float a = n[0] * n[0] + n[1] * n[1], k = 1.0f / sqrtf(a); p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0; q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k; }
+}
+// contact rows: normals [0, nc), then two friction rows per contact; lane per row
+DG_FN void phase_contact_rows(const Env& C, int ln, int nt, float h) {
+  const DevScene& sc = SC;
+  int nc = WSI(C)[sc.W_HDR + WH_NCONTACT];
+  for (int r = ln; r < 3 * nc; r += nt) {
+    int k = r < nc ? r : (r - nc) >> 1, dirk = r < nc ? -1 : (r - nc) & 1;
+    const float* c = C.ws + sc.X_CON + CT_W * k;
+    int fa = float_as_int(c[CT_FA]), fb = float_as_int(c[CT_FB]);
+    float dir[3];
+    if (dirk < 0) v_cpy(dir, c + CT_N); else { float t1[3], t2[3]; plane_space(c + CT_N, t1, t2); v_cpy(dir, dirk == 0 ? t1 : t2); }
+    float* row = C.ws + sc.X_CROW + sc.crow_stride * r; float* J = row + CR_HDR; float* M = J + sc.GP;
+    int ba = body_of_frame(sc, fa), bb = body_of_frame(sc, fb);
+    int dia = sc.body_plan[BP_W * ba + BP_DI], dib = sc.body_plan[BP_W * bb + BP_DI];
+    float den = 0.f, rel = 0.f; int ga = 0;
+    if (dia >= 0) {
+      const int* bp = sc.body_plan + BP_W * ba; ga = bp[BP_GDIM]; const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
+      point_jacobian(C, fa, c + CT_PA, dir, J);
+      body_genvel(C, ba, M);   // M doubles as scratch for the generalized velocity
+      for (int i = 0; i < ga; i++) rel += J[i] * M[i];
+      for (int i = 0; i < ga; i++) { float s = 0.f; for (int j = 0; j < ga; j++) s += Minv[j * ga + i] * J[j]; M[i] = s; }
+      for (int i = 0; i < ga; i++) den += J[i] * M[i];
+    }
+    if (dib >= 0) {
+      const int* bp = sc.body_plan + BP_W * bb; int gb = bp[BP_GDIM]; const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
+      float nd_[3]; v_scale(nd_, dir, -1.0f);
+      float *JB = J + ga, *MB = M + ga;
+      point_jacobian(C, fb, c + CT_PB, nd_, JB);
+      body_genvel(C, bb, MB);
+      for (int i = 0; i < gb; i++) rel += JB[i] * MB[i];
+      for (int i = 0; i < gb; i++) { float s = 0.f; for (int j = 0; j < gb; j++) s += Minv[j * gb + i] * JB[j]; MB[i] = s; }
+      for (int i = 0; i < gb; i++) den += JB[i] * MB[i];
+    }
+    float dinv = den > 1e-30f ? 1.0f / den : 0.f;
+    row[CR_DINV] = dinv; row[CR_APPLIED] = 0.f; row[CR_MU] = c[CT_MU];
+    row[CR_DA] = int_as_float(dia); row[CR_DB] = int_as_float(dib);
+    if (dirk < 0) {
+      float pen = c[CT_DIST] + sc.slop, pos_err = 0.f, vel_err = -rel;
+      if (pen > 0) vel_err -= pen / h; else pos_err = -pen * sc.cerp / h;
+      row[CR_RHS] = (pos_err + vel_err) * dinv; row[CR_LO] = 0.f; row[CR_HI] = 1e10f; row[CR_PARENT] = int_as_float(-1);
+    } else {
+      row[CR_RHS] = -rel * dinv; row[CR_LO] = 0.f; row[CR_HI] = 0.f; row[CR_PARENT] = int_as_float(k);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ projected Gauss-Seidel ---------------------
+DG_FN void pgs_unit_sweep(const Env& C, int b, int di, int it) {
+  const DevScene& sc = SC;
+  const int* bp = sc.body_plan + BP_W * b; int g = bp[BP_GDIM], n = WSI(C)[sc.W_UCNT + di];
+  const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF]; float* dv = C.ws + sc.W_DV + bp[BP_GVOFF];
+  float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW];
+  for (int j = 0; j < n; j++) {
+    float* r = rows + UR_W * ((it & 1) ? j : n - 1 - j);
+    int colc = float_as_int(r[UR_COL]); float sg = 1.f; int col = colc;
+    if (colc < 0) { col = -1 - colc; sg = -1.f; }
+    float d = r[UR_RHS] - sg * dv[col] * r[UR_DINV];
+    float ap = r[UR_APPLIED], sum = ap + d, lo = r[UR_LO], hi = r[UR_HI];
+    if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
+    r[UR_APPLIED] = sum;
+    float sd = sg * d; const float* Mc = Minv + col * g;
+    for (int i = 0; i < g; i++) dv[i] = fmaf(Mc[i], sd, dv[i]);
+  }
+}
+DG_FN void pgs_contact_sweep(const Env& C) {
+  const DevScene& sc = SC;
+  int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
+  for (int r = 0; r < ncr; r++) {
+    float* row = C.ws + sc.X_CROW + sc.crow_stride * r; const float* J = row + CR_HDR; const float* M = J + sc.GP;
+    int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
+    float dot = 0.f; int ga = 0; float *dva = nullptr, *dvb = nullptr; int gb = 0;
+    if (dia >= 0) { const int* bp = sc.body_plan + BP_W * sc.dyn_body[dia]; ga = bp[BP_GDIM]; dva = C.ws + sc.W_DV + bp[BP_GVOFF]; for (int i = 0; i < ga; i++) dot += J[i] * dva[i]; }
+    if (dib >= 0) { const int* bp = sc.body_plan + BP_W * sc.dyn_body[dib]; gb = bp[BP_GDIM]; dvb = C.ws + sc.W_DV + bp[BP_GVOFF]; for (int i = 0; i < gb; i++) dot += J[ga + i] * dvb[i]; }
+    float d = row[CR_RHS] - dot * row[CR_DINV];
+    float lo = row[CR_LO], hi = row[CR_HI];
+    int par = float_as_int(row[CR_PARENT]);
+    if (par >= 0) { hi = row[CR_MU] * (C.ws + sc.X_CROW + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
+    float ap = row[CR_APPLIED], sum = ap + d;
+    if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
+    row[CR_APPLIED] = sum;
+    for (int i = 0; i < ga; i++) dva[i] = fmaf(M[i], d, dva[i]);
+    for (int i = 0; i < gb; i++) dvb[i] = fmaf(M[ga + i], d, dvb[i]);
+  }
+}
+DG_FN void phase_pgs_unit(const Env& C, int ln, int nt, int it0, int it1) {
+  for (int di = ln; di < SC.ndyn; di += nt) for (int it = it0; it < it1; it++) pgs_unit_sweep(C, SC.dyn_body[di], di, it);
+}
+DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_contact_sweep(C); }
+
+// ------------------------------------------------------------------ integration --------------------------------
+DG_FN void integrate_base_quat(float* q, const float* om, float h) {
+  float ang = v_len(om), ax[3];
+  if (ang * h > 0.25f * kPi) ang = 0.25f * kPi / h;
+  if (ang < 0.001f) v_scale(ax, om, 0.5f * h - h * h * h * 0.020833333333f * ang * ang); else v_scale(ax, om, sinf(0.5f * ang * h) / ang);
+  float dq[4] = {ax[0], ax[1], ax[2], cosf(0.5f * ang * h)}, out[4];
+  q_mul(out, dq, q); q_norm(out); q[0] = out[0]; q[1] = out[1]; q[2] = out[2]; q[3] = out[3];
+}
+DG_FN void phase_integrate(const Env& C, int ln, int nt, float h) {
+  const DevScene& sc = SC;
+  for (int di = ln; di < sc.ndyn; di += nt) {
+    int b = sc.dyn_body[di]; const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+    const float* dv = C.ws + sc.W_DV + bp[BP_GVOFF]; int jo = 0;
+    // record the motor impulses of this sub-step
+    int n = WSI(C)[sc.W_UCNT + di]; const float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW];
+    for (int j = 0; j < n; j++) { int md = float_as_int(rows[UR_W * j + UR_MOTOR]); if (md >= 0) DOF(D_APPLIED, md) = rows[UR_W * j + UR_APPLIED]; }
+    if (bi[0] == 2) {
+      float* bs = BST(di);
+      for (int i = 0; i < 3; i++) { bs[10 + i] += dv[i]; bs[7 + i] += dv[3 + i]; }
+      for (int i = 0; i < 3; i++) bs[i] += h * bs[7 + i];
+      integrate_base_quat(bs + 3, bs + 10, h);
+      jo = 6;
+    }
+    for (int i = 0; i < bi[4]; i++) {
+      int d = bi[3] + i; float qd = DOF(D_QD, d) + dv[jo + i];
+      qd = clampf(qd, -sc.max_joint_vel, sc.max_joint_vel);
+      DOF(D_QD, d) = qd; DOF(D_Q, d) += h * qd;
+    }
+  }
+}
+DG_FN void phase_final_kin(const Env& C, int ln, int nt) {
+  for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body(C, SC.dyn_body[di]);
+}
+// write the dynamic state back, refresh the link pose / velocity cache the sensors read, clear applied wrenches
+DG_FN void phase_store(const Env& C, int ln, int nt, int clear_forces) {
+  const DevScene& sc = SC;
+  for (int i = ln; i < 13 * sc.ndyn; i += nt) {
+    int di = i / 13, k = i - 13 * di, b = sc.dyn_body[di]; float v = BST(di)[k];
+    if (k < 3) ST(S_BPOS)[3 * b + k] = v;
+    else if (k < 7) ST(S_BQUAT)[4 * b + k - 3] = v;
+    else if (k < 10) ST(S_BVEL)[3 * b + k - 7] = v;
+    else ST(S_BOMEGA)[3 * b + k - 10] = v;
+  }
+  for (int d = ln; d < sc.nd; d += nt) {
+    ST(S_Q)[d] = DOF(D_Q, d); ST(S_QD)[d] = DOF(D_QD, d); ST(S_MAPPLIED)[d] = DOF(D_APPLIED, d);
+    if (clear_forces) ST(S_JTORQUE)[d] = 0.f;
+  }
+  for (int gl = ln; gl < sc.nl; gl += nt) {
+    int s = sc.frame_slot[sc.nb + gl];
+    if (s < 0) continue;
+    const float* K = KIN(s); float q[4], t[3];
+    v_cpy(ST(S_LPOS) + 3 * gl, K + 9);
+    mat_to_q(q, K); for (int i = 0; i < 4; i++) ST(S_LQUAT)[4 * gl + i] = q[i];
+    m_vec(t, K, K + 15); v_cpy(ST(S_LVEL) + 3 * gl, t);
+    m_vec(t, K, K + 12); v_cpy(ST(S_LOMEGA) + 3 * gl, t);
+  }
+  if (clear_forces) for (int f = ln; f < sc.nframes; f += nt) {
+    if (sc.frame_slot[f] < 0) continue;
+    for (int i = 0; i < 3; i++) { ST(S_EXTF)[3 * f + i] = 0.f; ST(S_EXTT)[3 * f + i] = 0.f; }
+  }
+}
+
+// ------------------------------------------------------------------ frame queries on the state row -------------
+// COM-frame pose and velocity as cached after the last step (what the reference reads through
+// getBasePositionAndOrientation / getLinkState[0,1,6,7], e.g. object_state_sensor.py:33-48)
+DG_FN void frame_com_state(const Env& C, int f, float* pos, float* quat, float* vel, float* om) {
+  const DevScene& sc = SC;
+  if (f < sc.nb) { v_cpy(pos, ST(S_BPOS) + 3 * f); for (int i = 0; i < 4; i++) quat[i] = ST(S_BQUAT)[4 * f + i]; v_cpy(vel, ST(S_BVEL) + 3 * f); v_cpy(om, ST(S_BOMEGA) + 3 * f); }
+  else { int gl = f - sc.nb; v_cpy(pos, ST(S_LPOS) + 3 * gl); for (int i = 0; i < 4; i++) quat[i] = ST(S_LQUAT)[4 * gl + i]; v_cpy(vel, ST(S_LVEL) + 3 * gl); v_cpy(om, ST(S_LOMEGA) + 3 * gl); }
+}
+// URDF link-frame pose (getLinkState[4,5]; reach_target.py:21-30, camera.py:60)
+DG_FN void frame_link_pose(const Env& C, int f, float* pos, float* quat) {
+  float v[3], o[3];
+  frame_com_state(C, f, pos, quat, v, o);
+  if (f >= SC.nb) {
+    const float* lf = SC.link_f + DG_LINK_F_W * (f - SC.nb);
+    float R[9], t[3], qi[4] = {-lf[16], -lf[17], -lf[18], lf[19]}, qo[4];
+    q_to_mat(R, quat); m_vec(t, R, lf + 7); v_sub(pos, pos, t);
+    q_mul(qo, quat, qi); for (int i = 0; i < 4; i++) quat[i] = qo[i];
+  }
+}
+
+// ------------------------------------------------------------------ inverse kinematics -------------------------
+// In-place Gaussian elimination with partial pivoting on workspace arrays
+DG_FN int solve_dense(float* A, float* bvec, int n) {
+  for (int c = 0; c < n; c++) {
+    int p = c;
+    for (int r2 = c + 1; r2 < n; r2++) if (fabsf(A[r2 * n + c]) > fabsf(A[p * n + c])) p = r2;
+    if (fabsf(A[p * n + c]) < 1e-30f) return -1;
+    if (p != c) { for (int j = 0; j < n; j++) { float t = A[c * n + j]; A[c * n + j] = A[p * n + j]; A[p * n + j] = t; } float t = bvec[c]; bvec[c] = bvec[p]; bvec[p] = t; }
+    for (int r2 = c + 1; r2 < n; r2++) { float f = A[r2 * n + c] / A[c * n + c]; if (f != 0.f) { for (int j = c; j < n; j++) A[r2 * n + j] -= f * A[c * n + j]; bvec[r2] -= f * bvec[c]; } }
+  }
+  for (int r2 = n - 1; r2 >= 0; r2--) { float s = bvec[r2]; for (int j = r2 + 1; j < n; j++) s -= A[r2 * n + j] * bvec[j]; bvec[r2] = s / A[r2 * n + r2]; }
+  return 0;
+}
+// Damped least squares on the end-effector link frame in base coordinates over all DoF of body b
+// (what ik_controller.py:61-69 asks of calculateInverseKinematics); result in scr[0 .. nd_b)
+DG_FN void ik_solve(const Env& C, int b, int ee_gl, const float* tpos_w, const float* torn_w, int use_orn, int nullspace,
+                    const float* lower, const float* upper, const float* range, const float* rest, float* scr) {
+  const DevScene& sc = SC;
+  const int* bi = sc.body_i + DG_BODY_I_W * b; int d0 = bi[3], ndb = bi[4];
+  int mc = sc.max_depth + 2;
+  float* qb = scr; float* nullv = qb + ndb; float* dth = nullv + ndb; float* J = dth + ndb;     // J: 6 x ndb
+  float* A = J + 6 * ndb; int asz = ndb * ndb > 36 ? ndb * ndb : 36;
+  float* rhs = A + asz; float* axw = rhs + (ndb > 6 ? ndb : 6); float* orgw = axw + 3 * mc;
+  int* chain = (int*)(orgw + 3 * mc);
+  for (int i = 0; i < ndb; i++) qb[i] = ST(S_Q)[d0 + i];
+  const float *bp = ST(S_BPOS) + 3 * b, *bq = ST(S_BQUAT) + 4 * b;
+  float Rb[9], tp[3], d[3], tq[4] = {0, 0, 0, 1};
+  q_to_mat(Rb, bq); v_sub(d, tpos_w, bp); mT_vec(tp, Rb, d);
+  if (use_orn) { float bqi[4] = {-bq[0], -bq[1], -bq[2], bq[3]}; q_mul(tq, bqi, torn_w); }
+  if (nullspace) for (int i = 0; i < ndb; i++) {
+    float nv = 0.001f * (rest[i] - qb[i]);
+    if (qb[i] > upper[i]) nv += 10.0f * (upper[i] - qb[i]) / range[i];
+    if (qb[i] < lower[i]) nv += 10.0f * (lower[i] - qb[i]) / range[i];
+    nullv[i] = nv;
+  }
+  int nc = 0;
+  for (int gl = ee_gl; gl >= 0; gl = sc.link_i[DG_LINK_I_W * gl + 1]) chain[nc++] = gl;
+  int m = use_orn ? 6 : 3;
+  float diff = 1e30f;
+  for (int it = 0; it < sc.ik_iters && diff > sc.ik_threshold; it++) {
+    // forward kinematics of the chain in base coordinates + geometric Jacobian
+    float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pc[3] = {0, 0, 0};
+    for (int i = nc - 1; i >= 0; i--) {
+      int gl = chain[i]; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl;
+      float E[9], r[3], t[3], Rn[9];
+      joint_xform(sc, gl, li[3] >= 0 ? qb[li[3] - d0] : 0.0f, E, r);
+      m_vec(t, Rc, r); v_add(pc, pc, t); m_mulT(Rn, Rc, E); m_cpy(Rc, Rn);
+      m_vec(axw + 3 * i, Rc, lf + 10);
+      float dw[3]; m_vec(dw, Rc, lf + 7); v_sub(orgw + 3 * i, pc, dw);
+    }
+    const float* lfe = sc.link_f + DG_LINK_F_W * ee_gl;
+    float pos[3], R[9], dw[3], Rli[9], qi[4] = {-lfe[16], -lfe[17], -lfe[18], lfe[19]};
+    m_vec(dw, Rc, lfe + 7); v_sub(pos, pc, dw);
+    q_to_mat(Rli, qi); m_mul(R, Rc, Rli);
+    for (int i = 0; i < 6 * ndb; i++) J[i] = 0.f;
+    for (int i = 0; i < nc; i++) {
+      const int* li = sc.link_i + DG_LINK_I_W * chain[i];
+      if (li[3] < 0) continue;
+      int jd = li[3] - d0;
+      if (li[2] == 1) { float rel[3], t[3]; v_sub(rel, pos, orgw + 3 * i); v_cross(t, axw + 3 * i, rel); for (int k = 0; k < 3; k++) { J[k * ndb + jd] = t[k]; J[(3 + k) * ndb + jd] = axw[3 * i + k]; } }
+      else if (li[2] == 2) for (int k = 0; k < 3; k++) J[k * ndb + jd] = axw[3 * i + k];
+    }
+    float e[6];
+    v_sub(e, tp, pos); diff = v_len(e);
+    if (use_orn) {
+      float qc[4], qci[4], dq[4]; mat_to_q(qc, R); qci[0] = -qc[0]; qci[1] = -qc[1]; qci[2] = -qc[2]; qci[3] = qc[3];
+      q_mul(dq, tq, qci);
+      // axis * angle of dq; same value as 2 acos(w) with axis xyz / sqrt(1 - w^2), written with atan2 on |xyz|
+      // because acos loses half the fp32 mantissa for the small rotations this controller asks for
+      float vn = v_len(dq), ax[3];
+      float ang = 2 * atan2f(vn, dq[3]);
+      if (vn * vn < 10 * 2.220446049250313e-16f) v_set(ax, 1, 0, 0); else v_scale(ax, dq, 1.0f / vn);
+      if (ang > kPi) ang -= 2 * kPi; else if (ang < -kPi) ang += 2 * kPi;
+      v_scale(e + 3, ax, ang);
+    }
+    if (!nullspace) {   // dth = (J^T J + lam I)^-1 J^T e
+      for (int i = 0; i < ndb; i++) {
+        for (int j = 0; j < ndb; j++) { float s = 0.f; for (int k = 0; k < m; k++) s += J[k * ndb + i] * J[k * ndb + j]; A[i * ndb + j] = s + (i == j ? sc.ik_damping : 0.f); }
+        float s = 0.f; for (int k = 0; k < m; k++) s += J[k * ndb + i] * e[k]; rhs[i] = s;
+      }
+      if (solve_dense(A, rhs, ndb) != 0) break;
+      for (int i = 0; i < ndb; i++) dth[i] = rhs[i];
+    } else {            // dth = J^T (J J^T + lam2 I)^-1 (e - J n) + n
+      for (int i = 0; i < m; i++) { float s = 0.f; for (int k = 0; k < ndb; k++) s += J[i * ndb + k] * nullv[k]; rhs[i] = e[i] - s; }
+      for (int i = 0; i < m; i++) for (int j = 0; j < m; j++) { float s = 0.f; for (int k = 0; k < ndb; k++) s += J[i * ndb + k] * J[j * ndb + k]; A[i * m + j] = s + (i == j ? sc.ik_null_lambda_sq : 0.f); }
+      if (solve_dense(A, rhs, m) != 0) break;
+      for (int k = 0; k < ndb; k++) { float s = nullv[k]; for (int i = 0; i < m; i++) s += J[i * ndb + k] * rhs[i]; dth[k] = s; }
+    }
+    float mx = 0.f; for (int i = 0; i < ndb; i++) mx = fmaxf(mx, fabsf(dth[i]));
+    float cap = 45.0f * kPi / 180.0f;
+    if (mx > cap) for (int i = 0; i < ndb; i++) dth[i] *= cap / mx;
+    for (int i = 0; i < ndb; i++) qb[i] += dth[i];
+  }
+}
+
+// ------------------------------------------------------------------ add-on ops ---------------------------------
+// controllers: update() bodies of /root/reference/diy_gym/addons/controllers/
+DG_FN void phase_actions(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  int ik_seen = 0;
+  for (int k = 0; k < sc.nop; k++) {
+    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    const float* a = op[3] >= 0 ? C.act + op[3] : nullptr;
+    if (op[0] == OP_JOINT_CTRL && ln == 0) {                 // joint_controller.py:40-58
+      int mode = ia[0], n = ia[1];
+      for (int i = 0; i < n; i++) {
+        int d = ia[2 + i];
+        if (mode == 2) { ST(S_JTORQUE)[d] += a[i]; continue; }
+        ST(S_MKD)[d] = fa[1]; ST(S_MMAXF)[d] = fa[2 + i];
+        if (mode == 0) { ST(S_MKP)[d] = fa[0]; ST(S_MTPOS)[d] = a[i]; ST(S_MTVEL)[d] = 0.f; }
+        else { ST(S_MKP)[d] = 0.f; ST(S_MTPOS)[d] = 0.f; ST(S_MTVEL)[d] = a[i]; }
+      }
+    } else if (op[0] == OP_EXT_FORCE && ln == 0) {           // external_force.py:21-24 (+ LINK_FRAME variant, drone_pilot.py:35-37)
+      int f = ia[0]; float pos[3], quat[4], v[3], o[3], F[3], rel[3], t[3];
+      frame_com_state(C, f, pos, quat, v, o);
+      if (ia[1] == 0) { v_cpy(F, a); v_sub(rel, fa, pos); }
+      else { float R[9]; q_to_mat(R, quat); m_vec(F, R, a); m_vec(rel, R, fa); }
+      v_add(ST(S_EXTF) + 3 * f, ST(S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(ST(S_EXTT) + 3 * f, ST(S_EXTT) + 3 * f, t);
+    } else if (op[0] == OP_IK_CTRL) {                         // ik_controller.py:51-80
+      int mine = (ik_seen++ % nt) == ln;
+      if (!mine) continue;
+      int b = ia[0], ee = ia[1], n = ia[2], use_orn = ia[3], nsp = ia[4]; int ndb = sc.body_i[DG_BODY_I_W * b + 4];
+      float pos[3], quat[4], v[3], o[3], tq[4] = {0, 0, 0, 1};
+      frame_com_state(C, sc.nb + ee, pos, quat, v, o);
+      float tpos[3] = {pos[0] + a[0], pos[1] + a[1], pos[2] + a[2]};
+      if (use_orn) { float dq[4]; q_from_euler(dq, a + 3); q_mul(tq, quat, dq); }
+      const float* lim = fa + 2 + n;
+      float* scr = C.ws + sc.W_X + sc.ik_stride * (ln % (sc.n_ik < nt ? sc.n_ik : nt));
+      ik_solve(C, b, ee, tpos, tq, use_orn, nsp, lim, lim + ndb, lim + 2 * ndb, lim + 3 * ndb, scr);
+      for (int i = 0; i < n; i++) {
+        int d = ia[5 + i];
+        ST(S_MKP)[d] = fa[0]; ST(S_MKD)[d] = fa[1]; ST(S_MMAXF)[d] = fa[2 + i]; ST(S_MTPOS)[d] = scr[i]; ST(S_MTVEL)[d] = 0.f;
+      }
+    }
+  }
+  if (ln == 0) ST(S_STEP)[0] += 1.f;
+}
+// sensors / rewards / terminals: observe(), reward(), is_terminal() bodies of diy_gym/addons/{sensors,rewards}/
+DG_FN void phase_observe(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  for (int k = ln; k < sc.nop; k += nt) {
+    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    float* o = op[4] >= 0 ? C.obs + op[4] : nullptr;
+    if (op[0] == OP_JOINT_SENSOR) {                     // joint_state_sensor.py:46-57
+      int n = ia[0], flags = ia[1], j = 0;
+      for (int i = 0; i < n; i++) o[j++] = ST(S_Q)[ia[2 + i]];
+      if (flags & 1) for (int i = 0; i < n; i++) o[j++] = ST(S_QD)[ia[2 + i]];
+      if (flags & 2) for (int i = 0; i < n; i++) o[j++] = ST(S_MAPPLIED)[ia[2 + i]] / sc.dt;
+    } else if (op[0] == OP_OBJECT_SENSOR) {             // object_state_sensor.py:33-75
+      float p[3], q[4], v[3], w[3]; int flags = ia[2], j = 0;
+      frame_com_state(C, ia[0], p, q, v, w);
+      if (ia[1] >= 0) {
+        float sp[3], sq[4], sv[3], sw[3], qq[4];
+        frame_com_state(C, ia[1], sp, sq, sv, sw);
+        v_sub(p, p, sp); v_sub(v, v, sv); q_mul(qq, sq, q); for (int i = 0; i < 4; i++) q[i] = qq[i]; v_sub(w, w, sw);
+      }
+      for (int i = 0; i < 3; i++) o[j++] = p[i];
+      if (flags & 2) for (int i = 0; i < 3; i++) o[j++] = v[i];
+      if (flags & 1) { float e[3]; euler_from_q(e, q); for (int i = 0; i < 3; i++) o[j++] = e[i]; }
+      if ((flags & 3) == 3) for (int i = 0; i < 3; i++) o[j++] = w[i];
+    } else if (op[0] == OP_REACH_TARGET) {              // reach_target.py:21-36
+      float sp[3], sq[4], tp[3], tq[4], d[3];
+      frame_link_pose(C, ia[0], sp, sq); frame_link_pose(C, ia[1], tp, tq); v_sub(d, tp, sp);
+      float dist = v_len(d);
+      C.rew[op[5]] = -dist * fa[0]; C.term[op[6]] = dist < fa[1];
+    } else if (op[0] == OP_ELECTRICITY) {               // electricity_cost.py:15-18
+      const int* bi = sc.body_i + DG_BODY_I_W * ia[0]; float s = 0.f;
+      for (int i = 0; i < bi[4]; i++) s += fabsf(ST(S_MAPPLIED)[bi[3] + i] / sc.dt * ST(S_QD)[bi[3] + i]);
+      C.rew[op[5]] = -s * fa[0];
+    } else if (op[0] == OP_STUCK_JOINT) {               // stuck_joint_cost.py:19-21 (intent; the reference raises NameError)
+      const int* bi = sc.body_i + DG_BODY_I_W * ia[0]; int stuck = 0;
+      for (int l = 0; l < bi[2]; l++) {
+        const int* li = sc.link_i + DG_LINK_I_W * (bi[1] + l); const float* lf = sc.link_f + DG_LINK_F_W * (bi[1] + l);
+        if (li[3] < 0) continue;
+        float qq = ST(S_Q)[li[3]];
+        if (fminf(fabsf(lf[20] - qq), fabsf(lf[21] - qq)) < 0.01f) stuck = 1;
+      }
+      C.rew[op[5]] = stuck ? -fa[0] : 0.0f;
+    } else if (op[0] == OP_TIME_PENALTY) {              // time_penalty.py:11-12
+      C.rew[op[5]] = fa[0];
+    } else if (op[0] == OP_EPISODE_TIMER) {             // diy_gym.py:180-183
+      C.term[op[6]] = ST(S_STEP)[0] >= fa[0];
+    }
+  }
+}
+// reset() bodies of joint/ik controllers, respawn, dynamics_randomizer (diy_gym.py:139-143)
+DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
+  if (ln != 0) return;
+  const DevScene& sc = SC;
+  ST(S_STEP)[0] = 0.f;
+  uint32_t epoch = (uint32_t)ST(S_RESETS)[0];
+  for (int k = 0; k < sc.nop; k++) {
+    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    if (op[0] == OP_JOINT_RESET) {                      // joint_controller.py:36-38, ik_controller.py:47-49
+      for (int i = 0; i < ia[0]; i++) { ST(S_Q)[ia[1 + i]] = fa[i]; ST(S_QD)[ia[1 + i]] = 0.f; }
+    } else if (op[0] == OP_RESPAWN) {                   // respawn.py:31-39
+      int b = ia[0]; uint32_t ep = ia[1] ? 0u : epoch; const float* ip = PR(P_INITPOSE) + 7 * b;
+      float e[3], dq[4], qo[4];
+      for (int i = 0; i < 3; i++) ST(S_BPOS)[3 * b + i] = ip[i] + (urand(C.seed, (uint32_t)C.env_id, ep, (uint32_t)(k * 8 + i)) - 0.5f) * fa[i];
+      for (int i = 0; i < 3; i++) e[i] = (urand(C.seed, (uint32_t)C.env_id, ep, (uint32_t)(k * 8 + 3 + i)) - 0.5f) * fa[3 + i];
+      q_from_euler(dq, e); q_mul(qo, ip + 3, dq); for (int i = 0; i < 4; i++) ST(S_BQUAT)[4 * b + i] = qo[i];
+      v_set(ST(S_BVEL) + 3 * b, 0, 0, 0); v_set(ST(S_BOMEGA) + 3 * b, 0, 0, 0);
+    } else if (op[0] == OP_DYN_RANDOMIZE) {             // dynamics_randomizer.py:24-32 (log-uniform on nominal values)
+      int b = ia[0]; const int* bi = sc.body_i + DG_BODY_I_W * b;
+      for (int l = -1; l < bi[2]; l++) {
+        int f = l < 0 ? b : sc.nb + bi[1] + l; int d = l < 0 ? -1 : sc.link_i[DG_LINK_I_W * (bi[1] + l) + 3];
+        if (l >= 0 && d < 0) continue;
+        if (l < 0 && bi[4] > 0) continue;
+        float u1 = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 64 + 2 * (l + 1)));
+        float u2 = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 65 + 2 * (l + 1)));
+        float ms = expf(logf(fa[0]) + u1 * (logf(fa[1]) - logf(fa[0]))), ds = expf(logf(fa[2]) + u2 * (logf(fa[3]) - logf(fa[2])));
+        PR(P_MASS)[f] = sc.param_def[DG_PO(C.sc, P_MASS) + f] * ms;
+        for (int i = 0; i < 3; i++) PR(P_INERTIA)[3 * f + i] = sc.param_def[DG_PO(C.sc, P_INERTIA) + 3 * f + i] * ms;
+        if (d >= 0) PR(P_JDAMP)[d] = sc.param_def[DG_PO(C.sc, P_JDAMP) + d] * ds;
+      }
+    }
+  }
+  ST(S_RESETS)[0] += 1.f;
+}
+
+// ------------------------------------------------------------------ the phase schedule -------------------------
+// DG_PHASE(call): on the GPU every lane runs `call` with its own `ln`, then the team synchronises; the CPU
+// emulation runs `call` for ln = 0..nt-1 in turn.  Control flow between phases depends only on team-uniform values.
+DG_HD void team_sync(unsigned tmask) {
+#if defined(__CUDA_ARCH__)
+  if (tmask != 1u) __syncwarp(tmask);
+#else
+  (void)tmask;
+#endif
+}
+#if defined(__CUDA_ARCH__)
+#define DG_PHASE(call) do { call; team_sync(tmask); } while (0)
+#define DG_LANE_ARGS int ln, unsigned tmask
+#else
+#define DG_PHASE(call) do { for (int ln = 0; ln < nt; ln++) { call; } } while (0)
+#define DG_LANE_ARGS int, unsigned
+#endif
+
+// p.stepSimulation() (diy_gym.py:146,207); nsub = 0 only refreshes the link cache
+DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {
+  const DevScene& sc = SC;
+  float h = sc.dt / (float)sc.substeps;
+  DG_PHASE(phase_load(C, ln, nt));
+  for (int sub = 0; sub < nsub; sub++) {
+    DG_PHASE(phase_dynamics(C, ln, nt, h));
+    DG_PHASE(phase_shape_world(C, ln, nt));
+    if (sc.npair > 0) {
+      DG_PHASE(phase_broad(C, ln, nt));
+      DG_PHASE(phase_count_survivors(C, ln, nt));
+      int nsurv = WSI(C)[sc.W_HDR + WH_NSURV];
+      for (int rnd = 0; rnd * nt < nsurv; rnd++) {
+        DG_PHASE(phase_narrow(C, ln, nt, rnd));
+        DG_PHASE(phase_append(C, ln, nt));
+      }
+    }
+    DG_PHASE(phase_minv(C, ln, nt));
+    DG_PHASE(phase_unit_rows(C, ln, nt, h));
+    int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
+    if (ncr == 0) {
+      DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
+    } else {
+      DG_PHASE(phase_contact_rows(C, ln, nt, h));
+      for (int it = 0; it < sc.iters; it++) {
+        DG_PHASE(phase_pgs_unit(C, ln, nt, it, it + 1));
+        DG_PHASE(phase_pgs_contact(C, ln, nt));
+      }
+    }
+    DG_PHASE(phase_integrate(C, ln, nt, h));
+  }
+  DG_PHASE(phase_final_kin(C, ln, nt));
+  DG_PHASE(phase_store(C, ln, nt, clear_forces));
+}
+
+// DIYGym.step for one environment
+DG_FN void run_env_step(const Env& C, int nt, DG_LANE_ARGS) {
+#if defined(__CUDA_ARCH__)
+  DG_PHASE(phase_actions(C, ln, nt));
+  run_physics(C, nt, SC.substeps, 1, ln, tmask);
+  DG_PHASE(phase_observe(C, ln, nt));
+#else
+  DG_PHASE(phase_actions(C, ln, nt));
+  run_physics(C, nt, SC.substeps, 1, 0, 0);
+  DG_PHASE(phase_observe(C, ln, nt));
+#endif
+}
+// DIYGym.reset for one environment
+DG_FN void run_env_reset(const Env& C, int nt, DG_LANE_ARGS) {
+#if defined(__CUDA_ARCH__)
+  DG_PHASE(phase_reset_ops(C, ln, nt));
+  run_physics(C, nt, 0, 0, ln, tmask);
+  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, ln, tmask);
+  DG_PHASE(phase_observe(C, ln, nt));
+#else
+  DG_PHASE(phase_reset_ops(C, ln, nt));
+  run_physics(C, nt, 0, 0, 0, 0);
+  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, 0, 0);
+  DG_PHASE(phase_observe(C, ln, nt));
+#endif
+}
+
+}  // namespace dg

@@ -1,0 +1,334 @@
+// dg_kernels.cu - sm_100a kernels and the C ABI (include/diygym_b200.h) of the batched DIYGym backend.
+//
+// dg_step_kernel<T>: persistent grid; a block holds blockDim/T teams of T lanes, each team advances one
+// environment at a time with its whole working set (dg_scene.h workspace plan) in dynamic shared memory, and
+// walks the environment list with a grid stride.  Scene constants are read-only global arrays shared by all
+// environments (L1/L2 resident).  State rows are [env][S] so that a team's loads and stores are contiguous.
+// dg_render_kernel: one block per (environment, pixel tile); visual shapes are staged in shared memory once per
+// block and every thread ray-casts its pixels (camera.py:58-92 of the reference, TinyRenderer replaced).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/diygym_b200.h"
+#include "dg_env.cuh"
+
+namespace dg {
+
+struct LaunchArgs {
+  float* state; float* param; const float* act; float* obs; float* rew; uint8_t* term;
+  const uint8_t* mask; int n_envs; int mode; uint32_t seed; int env_off;
+};
+
+template <int T>
+__global__ void __launch_bounds__(128) dg_step_kernel(const __grid_constant__ DevScene sc, const LaunchArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const int teams_per_block = blockDim.x / T;
+  const int team = threadIdx.x / T, ln = threadIdx.x % T;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned tmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(unsigned)(T - 1)));
+  Env C;
+  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.seed = a.seed;
+  for (int e = blockIdx.x * teams_per_block + team; e < a.n_envs; e += gridDim.x * teams_per_block) {
+    if (a.mask != nullptr && a.mask[e] == 0) continue;
+    C.st = a.state + (size_t)e * sc.S; C.pr = a.param + (size_t)e * sc.P;
+    C.act = a.act + (size_t)e * sc.n_act; C.obs = a.obs + (size_t)e * sc.n_obs; C.rew = a.rew + (size_t)e * sc.n_rew;
+    C.term = a.term + (size_t)e * sc.n_term; C.env_id = a.env_off + e;
+    if (a.mode == 0) run_env_step(C, T, ln, tmask); else run_env_reset(C, T, ln, tmask);
+    team_sync(tmask);
+  }
+}
+
+__global__ void dg_init_kernel(const __grid_constant__ DevScene sc, float* state, float* param, int n_envs) {
+  size_t total_s = (size_t)n_envs * sc.S, total_p = (size_t)n_envs * sc.P;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_s; i += stride) state[i] = sc.state_def[i % sc.S];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_p; i += stride) param[i] = sc.param_def[i % sc.P];
+}
+
+// ---------------------------------------------------------------- camera ----------------------------------------
+// nearest hit of a ray (shape-local origin o, direction dir) within (1e-9, tmax)
+__device__ __forceinline__ bool ray_shape(int type, const float* d, const float* o, const float* dir, float tmax, float* t_out, float* n_out) {
+  float best = tmax; bool hit = false; float nb_[3] = {0, 0, 1};
+  if (type == SHAPE_SPHERE || type == SHAPE_CAPSULE) {
+    int nsph = type == SHAPE_SPHERE ? 1 : 2;
+    for (int s = 0; s < nsph; s++) {
+      float cz = type == SHAPE_SPHERE ? 0.f : (s ? d[1] : -d[1]);
+      float oc[3] = {o[0], o[1], o[2] - cz};
+      float A = v_dot(dir, dir), B = v_dot(oc, dir), Cc = v_dot(oc, oc) - d[0] * d[0], disc = B * B - A * Cc;
+      if (disc < 0) continue;
+      float t = (-B - sqrtf(disc)) / A;
+      if (t > 1e-9f && t < best) { best = t; hit = true; for (int i = 0; i < 3; i++) nb_[i] = (oc[i] + t * dir[i]) / d[0]; }
+    }
+  }
+  if (type == SHAPE_CAPSULE || type == SHAPE_CYLINDER) {
+    float A = dir[0] * dir[0] + dir[1] * dir[1], B = o[0] * dir[0] + o[1] * dir[1], Cc = o[0] * o[0] + o[1] * o[1] - d[0] * d[0];
+    float disc = B * B - A * Cc;
+    if (A > 1e-18f && disc >= 0) {
+      float t = (-B - sqrtf(disc)) / A, z = o[2] + t * dir[2];
+      if (t > 1e-9f && t < best && fabsf(z) <= d[1]) { best = t; hit = true; nb_[0] = (o[0] + t * dir[0]) / d[0]; nb_[1] = (o[1] + t * dir[1]) / d[0]; nb_[2] = 0; }
+    }
+    if (type == SHAPE_CYLINDER && fabsf(dir[2]) > 1e-18f) for (int s = -1; s <= 1; s += 2) {
+      float t = (s * d[1] - o[2]) / dir[2], x = o[0] + t * dir[0], y = o[1] + t * dir[1];
+      if (t > 1e-9f && t < best && x * x + y * y <= d[0] * d[0]) { best = t; hit = true; nb_[0] = 0; nb_[1] = 0; nb_[2] = (float)s; }
+    }
+  }
+  if (type == SHAPE_BOX) {
+    float t0 = -1e30f, t1 = 1e30f; int ax0 = 0; float sg0 = 1; bool ok = true;
+    for (int i = 0; i < 3; i++) {
+      if (fabsf(dir[i]) < 1e-18f) { if (fabsf(o[i]) > d[i]) ok = false; continue; }
+      float inv = 1.0f / dir[i];
+      float ta = (-d[i] - o[i]) * inv, tb = (d[i] - o[i]) * inv, sg = -1;
+      if (ta > tb) { float t = ta; ta = tb; tb = t; sg = 1; }
+      if (ta > t0) { t0 = ta; ax0 = i; sg0 = sg; }
+      if (tb < t1) t1 = tb;
+    }
+    if (ok && t0 <= t1 && t0 > 1e-9f && t0 < best) { best = t0; hit = true; nb_[0] = nb_[1] = nb_[2] = 0; if (ax0 == 0) nb_[0] = sg0; else if (ax0 == 1) nb_[1] = sg0; else nb_[2] = sg0; }
+  }
+  if (hit) { *t_out = best; v_cpy(n_out, nb_); }
+  return hit;
+}
+
+// per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1) = 21 floats
+#define VS_W 21
+__global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth, int tiles_per_env) {
+  extern __shared__ __align__(16) float vs[];
+  __shared__ float camRp[12];
+  const int e = blockIdx.x / tiles_per_env, tile = blockIdx.x % tiles_per_env;
+  const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
+  const int width = ci[1], height = ci[2];
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.pr = nullptr;
+  for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
+    const int* vi = sc.vis_i + DG_VIS_I_W * s; const float* vf = sc.vis_f + DG_VIS_F_W * s; float* o = vs + VS_W * s;
+    if (vi[2]) { for (int i = 0; i < 12; i++) o[i] = sc.vis_wb[12 * s + i]; }
+    else {
+      float p[3], q[4], v[3], w[3], R[9], Rs[9], t[3];
+      frame_com_state(C, vi[0], p, q, v, w); q_to_mat(R, q); q_to_mat(Rs, vf + 3); m_mul(o, R, Rs);
+      m_vec(t, R, vf); v_add(o + 9, p, t);
+    }
+    for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
+    for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
+    o[19] = int_as_float(vi[1]); o[20] = vf[15];
+  }
+  if (threadIdx.x == 0) {
+    float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0}, Rl[9], t[3];
+    if (ci[0] >= 0) { float q[4]; frame_link_pose(C, ci[0], pp, q); q_to_mat(Rp, q); }
+    q_to_mat(Rl, cf + 3); m_mul(camRp, Rp, Rl); m_vec(t, Rp, cf); v_add(camRp + 9, pp, t);
+  }
+  __syncthreads();
+  const float fov = cf[7], nearp = cf[8], farp = cf[9];
+  const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
+  const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
+  const int npx = width * height, per_tile = (npx + tiles_per_env - 1) / tiles_per_env;
+  const int p0 = tile * per_tile, p1 = min(npx, p0 + per_tile);
+  float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx;
+  for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
+    int j = px / width, i = px - j * width;
+    float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f}, dw[3];
+    m_vec(dw, camRp, dc);
+    float dd = v_dot(dw, dw);
+    float best = farp; int hs = -1; float hn[3] = {0, 0, 1};
+    for (int s = 0; s < sc.nv; s++) {
+      const float* o = vs + VS_W * s;
+      float oc[3]; v_sub(oc, camRp + 9, o + 9);
+      // bounding-sphere reject: closest approach of the ray to the shape centre
+      float b = v_dot(oc, dw), c2 = v_dot(oc, oc) - o[20] * o[20];
+      if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
+      float ol[3], dl[3], tt, nn[3];
+      mT_vec(ol, o, oc); mT_vec(dl, o, dw);
+      if (ray_shape(float_as_int(o[19]), o + 12, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, o, nn); }
+    }
+    float r, g, bl, dz;
+    if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
+    else {
+      const float* col = vs + VS_W * hs + 16; float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
+      r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best;
+    }
+    rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
+  }
+}
+
+}  // namespace dg
+
+// ---------------------------------------------------------------- C ABI ------------------------------------------
+using namespace dg;
+
+struct DgWorld {
+  HostScene hs;
+  DevScene dev;            // pointers re-targeted to device memory
+  int* d_ints = nullptr; float* d_floats = nullptr;
+  int n_envs = 0, device = 0, team = 1, block_threads = 64, grid = 1, sm_count = 148;
+  size_t smem = 0;
+  DgBufferTable buf{};
+  bool bound = false;
+  uint32_t seed = 1234u; int env_off = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+static std::string g_create_err;
+
+#define CK(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (w)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DG_E_CUDA; } } while (0)
+
+template <int T> static cudaError_t configure(DgWorld* w) {
+  cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dg_step_kernel<T>, w->block_threads, w->smem);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) occ = 1;
+  int teams_per_block = w->block_threads / T;
+  int need = (w->n_envs + teams_per_block - 1) / teams_per_block;
+  w->grid = std::max(1, std::min(need, w->sm_count * occ));
+  return cudaSuccess;
+}
+template <int T> static cudaError_t launch(DgWorld* w, const LaunchArgs& a, cudaStream_t s) {
+  dg_step_kernel<T><<<w->grid, w->block_threads, w->smem, s>>>(w->dev, a);
+  return cudaGetLastError();
+}
+static cudaError_t configure_any(DgWorld* w) {
+  switch (w->team) { case 1: return configure<1>(w); case 2: return configure<2>(w); case 4: return configure<4>(w); case 8: return configure<8>(w);
+                     case 16: return configure<16>(w); default: return configure<32>(w); }
+}
+static cudaError_t launch_any(DgWorld* w, const LaunchArgs& a, cudaStream_t s) {
+  w->launches++;
+  switch (w->team) { case 1: return launch<1>(w, a, s); case 2: return launch<2>(w, a, s); case 4: return launch<4>(w, a, s); case 8: return launch<8>(w, a, s);
+                     case 16: return launch<16>(w, a, s); default: return launch<32>(w, a, s); }
+}
+
+extern "C" {
+
+const char* dg_last_error(const DgWorld* w) { return w ? w->err.c_str() : g_create_err.c_str(); }
+
+int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_fbuf, int n_envs, int device, int team, DgWorld** out) {
+  if (!ibuf || !fbuf || !out || n_envs < 1) { g_create_err = "dg_world_create: bad argument"; return DG_E_ARG; }
+  if (team != 0 && team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) { g_create_err = "dg_world_create: team must be 0,1,2,4,8,16,32"; return DG_E_ARG; }
+  DgWorld* w = new DgWorld();
+  w->n_envs = n_envs; w->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
+  w->sm_count = prop.multiProcessorCount;
+  const size_t smem_cap = prop.sharedMemPerBlockOptin;
+  if (team == 0) {
+    // built-in choice: enough lanes for the per-item phases, few enough that many environments stay resident
+    const char* env_team = getenv("DG_TEAM");
+    team = env_team ? atoi(env_team) : 4;
+    if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
+  }
+  const char* env_block = getenv("DG_BLOCK");
+  int block = env_block ? atoi(env_block) : 64;
+  if (block < team) block = team;
+  if (block > 128) block = 128;
+  block = (block / team) * team;
+  for (;;) {
+    if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+    size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
+    int teams = block / team;
+    while (teams > 1 && per_team * teams > smem_cap) teams--;
+    if (per_team * teams <= smem_cap) { w->block_threads = teams * team; w->smem = per_team * teams; break; }
+    g_create_err = "scene workspace (" + std::to_string(per_team) + " B per environment) exceeds shared memory"; delete w; return DG_E_NOMEM;
+  }
+  w->team = team;
+  // upload the constant tables
+  size_t nbi = w->hs.ints.size() * sizeof(int), nbf = w->hs.floats.size() * sizeof(float);
+  if (cudaMalloc(&w->d_ints, nbi) != cudaSuccess || cudaMalloc(&w->d_floats, nbf) != cudaSuccess) { g_create_err = "cudaMalloc of scene tables failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
+  if (cudaMemcpy(w->d_ints, w->hs.ints.data(), nbi, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(w->d_floats, w->hs.floats.data(), nbf, cudaMemcpyHostToDevice) != cudaSuccess) { g_create_err = "upload of scene tables failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
+  w->dev = w->hs.dev;
+  w->hs.point(w->dev, w->d_ints, w->d_floats);
+  e = configure_any(w);
+  if (e != cudaSuccess) { g_create_err = std::string("kernel configuration: ") + cudaGetErrorString(e); dg_world_destroy(w); return DG_E_CUDA; }
+  *out = w;
+  return DG_OK;
+}
+
+void dg_world_destroy(DgWorld* w) {
+  if (!w) return;
+  if (w->d_ints) cudaFree(w->d_ints);
+  if (w->d_floats) cudaFree(w->d_floats);
+  delete w;
+}
+
+int64_t dg_query(const DgWorld* w, int key) {
+  if (!w) return -1;
+  const DevScene& d = w->dev;
+  switch (key) {
+    case DG_Q_STATE_SIZE: return d.S; case DG_Q_PARAM_SIZE: return d.P; case DG_Q_N_ACT: return d.n_act; case DG_Q_N_OBS: return d.n_obs;
+    case DG_Q_N_REW: return d.n_rew; case DG_Q_N_TERM: return d.n_term; case DG_Q_N_ENVS: return w->n_envs; case DG_Q_TEAM: return w->team;
+    case DG_Q_BLOCK_THREADS: return w->block_threads; case DG_Q_GRID_BLOCKS: return w->grid; case DG_Q_SMEM_BYTES: return (int64_t)w->smem;
+    case DG_Q_WS_FLOATS: return d.w_total; case DG_Q_N_CAMERAS: return d.ncam; case DG_Q_LAUNCHES: return w->launches;
+  }
+  return -1;
+}
+
+int dg_bind_buffers(DgWorld* w, const DgBufferTable* t) {
+  if (!w || !t) return DG_E_ARG;
+  const DevScene& d = w->dev;
+  if (!t->state || !t->param || (d.n_act && !t->action) || (d.n_obs && !t->obs) || (d.n_rew && !t->reward) || (d.n_term && !t->term)) { w->err = "dg_bind_buffers: a required buffer is NULL"; return DG_E_ARG; }
+  w->buf = *t; w->bound = true;
+  return DG_OK;
+}
+
+int dg_set_seed(DgWorld* w, uint32_t seed, int env_id_offset) {
+  if (!w) return DG_E_ARG;
+  w->seed = seed; w->env_off = env_id_offset;
+  return DG_OK;
+}
+
+int dg_init_state(DgWorld* w, void* stream) {
+  if (!w) return DG_E_ARG;
+  if (!w->bound) { w->err = "dg_init_state: buffers not bound"; return DG_E_UNBOUND; }
+  CK(w, cudaSetDevice(w->device));
+  w->launches++;
+  dg_init_kernel<<<w->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, w->n_envs);
+  CK(w, cudaGetLastError());
+  return DG_OK;
+}
+
+static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
+  if (!w) return DG_E_ARG;
+  if (!w->bound) { w->err = "buffers not bound"; return DG_E_UNBOUND; }
+  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off};
+  CK(w, launch_any(w, a, (cudaStream_t)stream));
+  return DG_OK;
+}
+int dg_step(DgWorld* w, void* stream) { return run(w, 0, nullptr, stream); }
+int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream) { return run(w, 1, mask_dev, stream); }
+
+int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream) {
+  if (!w || !rgb_dev || !depth_dev) return DG_E_ARG;
+  if (!w->bound) { w->err = "dg_render: buffers not bound"; return DG_E_UNBOUND; }
+  const DevScene& d = w->dev;
+  if (cam < 0 || cam >= d.ncam) { w->err = "dg_render: no such camera"; return DG_E_ARG; }
+  const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
+  int npx = ci[1] * ci[2];
+  int tiles = std::max(1, std::min((npx + 2047) / 2048, 64));
+  size_t smem = (size_t)std::max(d.nv, 1) * VS_W * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+  attr_set = true;
+  w->launches++;
+  dg_render_kernel<<<w->n_envs * tiles, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, tiles);
+  CK(w, cudaGetLastError());
+  return DG_OK;
+}
+
+int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* reward_host, uint8_t* term_host, void* stream) {
+  if (!w) return DG_E_ARG;
+  if (!w->bound) { w->err = "dg_step_host: buffers not bound"; return DG_E_UNBOUND; }
+  const DevScene& d = w->dev; cudaStream_t s = (cudaStream_t)stream; size_t n = (size_t)w->n_envs;
+  if (d.n_act && action_host) CK(w, cudaMemcpyAsync(w->buf.action, action_host, n * d.n_act * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = dg_step(w, stream);
+  if (rc != DG_OK) return rc;
+  if (d.n_obs && obs_host) CK(w, cudaMemcpyAsync(obs_host, w->buf.obs, n * d.n_obs * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (d.n_rew && reward_host) CK(w, cudaMemcpyAsync(reward_host, w->buf.reward, n * d.n_rew * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (d.n_term && term_host) CK(w, cudaMemcpyAsync(term_host, w->buf.term, n * d.n_term, cudaMemcpyDeviceToHost, s));
+  CK(w, cudaStreamSynchronize(s));
+  return DG_OK;
+}
+
+}  // extern "C"

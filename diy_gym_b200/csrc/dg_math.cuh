@@ -6,10 +6,10 @@
 
 #if defined(__CUDACC__)
 #define DG_HD __host__ __device__ __forceinline__
-#define DG_FN __host__ __device__
+#define DG_FN __host__ __device__ inline
 #else
 #define DG_HD inline
-#define DG_FN
+#define DG_FN inline
 #endif
 
 namespace dg {

@@ -1,0 +1,257 @@
+// dg_scene.h - device-visible scene description and the per-environment workspace plan.
+//
+// The Python compiler (diy_gym_b200/compiler/scene.py) hands the C ABI two flat buffers (int32 + float64
+// sections, layout in scene_sections.h).  `HostScene::build` converts them to fp32, derives the tables the
+// kernels need (dynamic-body list, frame slots, depth of every link, baked world poses of static shapes)
+// and lays out the per-environment workspace that the step kernel keeps in shared memory.
+//
+// This replaces what the reference keeps inside its physics server after `p.loadURDF`
+// (/root/reference/diy_gym/model.py:65) - here it is plain constant arrays shared by all environments.
+#pragma once
+#include <stdint.h>
+
+#include "scene_sections.h"
+
+namespace dg {
+
+// number of per-dof hot arrays in the workspace (q, qd, kp, kd, tpos, tvel, maxf, applied, jtorque, tdamp, qdd)
+enum { D_Q = 0, D_QD, D_KP, D_KD, D_TPOS, D_TVEL, D_MAXF, D_APPLIED, D_JTQ, D_TDAMP, D_QDD, D_COUNT };
+// body plan columns
+enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_W };
+// workspace header ints
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_FLAGS, WH_COUNT = 8 };
+// row record strides
+enum { UR_RHS = 0, UR_DINV, UR_LO, UR_HI, UR_APPLIED, UR_COL, UR_MOTOR, UR_W = 8 };
+enum { CR_RHS = 0, CR_DINV, CR_LO, CR_HI, CR_APPLIED, CR_MU, CR_DA, CR_DB, CR_PARENT, CR_HDR = 10 };
+enum { CT_FA = 0, CT_FB, CT_PA = 2, CT_PB = 5, CT_N = 8, CT_DIST = 11, CT_MU = 12, CT_W = 13 };
+
+struct DevScene {
+  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters;
+  int n_act, n_obs, n_rew, n_term;
+  int so[24];  // state offsets:  so[HI_S_x - HI_S_BPOS]
+  int po[8];   // param offsets:  po[HI_P_x - HI_P_MASS]
+  float dt, g[3], erp, cerp, slop, margin, ik_damping, ik_threshold, max_joint_vel, limit_max_impulse, ik_null_lambda_sq;
+  const int *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
+  const float *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *cam_f, *param_def, *state_def;
+  // ---- plan ----
+  int ndyn, nslot, nshw, nfloat, GD, GP, max_depth, max_nlb, n_ik, team;
+  const int* dyn_body;    // [ndyn] body index of every body with kind != 0
+  const int* body_plan;   // [nb][BP_W]
+  const int* frame_slot;  // [nframes] workspace slot of a frame, -1 for frames of baked static bodies
+  const int* link_depth;  // [nl] depth below the base (children of the base = 0)
+  const int* shape_slot;  // [ns] index into the per-env shape-world array, -1 when baked
+  const float* shape_wb;  // [ns][12] world rotation (9) + centre (3) of baked shapes
+  const float* vis_wb;    // [nv][12] same for baked visual shapes
+  const float* link_x;    // [nl][16] joint rest rotation R0 (9), motion subspace angular (3) / linear (3), pad
+  // ---- workspace layout (float offsets) ----
+  int w_total;
+  int W_HDR, W_BST, W_DOF, W_EXT, W_KIN, W_LINK, W_MINV, W_DV, W_I0, W_UCNT, W_X;
+  // region X, articulated-body phase
+  int X_ABA, X_LNK, X_I0T;
+  // region X, constraint phase
+  int X_SHW, X_CON, X_SURV, X_CTMP, X_UROW, X_CROW, X_MSCR;
+  int crow_stride, mscr_stride, ctmp_stride, ik_stride;
+};
+
+#define DG_SO(sc, name) ((sc)->so[HI_##name - HI_S_BPOS])
+#define DG_PO(sc, name) ((sc)->po[HI_##name - HI_P_MASS])
+
+}  // namespace dg
+
+#ifndef __CUDACC_RTC__
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace dg {
+
+// Host-side owner of the converted scene.  `dev` holds HOST pointers into the vectors below; the CUDA
+// backend re-targets them to device copies, the test-only emulation uses them as they are.
+struct HostScene {
+  std::vector<int> ints;      // all int tables, concatenated
+  std::vector<float> floats;  // all float tables, concatenated
+  DevScene dev;
+  std::string error;
+
+  // offsets of every table inside ints / floats (so a device copy can be re-pointed)
+  struct Off { size_t body_i, link_i, shape_i, pair_i, vis_i, op_i, oparg_i, cam_i, dyn_body, body_plan, frame_slot, link_depth, shape_slot;
+               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x; } off;
+
+  static void quat_to_mat(const double* q, double* m) {
+    double x = q[0], y = q[1], z = q[2], w = q[3];
+    double n = 1.0 / std::sqrt(x * x + y * y + z * z + w * w); x *= n; y *= n; z *= n; w *= n;
+    m[0] = 1 - 2 * (y * y + z * z); m[1] = 2 * (x * y - z * w); m[2] = 2 * (x * z + y * w);
+    m[3] = 2 * (x * y + z * w); m[4] = 1 - 2 * (x * x + z * z); m[5] = 2 * (y * z - x * w);
+    m[6] = 2 * (x * z - y * w); m[7] = 2 * (y * z + x * w); m[8] = 1 - 2 * (x * x + y * y);
+  }
+
+  void point(DevScene& d, const int* ib, const float* fb) const {
+    d.body_i = ib + off.body_i; d.link_i = ib + off.link_i; d.shape_i = ib + off.shape_i; d.pair_i = ib + off.pair_i;
+    d.vis_i = ib + off.vis_i; d.op_i = ib + off.op_i; d.oparg_i = ib + off.oparg_i; d.cam_i = ib + off.cam_i;
+    d.dyn_body = ib + off.dyn_body; d.body_plan = ib + off.body_plan; d.frame_slot = ib + off.frame_slot;
+    d.link_depth = ib + off.link_depth; d.shape_slot = ib + off.shape_slot;
+    d.body_f = fb + off.body_f; d.link_f = fb + off.link_f; d.shape_f = fb + off.shape_f; d.vis_f = fb + off.vis_f;
+    d.oparg_f = fb + off.oparg_f; d.cam_f = fb + off.cam_f; d.param_def = fb + off.param_def; d.state_def = fb + off.state_def;
+    d.shape_wb = fb + off.shape_wb; d.vis_wb = fb + off.vis_wb; d.link_x = fb + off.link_x;
+  }
+
+  bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team) {
+    if (ni < 2 + 3 * DG_NSECTIONS || ibuf[0] != (int32_t)DG_SCENE_MAGIC || ibuf[1] != DG_NSECTIONS) { error = "bad scene magic / section count"; return false; }
+    auto sec_off = [&](int s) { return (size_t)ibuf[2 + 3 * s + 1]; };
+    auto sec_len = [&](int s) { return (size_t)ibuf[2 + 3 * s + 2]; };
+    for (int s = 0; s < DG_NSECTIONS; s++) {
+      bool is_f = ibuf[2 + 3 * s] != 0;
+      if (sec_off(s) + sec_len(s) > (size_t)(is_f ? nf : ni)) { error = "section out of range"; return false; }
+    }
+    const int32_t* hi = ibuf + sec_off(SEC_HDR_I);
+    const double* hf = fbuf + sec_off(SEC_HDR_F);
+    DevScene& d = dev;
+    d = DevScene();
+    d.nb = hi[HI_nb]; d.nl = hi[HI_nl]; d.nd = hi[HI_nd]; d.ns = hi[HI_ns]; d.nv = hi[HI_nv]; d.npair = hi[HI_npair];
+    d.ncam = hi[HI_ncam]; d.nop = hi[HI_nop]; d.nframes = hi[HI_nframes]; d.S = hi[HI_S]; d.P = hi[HI_P];
+    d.substeps = hi[HI_substeps]; d.iters = hi[HI_iterations]; d.maxc = hi[HI_max_contacts]; d.hot_start = hi[HI_hot_start];
+    d.ik_iters = hi[HI_ik_iters]; d.n_act = hi[HI_n_act]; d.n_obs = hi[HI_n_obs]; d.n_rew = hi[HI_n_rew]; d.n_term = hi[HI_n_term];
+    for (int k = HI_S_BPOS; k <= HI_S_ADDON; k++) d.so[k - HI_S_BPOS] = hi[k];
+    for (int k = HI_P_MASS; k <= HI_P_RESTQ; k++) d.po[k - HI_P_MASS] = hi[k];
+    d.dt = (float)hf[HF_dt]; d.g[0] = (float)hf[HF_gx]; d.g[1] = (float)hf[HF_gy]; d.g[2] = (float)hf[HF_gz];
+    d.erp = (float)hf[HF_erp]; d.cerp = (float)hf[HF_contact_erp]; d.slop = (float)hf[HF_linear_slop]; d.margin = (float)hf[HF_contact_margin];
+    d.ik_damping = (float)hf[HF_ik_damping]; d.ik_threshold = (float)hf[HF_ik_threshold]; d.max_joint_vel = (float)hf[HF_max_joint_vel];
+    d.limit_max_impulse = (float)hf[HF_limit_max_impulse]; d.ik_null_lambda_sq = (float)hf[HF_ik_null_lambda_sq];
+    d.team = team;
+
+    ints.clear(); floats.clear();
+    auto put_i = [&](int s) { size_t o = ints.size(); ints.insert(ints.end(), ibuf + sec_off(s), ibuf + sec_off(s) + sec_len(s)); ints.push_back(0); return o; };
+    auto put_f = [&](int s) { size_t o = floats.size(); const double* p = fbuf + sec_off(s); for (size_t i = 0; i < sec_len(s); i++) floats.push_back((float)p[i]); floats.push_back(0.f); return o; };
+    off.body_i = put_i(SEC_BODY_I); off.link_i = put_i(SEC_LINK_I); off.shape_i = put_i(SEC_SHAPE_I); off.pair_i = put_i(SEC_PAIR_I);
+    off.vis_i = put_i(SEC_VIS_I); off.op_i = put_i(SEC_OP_I); off.oparg_i = put_i(SEC_OPARG_I); off.cam_i = put_i(SEC_CAM_I);
+    off.body_f = put_f(SEC_BODY_F); off.link_f = put_f(SEC_LINK_F); off.shape_f = put_f(SEC_SHAPE_F); off.vis_f = put_f(SEC_VIS_F);
+    off.oparg_f = put_f(SEC_OPARG_F); off.cam_f = put_f(SEC_CAM_F); off.param_def = put_f(SEC_PARAM_DEFAULT); off.state_def = put_f(SEC_STATE_DEFAULT);
+
+    const int32_t* body_i = ibuf + sec_off(SEC_BODY_I);
+    const int32_t* link_i = ibuf + sec_off(SEC_LINK_I);
+    const int32_t* shape_i = ibuf + sec_off(SEC_SHAPE_I);
+    const double* shape_f = fbuf + sec_off(SEC_SHAPE_F);
+    const int32_t* vis_i = ibuf + sec_off(SEC_VIS_I);
+    const double* vis_f = fbuf + sec_off(SEC_VIS_F);
+    const int32_t* pair_i = ibuf + sec_off(SEC_PAIR_I);
+    const int32_t* op_i = ibuf + sec_off(SEC_OP_I);
+
+    // ---- plan tables ----
+    std::vector<int> dyn_body, body_plan((size_t)d.nb * BP_W, 0), frame_slot(d.nframes, -1), link_depth(std::max(d.nl, 1), 0), shape_slot(std::max(d.ns, 1), -1);
+    int nslot = 0, gv = 0, minv = 0, i0 = 0, nfloat = 0, GD = 1, max_depth = 0, max_nlb = 0;
+    for (int b = 0; b < d.nb; b++) {
+      const int32_t* bi = body_i + DG_BODY_I_W * b; int* bp = &body_plan[(size_t)b * BP_W];
+      int kind = bi[0], l0 = bi[1], nlb = bi[2], ndb = bi[4], baked = bi[7];
+      bp[BP_DI] = -1; bp[BP_SLOT] = -1; bp[BP_I0OFF] = -1; bp[BP_UROW] = 2 * bi[3];
+      if (kind != 0) {
+        bp[BP_DI] = (int)dyn_body.size(); dyn_body.push_back(b);
+        int gdim = (kind == 2 ? 6 : 0) + ndb;
+        bp[BP_GDIM] = gdim; bp[BP_GVOFF] = gv; bp[BP_MINVOFF] = minv; gv += gdim; minv += gdim * gdim; GD = std::max(GD, gdim);
+        if (kind == 2) { bp[BP_I0OFF] = 36 * nfloat; nfloat++; i0 += 36; }
+        max_nlb = std::max(max_nlb, nlb);
+      }
+      if (kind != 0 || !baked) {
+        bp[BP_SLOT] = nslot; frame_slot[b] = nslot++;
+        for (int k = 0; k < nlb; k++) frame_slot[d.nb + l0 + k] = nslot++;
+      }
+      int depth_b = 0;
+      for (int k = 0; k < nlb; k++) {
+        int pl = link_i[DG_LINK_I_W * (l0 + k) + 1];
+        link_depth[l0 + k] = pl < 0 ? 0 : link_depth[pl] + 1;
+        depth_b = std::max(depth_b, link_depth[l0 + k]);
+      }
+      bp[BP_DEPTH] = depth_b; max_depth = std::max(max_depth, depth_b);
+    }
+    int nshw = 0;
+    std::vector<float> shape_wb((size_t)std::max(d.ns, 1) * 12, 0.f), vis_wb((size_t)std::max(d.nv, 1) * 12, 0.f);
+    for (int s = 0; s < d.ns; s++) {
+      if (shape_i[DG_SHAPE_I_W * s + 3]) {
+        double m[9]; quat_to_mat(shape_f + DG_SHAPE_F_W * s + 15, m);
+        for (int i = 0; i < 9; i++) shape_wb[12 * s + i] = (float)m[i];
+        for (int i = 0; i < 3; i++) shape_wb[12 * s + 9 + i] = (float)shape_f[DG_SHAPE_F_W * s + 12 + i];
+      } else shape_slot[s] = nshw++;
+    }
+    for (int s = 0; s < d.nv; s++) if (vis_i[DG_VIS_I_W * s + 2]) {
+      double m[9]; quat_to_mat(vis_f + DG_VIS_F_W * s + 19, m);
+      for (int i = 0; i < 9; i++) vis_wb[12 * s + i] = (float)m[i];
+      for (int i = 0; i < 3; i++) vis_wb[12 * s + 9 + i] = (float)vis_f[DG_VIS_F_W * s + 16 + i];
+    }
+    std::vector<float> link_x((size_t)std::max(d.nl, 1) * 16, 0.f);
+    {
+      const double* link_f = fbuf + sec_off(SEC_LINK_F);
+      for (int gl = 0; gl < d.nl; gl++) {
+        const double* lf = link_f + DG_LINK_F_W * gl; int jt = link_i[DG_LINK_I_W * gl + 2];
+        double m[9]; quat_to_mat(lf, m);
+        for (int i = 0; i < 9; i++) link_x[16 * gl + i] = (float)m[i];
+        const double *a = lf + 10, *dd = lf + 7;
+        if (jt == 1) {
+          for (int i = 0; i < 3; i++) link_x[16 * gl + 9 + i] = (float)a[i];
+          link_x[16 * gl + 12] = (float)(a[1] * dd[2] - a[2] * dd[1]); link_x[16 * gl + 13] = (float)(a[2] * dd[0] - a[0] * dd[2]);
+          link_x[16 * gl + 14] = (float)(a[0] * dd[1] - a[1] * dd[0]);
+        } else if (jt == 2) for (int i = 0; i < 3; i++) link_x[16 * gl + 12 + i] = (float)a[i];
+      }
+    }
+    int GP = 1;
+    auto gdim_of_shape = [&](int s) { int b = shape_i[DG_SHAPE_I_W * s]; return body_plan[(size_t)b * BP_W + BP_GDIM]; };
+    for (int k = 0; k < d.npair; k++) GP = std::max(GP, gdim_of_shape(pair_i[2 * k]) + gdim_of_shape(pair_i[2 * k + 1]));
+    int n_ik = 0;
+    for (int k = 0; k < d.nop; k++) n_ik += op_i[DG_OP_I_W * k] == OP_IK_CTRL;
+
+    auto put_vi = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); ints.push_back(0); return o; };
+    auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };
+    off.dyn_body = put_vi(dyn_body); off.body_plan = put_vi(body_plan); off.frame_slot = put_vi(frame_slot);
+    off.link_depth = put_vi(link_depth); off.shape_slot = put_vi(shape_slot);
+    off.shape_wb = put_vf(shape_wb); off.vis_wb = put_vf(vis_wb); off.link_x = put_vf(link_x);
+    point(d, ints.data(), floats.data());
+
+    d.ndyn = (int)dyn_body.size(); d.nslot = nslot; d.nshw = nshw; d.nfloat = nfloat; d.GD = GD; d.GP = GP;
+    d.max_depth = max_depth; d.max_nlb = max_nlb; d.n_ik = n_ik;
+
+    // ---- workspace layout ----
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep 16-byte alignment of every region
+    d.W_HDR = take(WH_COUNT);
+    d.W_BST = take(13 * d.ndyn);
+    d.W_DOF = take(D_COUNT * d.nd);
+    d.W_EXT = take(6 * nslot);
+    d.W_KIN = take(18 * nslot);
+    d.W_LINK = take(19 * d.nl);
+    d.W_MINV = take(minv);
+    d.W_DV = take(gv);
+    d.W_I0 = take(i0);
+    d.W_UCNT = take(d.ndyn);
+    d.W_X = o;
+    // phase A (articulated-body algorithm)
+    int xa = 0;
+    auto takex = [&](int& x, int n) { int r = d.W_X + x; x += (n + 3) & ~3; return r; };
+    d.X_ABA = takex(xa, 39 * nslot);
+    d.X_LNK = takex(xa, 7 * d.nl);
+    d.X_I0T = takex(xa, 36 * nfloat);
+    // phase B (collision, rows, solver)
+    int xb = 0;
+    d.crow_stride = 2 * GP + CR_HDR;
+    d.ctmp_stride = 1 + 4 * CT_W;
+    d.mscr_stride = max_nlb + 6 * (max_depth + 2);
+    d.X_SHW = takex(xb, 12 * nshw);
+    d.X_CON = takex(xb, CT_W * d.maxc);
+    d.X_UROW = takex(xb, UR_W * 2 * d.nd);
+    d.X_SURV = takex(xb, (d.npair + 31) / 32 + 1);
+    int xb_rows = xb, xb_tmp = xb, xb_scr = xb;
+    d.X_CROW = takex(xb_rows, d.crow_stride * 3 * d.maxc);
+    d.X_CTMP = takex(xb_tmp, d.ctmp_stride * team);     // aliases the contact rows (rows are built after collision)
+    d.X_MSCR = takex(xb_scr, d.mscr_stride * team);     // aliases the contact rows (M^-1 columns precede the rows)
+    xb = std::max(xb_rows, std::max(xb_tmp, xb_scr));
+    // phase C (inverse kinematics scratch, used before the physics step)
+    int gj = 1;
+    for (int b = 0; b < d.nb; b++) gj = std::max(gj, (int)body_i[DG_BODY_I_W * b + 4]);
+    d.ik_stride = (9 * (max_depth + 2) + 6 * gj + std::max(gj * gj, 36) + 8 * gj + 32 + 3) & ~3;
+    int xc = d.ik_stride * std::min(team, std::max(n_ik, 1));
+    if (n_ik == 0) xc = 0;
+    d.w_total = d.W_X + std::max(xa, std::max(xb, xc));
+    return true;
+  }
+};
+
+}  // namespace dg
+#endif
