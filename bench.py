@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the DIYGym step path on B200(s): aggregate env-steps/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME] [--envs E] [--impl ours|reference]
+
+One step = one DIYGym.step for every environment (add-on update -> 2 x 1/480 s physics sub-steps with 150 solver
+sweeps -> observe/reward/terminal), synthetic uniform random actions.  Default workload = BASELINE.json configs[1]:
+examples/r2d2_maze (maze_size 10, 119 walls), 4096 environments per GPU.  Other configs: --config ur_high_5
+(8192/GPU), from_the_readme (4096/GPU, 200x200 camera every step), drone_pilot (4096/GPU), ur_high_5_randomised.
+
+Printed JSON line (rank 0):
+  value      whole-job env-steps/s, actions already resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the host-buffer C-ABI call dg_step_host (pinned host actions H2D, outputs D2H, per step)
+  roofline   dominant kernel dg_step_kernel against the measured HBM peak (algorithmic bytes per env-step from
+             DESIGN.md) plus, under "fp32", its oracle-counted flops against the measured FMA peak - the bound that
+             actually binds the physics-only configs
+  cpu_baseline  the CPU oracle (kind "port", this repo's fp64 restatement - pybullet is absent) on the host cores
+With --impl reference the oracle itself is the timed arm (all host threads, bounded sample).
+Under torchrun (--gpus N > 1) every rank owns its own N environments (no per-step collective, weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (yaml path, envs per GPU, action scale)
+    'r2d2_maze': ('examples/r2d2_maze/r2d2_maze.yaml', 4096),
+    'ur_high_5': ('examples/ur_high_5/ur_high_5.yaml', 8192),
+    'ur_high_5_randomised': ('examples/ur_high_5/ur_high_5_randomised.yaml', 8192),
+    'from_the_readme': ('examples/from_the_readme/from_the_readme.yaml', 4096),
+    'drone_pilot': ('examples/drone_pilot/drone_pilot.yaml', 4096),
+    'basic_env': ('examples/basic_env/basic_env.yaml', 4096),
+}
+METRIC = 'aggregate env-steps/sec'
+UNIT = 'env-steps/s'
+
+
+def action_ranges(env):
+    """(low, high) rows of the flattened device action buffer, from the add-on action spaces; the maze wheels get the
+    example's +-10 rad/s instead of the +-0.5 of the space."""
+    import numpy as np
+    n_act = env.scene['n_act']
+    lo, hi = np.zeros(n_act, np.float32), np.zeros(n_act, np.float32)
+    for op in env.builder.ops:
+        if op['n_act']:
+            lo[op['act_off']:op['act_off'] + op['n_act']] = -1.0
+            hi[op['act_off']:op['act_off'] + op['n_act']] = 1.0
+    for r in env.receptors.values():
+        for a in r.addons.values():
+            op = getattr(a, 'op', None)
+            if op is None or not op['n_act']:
+                continue
+            from diy_gym_b200.utils import flatten, get_bounds_for_space
+            l = np.asarray(flatten(get_bounds_for_space(a.action_space, True), batched=False), np.float32).reshape(-1)
+            h = np.asarray(flatten(get_bounds_for_space(a.action_space, False), batched=False), np.float32).reshape(-1)
+            if type(a).__name__ == 'JointController' and env.name == 'r2d2_maze':
+                l, h = l * 20.0, h * 20.0
+            lo[op['act_off']:op['act_off'] + op['n_act']] = l
+            hi[op['act_off']:op['act_off'] + op['n_act']] = h
+    return lo, hi
+
+
+def register_example_addons():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('drone_pilot_example', os.path.join(ROOT, 'examples', 'drone_pilot', 'drone_pilot.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, device):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(device), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace('.', '').isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 8:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[4:8]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_oracle_rate(scene, lo, hi, seconds=12.0, threads=None, seed=1234):
+    """env-steps/s of the fp64 CPU oracle (oracle/bullet_restatement.c, one world per environment, pthreads over
+    environments) on a bounded sample of the workload."""
+    import ctypes
+    import numpy as np
+    from oracle import oracle as orc
+    L = orc.lib()
+    threads = threads or L.dgo_batch_max_threads()
+    n_env = max(threads * 2, 8)
+    worlds = [orc.OracleWorld(scene, seed=seed, env_id=i) for i in range(n_env)]
+    arr = (ctypes.c_void_p * n_env)(*[w._w for w in worlds])
+    L.dgo_batch_reset(arr, n_env, threads)
+    h = scene.hdr
+    rng = np.random.default_rng(seed)
+    obs = np.zeros((n_env, max(h['n_obs'], 1)))
+    rew = np.zeros((n_env, max(h['n_rew'], 1)))
+    term = np.zeros((n_env, max(h['n_term'], 1)), np.uint8)
+    dp = ctypes.POINTER(ctypes.c_double)
+
+    def run(nsteps):
+        act = rng.uniform(lo, hi, (nsteps, n_env, h['n_act'])) if h['n_act'] else np.zeros((nsteps, n_env, 1))
+        t0 = time.perf_counter()
+        L.dgo_batch_step(arr, n_env, nsteps, act.ctypes.data_as(dp), h['n_act'], obs.ctypes.data_as(dp), h['n_obs'], rew.ctypes.data_as(dp),
+                         h['n_rew'], term.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), h['n_term'], threads)
+        return time.perf_counter() - t0
+    run(2)
+    # flop counter of the oracle (SURVEY 8d "algorithmic work"): single-threaded probe, the counter is not atomic
+    probe = orc.OracleWorld(scene, seed=seed, env_id=0)
+    probe.env_reset()
+    orc.flops(reset=True)
+    for _ in range(4):
+        probe.env_step(rng.uniform(lo, hi) if h['n_act'] else np.zeros(1))
+    flops_per_step = orc.flops(reset=True) / 4.0
+    t_probe = run(4)
+    nsteps = int(max(4, min(2000, seconds / max(t_probe / 4, 1e-6))))
+    dt = run(nsteps)
+    return {'value': n_env * nsteps / dt, 'unit': UNIT, 'cores': int(threads), 'kind': 'port',
+            'sample': '%d envs x %d steps of %s on %d threads (fp64 oracle; pybullet is not installed)' % (n_env, nsteps, h.get('name', 'the workload'), threads),
+            'flops_per_env_step': flops_per_step}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--config', default='r2d2_maze', choices=sorted(CONFIGS))
+    ap.add_argument('--envs', type=int, default=0, help='environments per GPU (default: the config\'s BASELINE.json size)')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--team', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world_size = int(os.environ.get('WORLD_SIZE', 1))
+    path, envs_default = CONFIGS[args.config]
+    n_envs = args.envs or envs_default
+    warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    register_example_addons()
+    from diy_gym_b200 import DIYGym
+    from diy_gym_b200.config import Configuration
+
+    cfg_workload = {'workload': '%s, %d envs/GPU, 2 sub-steps x 150 solver sweeps at 1/240 s, uniform random actions' % (args.config, n_envs),
+                    'envs_per_gpu': n_envs, 'parallelism': 'env-sharded x%d, no per-step collective' % max(args.gpus, 1)}
+
+    # ---------------------------------------------------------------- reference arm: the CPU oracle ----------------
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        env = DIYGym(Configuration.from_file(os.path.join(ROOT, path)), num_envs=1, compile_only=True)   # host-side scene compile only
+        lo, hi = action_ranges(env)
+        vals, base = [], None
+        for _ in range(warmup and 1):
+            cpu_oracle_rate(env.scene, lo, hi, seconds=1.0)
+        t0 = time.perf_counter()
+        per = min(8.0, 120.0 / max(args.steps, 1))
+        for _ in range(max(args.steps, 1)):
+            base = cpu_oracle_rate(env.scene, lo, hi, seconds=per)
+            vals.append(base['value'])
+            if time.perf_counter() - t0 > 150:
+                break
+        v = float(np.median(vals))
+        base['value'] = v
+        line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': warmup,
+                'ms_per_step': None, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': cfg_workload, 'cpu_baseline': base,
+                'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm ----------------------------------------
+    if world_size > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    env = DIYGym(os.path.join(ROOT, path), num_envs=n_envs, device=local_rank, seed=1234, team=args.team, env_id_offset=rank * n_envs)
+    w, sc = env.world, env.scene
+    lo_np, hi_np = action_ranges(env)
+    lo, hi = torch.from_numpy(lo_np).to(dev), torch.from_numpy(hi_np).to(dev)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_pool = 8   # pre-generated action batches, resident in HBM, cycled (different actions every step)
+    pool = [lo + (hi - lo) * torch.rand((n_envs, w.n_act), device=dev, generator=g) for _ in range(n_pool)] if w.n_act else None
+    user_addons = [a for r in env.receptors.values() for a in r.addons.values() if getattr(a, 'op', None) is None and a.action_space is not None]
+    cams = [a for r in env.receptors.values() for a in r.addons.values() if type(a).__name__ == 'Camera']
+    has_term = w.n_term > 0
+
+    def device_step(i):
+        if pool is not None:
+            w.action.copy_(pool[i % n_pool])
+        for a in user_addons:   # user add-ons (drone_pilot's propellors) run their batched torch update
+            a.update(torch.rand((n_envs, ) + tuple(a.action_space.shape), device=dev, generator=g))
+        w.step()
+        for c in cams:
+            w.render(c.cam)
+        if has_term:
+            w.reset(w.term.amax(dim=1))   # masked reset of finished episodes, no host sync
+
+    def barrier():
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(warmup):
+        device_step(i)
+    barrier()
+    l0 = w.launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    step_plain = w.step
+
+    def step_timed(i):
+        kev[i][0].record()
+        step_plain()
+        kev[i][1].record()
+    e0.record()
+    for i in range(args.steps):
+        w.step = lambda i=i: step_timed(i)      # CUDA events around the dominant kernel, on the launching stream
+        device_step(warmup + i)
+    e1.record()
+    w.step = step_plain
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = w.launches - l0
+    clocks = sampler.stop() if sampler else None
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))   # average launch duration inside the timed region
+
+    # ---- end to end through the host-buffer C-ABI call ----------------------------------------------------------
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+    act_h = pin((n_envs, max(w.n_act, 1)), torch.float32)[:, :w.n_act]
+    obs_h, rew_h, term_h = pin((n_envs, max(w.n_obs, 1)), torch.float32), pin((n_envs, max(w.n_rew, 1)), torch.float32), pin((n_envs, max(w.n_term, 1)), torch.uint8)
+    extra_h = torch.empty((n_envs, 13), dtype=torch.float32).pin_memory()
+    rng = np.random.default_rng(99 + rank)
+    host_pool = [(lo_np + (hi_np - lo_np) * rng.random((n_envs, w.n_act), dtype=np.float32)) for _ in range(4)] if w.n_act else None
+    cam_h = [(torch.empty(w.render(c.cam)[0].shape, dtype=torch.float32).pin_memory(), torch.empty(w.render(c.cam)[1].shape, dtype=torch.float32).pin_memory()) for c in cams]
+    h2d = n_envs * w.n_act * 4
+    d2h = n_envs * (w.n_obs * 4 + w.n_rew * 4 + w.n_term)
+    dyn_body = next((b for b in sc.bodies if b.kind != 0), sc.bodies[0])
+    o_pose = sc.hdr['S_BPOS'] + 3 * dyn_body.index
+    if d2h == 0:
+        d2h = n_envs * 3 * 4   # no sensor in this config: read back the robot's base position as the step's result
+    d2h += sum(int(a.numel() + b.numel()) * 4 for a, b in cam_h)
+
+    def host_step(i):
+        if host_pool is not None:
+            np.copyto(act_h, host_pool[i % 4])
+        for a in user_addons:
+            a.update(torch.rand((n_envs, ) + tuple(a.action_space.shape), device=dev, generator=g))
+        w.step_host(act_h if w.n_act else None, obs_h if w.n_obs else None, rew_h if w.n_rew else None, term_h if w.n_term else None)
+        if w.n_obs + w.n_rew + w.n_term == 0:
+            extra_h[:, :3].copy_(w.state[:, o_pose:o_pose + 3])
+        for c, (rh, dh) in zip(cams, cam_h):
+            r, d = w.render(c.cam)
+            rh.copy_(r, non_blocking=True)
+            dh.copy_(d, non_blocking=True)
+        if cams:
+            torch.cuda.synchronize(dev)
+        if has_term and term_h[:, :w.n_term].any():
+            w.reset(torch.from_numpy(term_h[:, :w.n_term].max(axis=1)))
+    for i in range(3):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = args.steps
+    for i in range(n_e2e):
+        host_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- max over ranks --------------------------------------------------------------------------------------------
+    stats = torch.tensor([ms_total, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_total, e2e_s, kernel_ms = [float(x) for x in stats.tolist()]
+    if rank != 0:
+        if world_size > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return 0
+
+    total_envs = n_envs * world_size
+    value = total_envs * args.steps / (ms_total * 1e-3)
+    e2e_v = total_envs * n_e2e / e2e_s
+
+    # ---- roofline of the dominant kernel (dg_step_kernel) ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    # algorithmic bytes per env-step (DESIGN.md "bytes per unit"): dynamic state read + written, action, outputs
+    dyn_state = sum(13 for b in sc.bodies if b.kind != 0) + 9 * sc['nd'] + 13 * sc['nl'] + 2
+    alg_bytes = 4 * (2 * dyn_state + w.n_act + w.n_obs + w.n_rew) + w.n_term
+    achieved = alg_bytes * n_envs / (kernel_ms * 1e-3) / 1e9
+    from diy_gym_b200.backend import measure_fp32_peak
+    fp32_peak = measure_fp32_peak(local_rank)
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_oracle_rate(sc, lo_np, hi_np)
+    flops = cpu['flops_per_env_step'] if cpu else None
+    roofline = {'bound': 'hbm', 'kernel': 'dg_step_kernel<%d>' % w.team, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback',
+                'algorithmic_bytes_per_env_step': alg_bytes, 'kernel_ms': kernel_ms,
+                'note': 'physics-only configs are bound by FP32 issue / latency, not HBM: see fp32'}
+    if flops:
+        tf = flops * n_envs / (kernel_ms * 1e-3) / 1e12
+        roofline['fp32'] = {'achieved': tf, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': tf / fp32_peak if fp32_peak else None,
+                            'flops_per_env_step': flops, 'peak_source': 'measured FMA micro-kernel (dg_measure_fp32_peak)'}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps, 'warmup': warmup,
+            'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': dict(cfg_workload, team=w.team, block_threads=w.block_threads, grid_blocks=w.grid_blocks,
+                                                smem_bytes=w.smem_bytes, l2_policy='per-step inputs cycle through 8 pre-generated action batches; state is re-read and re-written every step'),
+            'e2e': {'value': e2e_v, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'api': 'dg_step_host (pinned host buffers)'},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu}
+    print(json.dumps(line))
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -51,10 +51,23 @@ def load_library():
     L.dg_reset.argtypes = [vp, vp, vp]
     L.dg_render.restype = ctypes.c_int
     L.dg_render.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    L.dg_set_action_mask.restype = ctypes.c_int
+    L.dg_set_action_mask.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int]
     L.dg_step_host.restype = ctypes.c_int
     L.dg_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dg_measure_fp32_peak.restype = ctypes.c_int
+    L.dg_measure_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L
+
+
+def measure_fp32_peak(device=0):
+    """Non-tensor FP32 FMA rate of the device in TFLOP/s (measured by an FMA micro-kernel)."""
+    out = ctypes.c_double(0.0)
+    rc = load_library().dg_measure_fp32_peak(int(device), ctypes.byref(out))
+    if rc != 0:
+        raise RuntimeError('dg_measure_fp32_peak failed: %d' % rc)
+    return out.value
 
 
 class World:
@@ -122,6 +135,10 @@ class World:
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         self._check(self.L.dg_reset(self._h, ctypes.c_void_p(mask.data_ptr()) if mask is not None else None, self._stream()))
+
+    def set_action_mask(self, enabled):
+        m = np.ascontiguousarray(enabled, np.uint8)
+        self._check(self.L.dg_set_action_mask(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), m.size))
 
     def render(self, cam=0):
         w, hgt = self.cams[cam]

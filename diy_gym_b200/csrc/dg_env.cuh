@@ -29,6 +29,7 @@ struct Env {
   uint8_t* term;      // [n_term]
   uint32_t seed;
   int env_id;
+  unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
 };
 
 #define SC (*C.sc)
@@ -886,6 +887,7 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
   for (int k = 0; k < sc.nop; k++) {
     const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
     const float* a = op[3] >= 0 ? C.act + op[3] : nullptr;
+    if (k < 128 && !((C.opmask[k >> 6] >> (k & 63)) & 1ull)) { if (op[0] == OP_IK_CTRL) ik_seen++; continue; }
     if (op[0] == OP_JOINT_CTRL && ln == 0) {                 // joint_controller.py:40-58
       int mode = ia[0], n = ia[1];
       for (int i = 0; i < n; i++) {

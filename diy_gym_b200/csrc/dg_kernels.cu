@@ -20,6 +20,7 @@ namespace dg {
 struct LaunchArgs {
   float* state; float* param; const float* act; float* obs; float* rew; uint8_t* term;
   const uint8_t* mask; int n_envs; int mode; uint32_t seed; int env_off;
+  unsigned long long opmask[2];
 };
 
 template <int T>
@@ -30,7 +31,7 @@ __global__ void __launch_bounds__(128) dg_step_kernel(const __grid_constant__ De
   const unsigned lane = threadIdx.x & 31u;
   const unsigned tmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(unsigned)(T - 1)));
   Env C;
-  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.seed = a.seed;
+  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.seed = a.seed; C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
   for (int e = blockIdx.x * teams_per_block + team; e < a.n_envs; e += gridDim.x * teams_per_block) {
     if (a.mask != nullptr && a.mask[e] == 0) continue;
     C.st = a.state + (size_t)e * sc.S; C.pr = a.param + (size_t)e * sc.P;
@@ -164,6 +165,7 @@ struct DgWorld {
   DgBufferTable buf{};
   bool bound = false;
   uint32_t seed = 1234u; int env_off = 0;
+  unsigned long long opmask[2] = {~0ull, ~0ull};
   int64_t launches = 0;
   std::string err;
 };
@@ -279,6 +281,13 @@ int dg_set_seed(DgWorld* w, uint32_t seed, int env_id_offset) {
   return DG_OK;
 }
 
+int dg_set_action_mask(DgWorld* w, const uint8_t* op_enabled, int n_ops) {
+  if (!w || (n_ops > 0 && !op_enabled)) return DG_E_ARG;
+  w->opmask[0] = w->opmask[1] = ~0ull;
+  for (int k = 0; k < n_ops && k < 128; k++) if (!op_enabled[k]) w->opmask[k >> 6] &= ~(1ull << (k & 63));
+  return DG_OK;
+}
+
 int dg_init_state(DgWorld* w, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_init_state: buffers not bound"; return DG_E_UNBOUND; }
@@ -292,7 +301,7 @@ int dg_init_state(DgWorld* w, void* stream) {
 static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "buffers not bound"; return DG_E_UNBOUND; }
-  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off};
+  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}};
   CK(w, launch_any(w, a, (cudaStream_t)stream));
   return DG_OK;
 }
@@ -332,3 +341,40 @@ int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* r
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- FP32 FMA peak (roofline denominator) ------------
+namespace dg {
+__global__ void dg_fma_peak_kernel(float* out, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+  const float b = 0.999f, c = 1e-4f;
+  for (int i = 0; i < iters; i++) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+}  // namespace dg
+
+extern "C" int dg_measure_fp32_peak(int device, double* tflops_out) {
+  if (!tflops_out) return DG_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return DG_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return DG_E_CUDA;
+  const int blocks = prop.multiProcessorCount * 8, threads = 512, iters = 1 << 14;
+  float* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(float)) != cudaSuccess) return DG_E_CUDA;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0);
+    dg::dg_fma_peak_kernel<<<blocks, threads>>>(out, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(out); return DG_E_CUDA; }
+    float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+    double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops_out = best;
+  return DG_OK;
+}

@@ -64,6 +64,10 @@ int64_t dg_query(const DgWorld* w, int key);
 int dg_bind_buffers(DgWorld* w, const DgBufferTable* t);
 /* Per-environment RNG stream id = env_id_offset + local index (so results do not depend on the GPU count). */
 int dg_set_seed(DgWorld* w, uint32_t seed, int env_id_offset);
+/* Which action ops take part in the next dg_step calls: op_enabled[k] == 0 skips op k (HOST array, one byte per
+ * scene op).  Mirrors the reference's rule that only add-ons present in the action dict are updated
+ * (/root/reference/diy_gym/diy_gym.py:202-204).  Default: all enabled. */
+int dg_set_action_mask(DgWorld* w, const uint8_t* op_enabled, int n_ops);
 /* Fill state and parameter rows with the scene defaults (what loadURDF + resetBasePositionAndOrientation leave). */
 int dg_init_state(DgWorld* w, void* stream);
 
@@ -80,6 +84,9 @@ int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* strea
 /* Host-buffer form of dg_step (the reference-facing call when the caller keeps numpy arrays): copies the actions
  * host->device, steps, copies obs / reward / terminal device->host and waits.  Any output pointer may be NULL. */
 int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* reward_host, uint8_t* term_host, void* stream);
+
+/* Measured non-tensor FP32 FMA issue rate of the device in TFLOP/s (the physics kernels' compute roofline). */
+int dg_measure_fp32_peak(int device, double* tflops_out);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ struct EmulWorld {
   int n_envs, team;
   std::vector<float> state, param, ws;
   uint32_t seed = 1234u; int env_off = 0;
+  unsigned long long opmask[2] = {~0ull, ~0ull};
 };
 
 extern "C" {
@@ -35,12 +36,13 @@ void dge_destroy(EmulWorld* w) { delete w; }
 float* dge_state(EmulWorld* w) { return w->state.data(); }
 float* dge_param(EmulWorld* w) { return w->param.data(); }
 int dge_ws_floats(EmulWorld* w) { return w->hs.dev.w_total; }
+void dge_set_action_mask(EmulWorld* w, const uint8_t* en, int n) { w->opmask[0] = w->opmask[1] = ~0ull; for (int k = 0; k < n && k < 128; k++) if (!en[k]) w->opmask[k >> 6] &= ~(1ull << (k & 63)); }
 void dge_set_seed(EmulWorld* w, uint32_t seed, int env_off) { w->seed = seed; w->env_off = env_off; }
 static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* rew, uint8_t* term) {
   const DevScene& d = w->hs.dev; Env C;
   C.sc = &d; C.ws = w->ws.data(); C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
   C.act = act ? act + (size_t)e * d.n_act : nullptr; C.obs = obs + (size_t)e * d.n_obs; C.rew = rew + (size_t)e * d.n_rew;
-  C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e;
+  C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;
 }
 void dge_step(EmulWorld* w, const float* act, float* obs, float* rew, uint8_t* term) {

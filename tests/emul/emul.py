@@ -35,6 +35,7 @@ def lib():
         L.dge_ws_floats.restype = ctypes.c_int
         L.dge_ws_floats.argtypes = [vp]
         L.dge_set_seed.argtypes = [vp, ctypes.c_uint32, ctypes.c_int]
+        L.dge_set_action_mask.argtypes = [vp, u8, ctypes.c_int]
         L.dge_step.argtypes = [vp, fp, fp, fp, u8]
         L.dge_reset.argtypes = [vp, u8, fp, fp, u8]
         L.dge_physics.argtypes = [vp, ctypes.c_int]

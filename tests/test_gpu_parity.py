@@ -148,3 +148,105 @@ def test_library_fails_loudly_without_buffers_or_bad_scene():
     bad = np.zeros(64, np.int32)
     rc = L.dg_world_create(bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 64, np.zeros(4).ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 4, 1, 0, 0, ctypes.byref(h))
     assert rc == -2 and b'scene' in L.dg_last_error(None)
+
+
+# ---------------------------------------------------------------- through the public DIYGym API, every example ----
+import os  # noqa: E402
+
+EX = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'examples')
+
+
+def _env(name, n, **kw):
+    from diy_gym_b200 import DIYGym
+    return DIYGym(os.path.join(EX, name.split('/')[0], name.split('/')[-1] + '.yaml'), num_envs=n, device=0, **kw)
+
+
+@pytest.mark.parametrize('name,scale', [('ur_high_5', 0.01), ('ur_high_5/ur_high_5_randomised', 0.01), ('from_the_readme', 0.01),
+                                        ('r2d2_maze', 10.0), ('basic_env', 10.0)])
+def test_example_configs_reset_and_step_match_oracle(name, scale):
+    n = 6
+    env = _env(name, n, seed=77, env_id_offset=3)
+    sc, w = env.scene, env.world
+    oracles = [OracleWorld(sc, seed=77, env_id=3 + i) for i in range(n)]
+    outs = [o.env_reset() for o in oracles]
+    torch.cuda.synchronize()
+    assert np.allclose(w.obs.cpu().numpy(), np.stack([x[0] for x in outs]), rtol=1e-4, atol=2e-5)
+    assert np.allclose(w.param.cpu().numpy(), np.stack([o.param for o in oracles]), rtol=1e-5, atol=1e-7)
+    rng = np.random.default_rng(5)
+    nd, nb = sc['nd'], sc['nb']
+    for k in range(4):
+        _sync_state(w, oracles)
+        a = rng.uniform(-scale, scale, (n, max(sc['n_act'], 1)))[:, :sc['n_act']]
+        w.action.copy_(torch.from_numpy(a.astype(np.float32)))
+        w.step()
+        outs = [o.env_step(a[i]) for i, o in enumerate(oracles)]
+        torch.cuda.synchronize()
+        if nd:
+            q_o, qd_o = np.stack([o.s('S_Q', nd) for o in oracles]), np.stack([o.s('S_QD', nd) for o in oracles])
+            assert np.abs(w.s('S_Q', nd).cpu().numpy() - q_o).max() <= 1e-4 * max(np.abs(q_o).max(), 1.0)
+            assert np.abs(w.s('S_QD', nd).cpu().numpy() - qd_o).max() <= 2e-4 * max(np.abs(qd_o).max(), 1.0)
+        assert np.allclose(w.s('S_BPOS', 3 * nb).cpu().numpy(), np.stack([o.s('S_BPOS', 3 * nb) for o in oracles]), rtol=1e-4, atol=1e-5)
+        assert np.allclose(w.obs.cpu().numpy(), np.stack([x[0] for x in outs]), rtol=1e-4, atol=1e-4)
+        assert np.allclose(w.reward.cpu().numpy(), np.stack([x[1] for x in outs]), rtol=1e-3, atol=1e-4)
+        assert np.array_equal(w.term.cpu().numpy(), np.stack([x[2] for x in outs]))
+    env.close()
+
+
+def test_camera_kernel_matches_oracle_ray_cast():
+    """Depth within 1e-5 relative on primitive scenes, rgb within fp32 shading error, both cameras."""
+    for name in ('basic_env', 'from_the_readme'):
+        env = _env(name, 2)
+        o = OracleWorld(env.scene, env_id=0)
+        o.env_reset()
+        _sync_state(env.world, [o, o])
+        rgb, depth = env.world.render(0)
+        torch.cuda.synchronize()
+        rgb_o, depth_o = o.render(0)
+        d = depth.cpu().numpy()[0]
+        close = np.isclose(d, depth_o, rtol=1e-4, atol=1e-5)
+        assert close.mean() > 0.999, (name, close.mean())            # silhouette pixels may flip between fp32 / fp64
+        same = close[..., None] & np.ones(3, bool)
+        assert np.abs(rgb.cpu().numpy()[0] - rgb_o)[same].max() < 2e-3
+        assert torch.equal(rgb[0], rgb[1])
+        env.close()
+
+
+def test_drone_pilot_user_addons_on_device():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('drone_pilot_example', os.path.join(EX, 'drone_pilot', 'drone_pilot.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    env = _env('drone_pilot', 32)
+    obs = env.reset()
+    full = {'drone': {'motor%d' % (i + 1): torch.full((32, 1), 1.5, device='cuda') for i in range(4)}}
+    for _ in range(150):
+        obs, rew, term, _ = env.step(full)
+    assert float(obs['drone']['pose']['position'][:, 2].min()) > 1.0
+    assert obs['target']['pose']['position'].device.type == 'cuda' and term.shape == (32, )
+    env.close()
+
+
+def test_full_size_properties_ur_high_5_8192():
+    """BASELINE.json size (8192 envs): size-independent properties - identical environments stay bit-identical,
+    quaternions stay unit, nothing is NaN, per-environment results do not depend on the batch they ran in."""
+    env = _env('ur_high_5', 8192)
+    g = torch.Generator(device='cuda').manual_seed(0)
+    small = _env('ur_high_5', 16)
+    for k in range(5):
+        a = env.sample_action(g)
+        a['ur5_l']['controller']['linear'][1::2] = a['ur5_l']['controller']['linear'][0::2]   # pairs of twins
+        a['ur5_l']['controller']['rotation'][1::2] = a['ur5_l']['controller']['rotation'][0::2]
+        a['ur5_r']['controller']['linear'][1::2] = a['ur5_r']['controller']['linear'][0::2]
+        a['ur5_r']['controller']['rotation'][1::2] = a['ur5_r']['controller']['rotation'][0::2]
+        obs, rew, term, _ = env.step(a)
+        sub = {r: {c: {k2: v[:16] for k2, v in d.items()} for c, d in x.items()} for r, x in a.items()}
+        small.step(sub)
+    torch.cuda.synchronize()
+    st = env.world.state
+    assert torch.isfinite(st).all()
+    assert torch.equal(st[0::2], st[1::2])
+    lq = env.world.s('S_LQUAT', 4 * env.scene['nl']).reshape(8192, -1, 4)
+    assert (lq.norm(dim=2) - 1).abs().max() < 1e-5
+    assert torch.equal(st[:16], small.world.state)
+    env.close()
+    small.close()

@@ -1,0 +1,118 @@
+"""The device step code (csrc/dg_env.cuh), compiled for the CPU by tests/emul, against the fp64 oracle on every
+example scene: reset, single steps from identical states, per-environment random streams, team-size invariance.
+These are the same comparisons the `-m gpu` tests run through the C ABI on the B200."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from diy_gym_b200 import DIYGym
+from oracle.oracle import OracleWorld
+from tests.emul.emul import EmulWorld
+from tests.emul.world import factory
+
+EX = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'examples')
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+
+
+def scene_of(name, n=1):
+    return DIYGym(os.path.join(EX, name.split('/')[0], name.split('/')[-1] + '.yaml'), num_envs=n, world_factory=factory()).scene
+
+
+def action_batch(sc, rng, n, scale):
+    return rng.uniform(-scale, scale, (n, max(sc['n_act'], 1)))[:, :sc['n_act']]
+
+
+@pytest.mark.parametrize('name,scale,team', [('ur_high_5', 0.01, 1), ('ur_high_5', 0.01, 8), ('ur_high_5/ur_high_5_randomised', 0.01, 4),
+                                             ('from_the_readme', 0.01, 4), ('r2d2_maze', 10.0, 4), ('basic_env', 10.0, 2)])
+def test_reset_and_single_steps_match_oracle(name, scale, team):
+    sc = scene_of(name)
+    n = 3
+    e = EmulWorld(sc, n, team, seed=77, env_off=5)
+    oracles = [OracleWorld(sc, seed=77, env_id=5 + i) for i in range(n)]
+    obs_e, rew_e, term_e = e.reset()
+    outs = [o.env_reset() for o in oracles]
+    assert np.allclose(obs_e, np.stack([x[0] for x in outs]), rtol=1e-4, atol=2e-5)
+    assert np.allclose(e.param, np.stack([o.param for o in oracles]), rtol=1e-5, atol=1e-7)   # randomised parameters
+    rng = np.random.default_rng(1)
+    nd, nb = sc['nd'], sc['nb']
+    for k in range(4):
+        for i, o in enumerate(oracles):
+            e.state[i, :] = o.state
+        a = action_batch(sc, rng, n, scale)
+        obs_e, rew_e, term_e = e.step(a)
+        outs = [o.env_step(a[i]) for i, o in enumerate(oracles)]
+        for i, o in enumerate(oracles):
+            if nd:
+                assert np.abs(e.s('S_Q', nd, i) - o.s('S_Q', nd)).max() <= 1e-4 * max(np.abs(o.s('S_Q', nd)).max(), 1.0)
+                assert np.abs(e.s('S_QD', nd, i) - o.s('S_QD', nd)).max() <= 2e-4 * max(np.abs(o.s('S_QD', nd)).max(), 1.0)
+            assert np.allclose(e.s('S_BPOS', 3 * nb, i), o.s('S_BPOS', 3 * nb), rtol=1e-4, atol=1e-5)
+            assert np.allclose(e.s('S_BQUAT', 4 * nb, i), o.s('S_BQUAT', 4 * nb), rtol=1e-4, atol=1e-5)
+        assert np.allclose(obs_e, np.stack([x[0] for x in outs]), rtol=1e-4, atol=1e-4)
+        assert np.allclose(rew_e, np.stack([x[1] for x in outs]), rtol=1e-3, atol=1e-4)
+        assert np.array_equal(term_e, np.stack([x[2] for x in outs]))
+
+
+def test_team_size_does_not_change_results():
+    sc = scene_of('from_the_readme')
+    rng = np.random.default_rng(2)
+    acts = [action_batch(sc, rng, 2, 0.01) for _ in range(3)]
+    ref = None
+    for team in (1, 2, 8, 32):
+        e = EmulWorld(sc, 2, team)
+        e.reset()
+        for a in acts:
+            out = e.step(a)
+        cur = (e.state.copy(), out[0].copy(), out[1].copy())
+        if ref is None:
+            ref = cur
+        else:
+            for x, y in zip(ref, cur):
+                assert np.array_equal(x, y)
+
+
+def test_respawn_streams_depend_on_global_env_id_only():
+    """Environment g gets the same random pose whether it is local index g on one GPU or index 0 on another rank."""
+    sc = scene_of('drone_pilot') if False else scene_of('basic_env')
+    sc = DIYGym(os.path.join(EX, 'ur_high_5', 'ur_high_5_randomised.yaml'), num_envs=1, world_factory=factory()).scene
+    a = EmulWorld(sc, 4, 2, seed=9, env_off=0)
+    b = EmulWorld(sc, 2, 2, seed=9, env_off=2)
+    a.reset()
+    b.reset()
+    assert np.array_equal(a.state[2:4], b.state) and np.array_equal(a.param[2:4], b.param)
+    assert not np.array_equal(a.state[0], a.state[1])
+
+
+def test_contacts_r2d2_against_wall_short_horizon():
+    sc = scene_of('r2d2_maze')
+    e = EmulWorld(sc, 1, 4)
+    o = OracleWorld(sc)
+    e.reset()
+    o.env_reset()
+    a = np.array([[8.0, 8.0, 10.0, 10.0]])
+    hit = 0
+    for k in range(90):
+        oe = e.step(a)
+        oo = o.env_step(a[0])
+        hit = max(hit, len(o.contacts()))
+    assert hit >= 4                                            # wheels on the ground (+ walls)
+    assert np.allclose(e.s('S_BPOS', 6)[3:], o.s('S_BPOS', 6)[3:], atol=2e-3)
+    assert np.allclose(e.s('S_QD', sc['nd']), o.s('S_QD', sc['nd']), rtol=2e-2, atol=2e-2)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """libdiygym_b200.so loads on a GPU-less host and exports every function include/diygym_b200.h declares."""
+    from diy_gym_b200.build import build_library
+    lib = ctypes.CDLL(build_library())
+    header = open(os.path.join(ROOT, 'include', 'diygym_b200.h')).read()
+    names = sorted(set(re.findall(r'\b(dg_[a-z_]+)\s*\(', header)))
+    assert len(names) >= 12
+    for nme in names:
+        assert hasattr(lib, nme), nme
+    # argument checking works without a device
+    lib.dg_last_error.restype = ctypes.c_char_p
+    assert lib.dg_world_create(None, 0, None, 0, 1, 0, 0, None) == -1
+    assert b'bad argument' in lib.dg_last_error(None)
