@@ -345,6 +345,10 @@ class SceneBuilder:
             cam_f[k, 0:3], cam_f[k, 3:7] = c['xyz'], c['quat']
             cam_f[k, 7:10] = [c['fov'], c['near'], c['far']]
 
+        # contact-point capacity per environment (extension key `max_contacts`): floating bodies rest on several
+        # points at once, fixed-base arms only touch occasionally - their scenes keep the solver workspace small
+        if self.max_contacts <= 0:
+            self.max_contacts = 16 if any(b.kind == 2 for b in B) else 8
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
                    max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn)

@@ -20,29 +20,49 @@ namespace dg {
 
 struct Env {
   const DevScene* sc;
-  float* ws;          // team workspace (shared memory on the GPU)
+  float* ws;          // team workspace, hot part (shared memory on the GPU)
+  float* wg;          // team workspace, cold part (global memory, L1/L2 resident); regions with a negative offset live here
   float* st;          // this environment's state row  [S]
   float* pr;          // this environment's parameter row [P]
   const float* act;   // [n_act]
   float* obs;         // [n_obs]
   float* rew;         // [n_rew]
   uint8_t* term;      // [n_term]
+  const int* link_i;  // link tables: the scene's global arrays, or the block's shared-memory copies on the GPU
+  const float* link_f;
+  const float* link_x;
   uint32_t seed;
   int env_id;
   unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
 };
 
 #define SC (*C.sc)
-#define WSI(C) ((int*)(C).ws)
-#define KIN(s) (C.ws + SC.W_KIN + 18 * (s))
-#define LNK(gl) (C.ws + SC.W_LINK + 19 * (gl))
-#define ABA(s) (C.ws + SC.X_ABA + 39 * (s))
-#define LNX(gl) (C.ws + SC.X_LNK + 7 * (gl))
-#define DOF(k, d) (C.ws[SC.W_DOF + (k) * SC.nd + (d)])
-#define BST(di) (C.ws + SC.W_BST + 13 * (di))
-#define EXT(s) (C.ws + SC.W_EXT + 6 * (s))
-#define ST(name) (C.st + DG_SO(C.sc, name))
-#define PR(name) (C.pr + DG_PO(C.sc, name))
+// Address-space hints: regions with a fixed home are addressed through pointers the compiler knows to be shared /
+// global (LDS / LDG instead of generic loads); only the contact regions, whose home is chosen per scene, stay generic.
+#if defined(__CUDA_ARCH__)
+DG_HD float* as_shared(float* p) { __builtin_assume(__isShared(p)); return p; }
+DG_HD float* as_global(float* p) { __builtin_assume(__isGlobal(p)); return p; }
+template <class P> DG_HD const P* gc(const P* p) { __builtin_assume(__isGlobal(p)); return p; }
+template <class P> DG_HD const P* shc(const P* p) { __builtin_assume(__isShared(p)); return p; }
+#else
+DG_HD float* as_shared(float* p) { return p; }
+DG_HD float* as_global(float* p) { return p; }
+template <class P> DG_HD const P* gc(const P* p) { return p; }
+template <class P> DG_HD const P* shc(const P* p) { return p; }
+#endif
+#define WSH(C, off) (as_shared((C).ws) + (off))
+#define WSG(C, off) (as_global((C).wg) + (off))
+#define WSI(C) ((int*)as_shared((C).ws))
+#define WSP(C, off) ((off) >= 0 ? (C).ws + (off) : (C).wg + ~(off))
+#define WSIP(C, off) ((int*)WSP(C, off))
+#define KIN(s) (WSG(C, SC.W_KIN) + 12 * (s))
+#define LNK(gl) (WSG(C, SC.W_LINK) + 19 * (gl))
+#define ABA(s) (WSG(C, SC.X_ABA) + 45 * (s))   // pA6 IA27 acc6 w3 v3
+#define LNX(gl) (WSG(C, SC.X_LNK) + 7 * (gl))
+#define DOF(k, d) (as_shared(C.ws)[SC.W_DOF + (k) * SC.nd + (d)])
+#define BST(di) (WSH(C, SC.W_BST) + 13 * (di))
+#define ST(name) (as_global(C.st) + DG_SO(C.sc, name))
+#define PR(name) (as_global(C.pr) + DG_PO(C.sc, name))
 
 DG_HD float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 DG_HD int float_as_int(float f) { union { float f; int i; } u; u.f = f; return u.i; }
@@ -53,7 +73,7 @@ DG_HD float int_as_float(int i) { union { float f; int i; } u; u.i = i; return u
 DG_FN void phase_load(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   for (int i = ln; i < 13 * sc.ndyn; i += nt) {
-    int di = i / 13, k = i - 13 * di, b = sc.dyn_body[di];
+    int di = i / 13, k = i - 13 * di, b = gc(sc.dyn_body)[di];
     float v;
     if (k < 3) v = ST(S_BPOS)[3 * b + k];
     else if (k < 7) v = ST(S_BQUAT)[4 * b + k - 3];
@@ -63,30 +83,22 @@ DG_FN void phase_load(const Env& C, int ln, int nt) {
   }
   for (int d = ln; d < sc.nd; d += nt) {
     float qd = ST(S_QD)[d];
-    DOF(D_Q, d) = ST(S_Q)[d]; DOF(D_QD, d) = qd; DOF(D_KP, d) = ST(S_MKP)[d]; DOF(D_KD, d) = ST(S_MKD)[d];
-    DOF(D_TPOS, d) = ST(S_MTPOS)[d]; DOF(D_TVEL, d) = ST(S_MTVEL)[d]; DOF(D_MAXF, d) = ST(S_MMAXF)[d];
-    DOF(D_APPLIED, d) = ST(S_MAPPLIED)[d]; DOF(D_JTQ, d) = ST(S_JTORQUE)[d];
-    DOF(D_TDAMP, d) = -PR(P_JDAMP)[d] * qd;   // joint damping torque, evaluated once per outer step
-    DOF(D_QDD, d) = 0.f;
+    DOF(D_Q, d) = ST(S_Q)[d]; DOF(D_QD, d) = qd; DOF(D_APPLIED, d) = ST(S_MAPPLIED)[d];
+    DOF(D_TAU, d) = ST(S_JTORQUE)[d] - PR(P_JDAMP)[d] * qd;   // applied torque + joint damping, evaluated once per outer step
   }
-  for (int f = ln; f < sc.nframes; f += nt) {
-    int s = sc.frame_slot[f];
-    if (s < 0) continue;
-    float* e = EXT(s);
-    for (int i = 0; i < 3; i++) { e[i] = ST(S_EXTF)[3 * f + i]; e[3 + i] = ST(S_EXTT)[3 * f + i]; }
-    if (f < sc.nb && sc.body_i[DG_BODY_I_W * f] == 0) {   // static body with a per-environment pose
-      float* K = KIN(s);
-      q_to_mat(K, ST(S_BQUAT) + 4 * f); v_cpy(K + 9, ST(S_BPOS) + 3 * f);
-      v_set(K + 12, 0, 0, 0); v_set(K + 15, 0, 0, 0);
-    }
+  for (int f = ln; f < sc.nb; f += nt) {
+    int s = gc(sc.frame_slot)[f];
+    if (s < 0 || gc(sc.body_i)[DG_BODY_I_W * f] != 0) continue;
+    float* K = KIN(s);                                        // static body with a per-environment pose
+    q_to_mat(K, ST(S_BQUAT) + 4 * f); v_cpy(K + 9, ST(S_BPOS) + 3 * f);
   }
   if (ln == 0) for (int i = 0; i < WH_COUNT; i++) WSI(C)[sc.W_HDR + i] = 0;
 }
 
 // ------------------------------------------------------------------ kinematics ---------------------------------
 // joint transform of link gl at coordinate q:  E = child_from_parent rotation, r = child COM in parent coordinates
-DG_FN void joint_xform(const DevScene& sc, int gl, float q, float* E, float* r) {
-  const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl; const float* R0 = sc.link_x + 16 * gl;
+DG_FN void joint_xform(const Env& C, int gl, float q, float* E, float* r) {
+  const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl; const float* R0 = shc(C.link_x) + 16 * gl;
   float Rrel[9], tmp[3];
   if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
   else if (li[2] == 2) { m_cpy(Rrel, R0); float dd[3] = {lf[7] + lf[10] * q, lf[8] + lf[11] * q, lf[9] + lf[12] * q}; m_vec(tmp, R0, dd); }
@@ -99,26 +111,26 @@ DG_HD int parent_slot(const int* li, int l0, int s0) { return li[1] < 0 ? s0 : s
 // world pose and body-frame spatial velocity of every frame of dynamic body b
 DG_FN void fk_vel_body(const Env& C, int b) {
   const DevScene& sc = SC;
-  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
   int l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT];
   const float* bs = BST(bp[BP_DI]);
-  float* K0 = KIN(s0);
+  float* K0 = KIN(s0); float* V0 = ABA(s0) + 39;
   q_to_mat(K0, bs + 3); v_cpy(K0 + 9, bs);
-  mT_vec(K0 + 12, K0, bs + 10); mT_vec(K0 + 15, K0, bs + 7);
+  mT_vec(V0, K0, bs + 10); mT_vec(V0 + 3, K0, bs + 7);
   for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lx = sc.link_x + 16 * gl;
-    float* L = LNK(gl); float* K = KIN(s0 + 1 + k); const float* Kp = KIN(parent_slot(li, l0, s0));
+    int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lx = shc(C.link_x) + 16 * gl;
+    float* L = LNK(gl); float* K = KIN(s0 + 1 + k); const int psl = parent_slot(li, l0, s0); const float* Kp = KIN(psl); const float* Vp = ABA(psl) + 39;
     int dof = li[3];
     float E[9], r[3], t[3], t2[3];
-    joint_xform(sc, gl, dof >= 0 ? DOF(D_Q, dof) : 0.f, E, r);
+    joint_xform(C, gl, dof >= 0 ? DOF(D_Q, dof) : 0.f, E, r);
     m_cpy(L, E); v_cpy(L + 9, r);
     float Rw[9]; m_mulT(Rw, Kp, E); m_cpy(K, Rw);
     m_vec(t, Kp, r); v_add(K + 9, Kp + 9, t);
     float w[3], v[3];
-    m_vec(w, E, Kp + 12);
-    v_cross(t, Kp + 12, r); v_add(t2, Kp + 15, t); m_vec(v, E, t2);
+    m_vec(w, E, Vp);
+    v_cross(t, Vp, r); v_add(t2, Vp + 3, t); m_vec(v, E, t2);
     if (dof >= 0) { float qd = DOF(D_QD, dof); v_madd(w, lx + 9, qd); v_madd(v, lx + 12, qd); }
-    v_cpy(K + 12, w); v_cpy(K + 15, v);
+    float* V = ABA(s0 + 1 + k) + 39; v_cpy(V, w); v_cpy(V + 3, v);
   }
 }
 
@@ -147,7 +159,7 @@ DG_FN int invert_small(float* M, int n, float* inv) {
 // forward dynamics of dynamic body b, then the velocity half of the semi-implicit Euler step
 DG_FN void aba_body(const Env& C, int b, float h) {
   const DevScene& sc = SC;
-  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
   int kind = bi[0], l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT], di = bp[BP_DI];
   const float *mass = PR(P_MASS), *inertia = PR(P_INERTIA);
   float kl = PR(P_LINDAMP)[b], ka = PR(P_ANGDAMP)[b];
@@ -156,14 +168,14 @@ DG_FN void aba_body(const Env& C, int b, float h) {
     int s = s0 + 1 + k, f = k < 0 ? b : sc.nb + l0 + k;
     float* X = ABA(s);
     if (k < 0 && kind != 2) { for (int i = 0; i < 33; i++) X[i] = 0.f; continue; }
-    const float* K = KIN(s); const float *w = K + 12, *v = K + 15; const float* e = EXT(s);
+    const float* K = KIN(s); const float *w = X + 39, *v = X + 42; const float* ef = ST(S_EXTF) + 3 * f; const float* et = ST(S_EXTT) + 3 * f;
     float m = mass[f]; const float* I = inertia + 3 * f;
     float Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]}, t[3], fw[3], pa[3], pl[3];
     v_cross(pa, w, Iw);
     v_cross(t, w, v); v_scale(pl, t, m);
-    fw[0] = sc.g[0] * m + e[0]; fw[1] = sc.g[1] * m + e[1]; fw[2] = sc.g[2] * m + e[2];
+    fw[0] = sc.g[0] * m + ef[0]; fw[1] = sc.g[1] * m + ef[1]; fw[2] = sc.g[2] * m + ef[2];
     mT_vec(t, K, fw); v_sub(pl, pl, t);
-    mT_vec(t, K, e + 3); v_sub(pa, pa, t);
+    mT_vec(t, K, et); v_sub(pa, pa, t);
     float wn = v_len(w), vn = v_len(v);
     v_madd(pa, Iw, ka + ka * wn);
     float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, kl + kl * vn);
@@ -171,9 +183,9 @@ DG_FN void aba_body(const Env& C, int b, float h) {
     for (int i = 6; i < 33; i++) X[i] = 0.f;
     X[6] = I[0]; X[10] = I[1]; X[14] = I[2]; X[24] = m; X[28] = m; X[32] = m;
     if (k >= 0) {
-      int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; float* c = LNX(gl);
+      int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; float* c = LNX(gl);
       if (li[3] >= 0) {
-        const float* lx = sc.link_x + 16 * gl;
+        const float* lx = shc(C.link_x) + 16 * gl;
         float qd = DOF(D_QD, li[3]), sa[3], sl[3], t2[3];
         v_scale(sa, lx + 9, qd); v_scale(sl, lx + 12, qd);
         v_cross(c, w, sa); v_cross(c + 3, w, sl); v_cross(t2, v, sa); v_add(c + 3, c + 3, t2);
@@ -182,17 +194,17 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   }
   // pass 2: articulated inertias, leaves to root
   for (int k = nlb - 1; k >= 0; k--) {
-    int gl = l0 + k, s = s0 + 1 + k; const int* li = sc.link_i + DG_LINK_I_W * gl;
+    int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
     int ps = parent_slot(li, l0, s0);
     float* X = ABA(s); float* L = LNK(gl); float* cx = LNX(gl);
     float Aa[9], Ba[9], Ca[9], pa[6], n[3], fo[3];
     m_cpy(Aa, X + 6); m_cpy(Ba, X + 15); m_cpy(Ca, X + 24);
     if (li[3] >= 0) {
-      const float* lx = sc.link_x + 16 * gl; const float *sa = lx + 9, *sl = lx + 12;
+      const float* lx = shc(C.link_x) + 16 * gl; const float *sa = lx + 9, *sl = lx + 12;
       float U[6];
       ia_mul(Aa, Ba, Ca, sa, sl, U, U + 3);
       float D = v_dot(sa, U) + v_dot(sl, U + 3);
-      float tau = DOF(D_JTQ, li[3]) + DOF(D_TDAMP, li[3]);
+      float tau = DOF(D_TAU, li[3]);
       float uu = tau - (v_dot(sa, X) + v_dot(sl, X + 3));
       for (int i = 0; i < 6; i++) L[12 + i] = U[i];
       L[18] = D; cx[6] = uu;
@@ -222,7 +234,7 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   // base acceleration
   float* X0 = ABA(s0); float* a0 = X0 + 33;
   if (kind == 2) {
-    float* M = C.ws + sc.X_I0T + bp[BP_I0OFF]; float* Iv = C.ws + sc.W_I0 + bp[BP_I0OFF];
+    float* M = WSG(C, sc.X_I0T) + bp[BP_I0OFF]; float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
     const float *A = X0 + 6, *B = X0 + 15, *Cm = X0 + 24;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { M[6 * i + j] = A[3 * i + j]; M[6 * i + 3 + j] = B[3 * i + j]; M[6 * (3 + i) + j] = B[3 * j + i]; M[6 * (3 + i) + 3 + j] = Cm[3 * i + j]; }
     invert_small(M, 6, Iv);
@@ -230,15 +242,15 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
   // pass 3: accelerations, root to leaves
   for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k, s = s0 + 1 + k; const int* li = sc.link_i + DG_LINK_I_W * gl;
+    int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
     const float* L = LNK(gl); const float* cx = LNX(gl); const float* ap = ABA(parent_slot(li, l0, s0)) + 33;
     float* a = ABA(s) + 33; float t[3], t2[3], aa[3], al[3];
     m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
     v_add(aa, aa, cx); v_add(al, al, cx + 3);
     if (li[3] >= 0) {
-      const float* lx = sc.link_x + 16 * gl;
+      const float* lx = shc(C.link_x) + 16 * gl;
       float qdd = (cx[6] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
-      DOF(D_QDD, li[3]) = qdd;
+      DOF(D_QD, li[3]) += h * qdd;            // velocity half of the semi-implicit Euler step
       v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
     }
     v_cpy(a, aa); v_cpy(a + 3, al);
@@ -246,36 +258,36 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   // velocity update
   if (kind == 2) {
     const float* K0 = KIN(s0); float* bs = BST(di); float t[3], lin[3], aw[3];
-    v_cross(t, K0 + 12, K0 + 15); v_add(lin, a0 + 3, t);
+    v_cross(t, X0 + 39, X0 + 42); v_add(lin, a0 + 3, t);
     m_vec(aw, K0, a0); v_madd(bs + 10, aw, h);
     m_vec(aw, K0, lin); v_madd(bs + 7, aw, h);
   }
-  for (int i = 0; i < bi[4]; i++) DOF(D_QD, bi[3] + i) += h * DOF(D_QDD, bi[3] + i);
 }
 
 DG_FN void phase_dynamics(const Env& C, int ln, int nt, float h) {
-  for (int di = ln; di < SC.ndyn; di += nt) { int b = SC.dyn_body[di]; fk_vel_body(C, b); aba_body(C, b, h); }
+  for (int di = ln; di < SC.ndyn; di += nt) { int b = gc(SC.dyn_body)[di]; fk_vel_body(C, b); aba_body(C, b, h); }
 }
 
 // One column of M^-1 of body b: response of the generalized velocity to a unit generalized impulse at coordinate col.
 // Coordinates: floating bodies [torque_world(3), force_world(3), joints...], fixed-base bodies [joints...].
 DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
   const DevScene& sc = SC;
-  const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
-  int kind = bi[0], l0 = bi[1], nlb = bi[2], d0 = bi[3], s0 = bp[BP_SLOT], g = bp[BP_GDIM];
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
+  int kind = bi[0], l0 = bi[1], nlb = bi[2], d0 = bi[3], s0 = bp[BP_SLOT], g = bp[BP_GDIM], gs = bp[BP_GS];
   int jo = kind == 2 ? 6 : 0;
-  float* out = C.ws + sc.W_MINV + bp[BP_MINVOFF] + col * g;
+  float* out = WSH(C, sc.W_MINV) + bp[BP_MINVOFF] + col * gs;
+  for (int i = g; i < gs; i++) out[i] = 0.f;
   float* uu = scr; float* ast = scr + sc.max_nlb;   // a-stack indexed by depth+1 (0 = base)
   for (int k = 0; k < nlb; k++) uu[k] = 0.f;
   float p[6] = {0, 0, 0, 0, 0, 0};
   if (col >= jo) {
     int k0 = -1;
-    for (int k = 0; k < nlb; k++) if (sc.link_i[DG_LINK_I_W * (l0 + k) + 3] == d0 + col - jo) { k0 = k; break; }
+    for (int k = 0; k < nlb; k++) if (shc(C.link_i)[DG_LINK_I_W * (l0 + k) + 3] == d0 + col - jo) { k0 = k; break; }
     for (int k = k0; k >= 0;) {
-      int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* L = LNK(gl);
+      int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* L = LNK(gl);
       float pa[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
       if (li[3] >= 0) {
-        const float* lx = sc.link_x + 16 * gl;
+        const float* lx = shc(C.link_x) + 16 * gl;
         float u1 = (k == k0 ? 1.f : 0.f) - (v_dot(lx + 9, pa) + v_dot(lx + 12, pa + 3));
         uu[k] = u1; float s = u1 / L[18];
         for (int i = 0; i < 6; i++) pa[i] += L[12 + i] * s;
@@ -288,7 +300,7 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
   }
   float* a0 = ast;
   if (kind == 2) {
-    const float* K0 = KIN(s0); const float* Iv = C.ws + sc.W_I0 + bp[BP_I0OFF];
+    const float* K0 = KIN(s0); const float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
     float gen[6] = {0, 0, 0, 0, 0, 0}, rhs[6], t[3];
     if (col < 6) gen[col] = 1.f;
     mT_vec(t, K0, gen); v_sub(rhs, t, p); mT_vec(t, K0, gen + 3); v_sub(rhs + 3, t, p + 3);
@@ -296,13 +308,13 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
     m_vec(out, K0, a0); m_vec(out + 3, K0, a0 + 3);
   } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
   for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* L = LNK(gl);
-    int dep = sc.link_depth[gl];
+    int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* L = LNK(gl);
+    int dep = gc(sc.link_depth)[gl];
     const float* ap = ast + 6 * dep; float* ak = ast + 6 * (dep + 1);
     float t[3], t2[3], aa[3], al[3];
     m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
     if (li[3] >= 0) {
-      const float* lx = sc.link_x + 16 * gl;
+      const float* lx = shc(C.link_x) + 16 * gl;
       float qdd = (uu[k] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
       out[jo + li[3] - d0] = qdd;
       v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
@@ -312,10 +324,10 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
 }
 DG_FN void phase_minv(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
-  float* scr = C.ws + sc.X_MSCR + sc.mscr_stride * ln;
+  float* scr = WSG(C, sc.X_MSCR) + sc.mscr_stride * ln;
   int item = 0;
   for (int di = 0; di < sc.ndyn; di++) {
-    int b = sc.dyn_body[di], g = sc.body_plan[BP_W * b + BP_GDIM];
+    int b = gc(sc.dyn_body)[di], g = gc(sc.body_plan)[BP_W * b + BP_GDIM];
     for (int col = 0; col < g; col++, item++) if (item % nt == ln) minv_column(C, b, col, scr);
   }
 }
@@ -324,21 +336,21 @@ DG_FN void phase_minv(const Env& C, int ln, int nt) {
 struct Ct { int fa, fb; float pa[3], pb[3], n[3], dist, mu; };
 
 DG_FN void shape_pose(const Env& C, int s, const float** R, const float** p) {
-  int sl = SC.shape_slot[s];
-  const float* w = sl >= 0 ? C.ws + SC.X_SHW + 12 * sl : SC.shape_wb + 12 * s;
+  int sl = gc(SC.shape_slot)[s];
+  const float* w = sl >= 0 ? WSP(C, SC.X_SHW) + 12 * sl : gc(SC.shape_wb) + 12 * s;
   *R = w; *p = w + 9;
 }
 DG_FN void phase_shape_world(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   for (int s = ln; s < sc.ns; s += nt) {
-    int sl = sc.shape_slot[s];
+    int sl = gc(sc.shape_slot)[s];
     if (sl < 0) continue;
-    const float* sf = sc.shape_f + DG_SHAPE_F_W * s; const float* K = KIN(sc.frame_slot[sc.shape_i[DG_SHAPE_I_W * s + 1]]);
-    float* w = C.ws + sc.X_SHW + 12 * sl; float Rl[9], R[9], t[3];
+    const float* sf = gc(sc.shape_f) + DG_SHAPE_F_W * s; const float* K = KIN(gc(sc.frame_slot)[gc(sc.shape_i)[DG_SHAPE_I_W * s + 1]]);
+    float* w = WSP(C, sc.X_SHW) + 12 * sl; float Rl[9], R[9], t[3];
     q_to_mat(Rl, sf + 3); m_mul(R, K, Rl); m_cpy(w, R); m_vec(t, K, sf); v_add(w + 9, K + 9, t);
   }
   int nw = (sc.npair + 31) / 32;
-  for (int i = ln; i < nw; i += nt) WSI(C)[sc.X_SURV + i] = 0;
+  for (int i = ln; i < nw; i += nt) WSIP(C, sc.X_SURV)[i] = 0;
   if (ln == 0) { WSI(C)[sc.W_HDR + WH_NCONTACT] = 0; }
 }
 DG_HD void ct_add(Ct* list, int* n, int cap, int fa, int fb, const float* pa, const float* pb, const float* nrm, float dist, float mu, float margin) {
@@ -398,14 +410,14 @@ DG_HD bool pair_in_reach(const Env& C, int sa, int sb) {
   const float *Ra, *pa, *Rb, *pb;
   shape_pose(C, sa, &Ra, &pa); shape_pose(C, sb, &Rb, &pb);
   float dc[3]; v_sub(dc, pa, pb);
-  float reach = SC.shape_f[DG_SHAPE_F_W * sa + 11] + SC.shape_f[DG_SHAPE_F_W * sb + 11] + SC.margin;
+  float reach = gc(SC.shape_f)[DG_SHAPE_F_W * sa + 11] + gc(SC.shape_f)[DG_SHAPE_F_W * sb + 11] + SC.margin;
   return v_dot(dc, dc) <= reach * reach;
 }
 // narrow phase of one shape pair; writes at most 4 contacts into out, returns the count
 DG_FN int collide_pair(const Env& C, int sa, int sb, Ct* out) {
   const DevScene& sc = SC;
-  const int *ia = sc.shape_i + DG_SHAPE_I_W * sa, *ib = sc.shape_i + DG_SHAPE_I_W * sb;
-  const float *fa = sc.shape_f + DG_SHAPE_F_W * sa, *fb = sc.shape_f + DG_SHAPE_F_W * sb;
+  const int *ia = gc(sc.shape_i) + DG_SHAPE_I_W * sa, *ib = gc(sc.shape_i) + DG_SHAPE_I_W * sb;
+  const float *fa = gc(sc.shape_f) + DG_SHAPE_F_W * sa, *fb = gc(sc.shape_f) + DG_SHAPE_F_W * sb;
   const float *Ra, *pa, *Rb, *pb;
   shape_pose(C, sa, &Ra, &pa); shape_pose(C, sb, &Rb, &pb);
   float margin = sc.margin;
@@ -501,29 +513,44 @@ DG_HD int popc32(unsigned x) {
 // broad phase: bounding-sphere test of every candidate pair, survivors marked in a bit set
 DG_FN void phase_broad(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
-  for (int k = ln; k < sc.npair; k += nt)
-    if (pair_in_reach(C, sc.pair_i[2 * k], sc.pair_i[2 * k + 1])) surv_set(WSI(C) + sc.X_SURV + (k >> 5), k & 31);
+  for (int it = ln; it < sc.ngrp + sc.nloose; it += nt) {
+    if (it < sc.ngrp) {
+      // one test of the static shape against the body's bounding sphere rules out the whole group
+      const int* g = gc(sc.grp_i) + 4 * it; const float* w = gc(sc.shape_wb) + 12 * g[0];
+      const float* cb = KIN(gc(sc.body_plan)[BP_W * g[1] + BP_SLOT]) + 9;
+      float dc[3]; v_sub(dc, w + 9, cb);
+      float reach = gc(sc.shape_f)[DG_SHAPE_F_W * g[0] + 11] + gc(sc.body_reach)[g[1]] + sc.margin;
+      if (v_dot(dc, dc) > reach * reach) continue;
+      for (int j = 0; j < g[3]; j++) {
+        int k = gc(sc.grp_pairs)[g[2] + j];
+        if (pair_in_reach(C, gc(sc.pair_i)[2 * k], gc(sc.pair_i)[2 * k + 1])) surv_set(WSIP(C, sc.X_SURV) + (k >> 5), k & 31);
+      }
+    } else {
+      int k = gc(sc.loose_pairs)[it - sc.ngrp];
+      if (pair_in_reach(C, gc(sc.pair_i)[2 * k], gc(sc.pair_i)[2 * k + 1])) surv_set(WSIP(C, sc.X_SURV) + (k >> 5), k & 31);
+    }
+  }
 }
 DG_FN void phase_count_survivors(const Env& C, int ln, int nt) {
   if (ln != 0) return;
   int nw = (SC.npair + 31) / 32, n = 0;
-  for (int i = 0; i < nw; i++) n += popc32((unsigned)WSI(C)[SC.X_SURV + i]);
+  for (int i = 0; i < nw; i++) n += popc32((unsigned)WSIP(C, SC.X_SURV)[i]);
   WSI(C)[SC.W_HDR + WH_NSURV] = n;
 }
 // narrow phase, round `rnd`: lane ln takes survivor number rnd*nt + ln (in pair order) and parks its contacts
 DG_FN void phase_narrow(const Env& C, int ln, int nt, int rnd) {
   const DevScene& sc = SC;
-  float* tmp = C.ws + sc.X_CTMP + sc.ctmp_stride * ln;
+  float* tmp = WSG(C, sc.X_CTMP) + sc.ctmp_stride * ln;
   int want = rnd * nt + ln, nw = (sc.npair + 31) / 32, seen = 0, pair = -1;
   for (int i = 0; i < nw && pair < 0; i++) {
-    unsigned wd = (unsigned)WSI(C)[sc.X_SURV + i]; int c = popc32(wd);
+    unsigned wd = (unsigned)WSIP(C, sc.X_SURV)[i]; int c = popc32(wd);
     if (seen + c <= want) { seen += c; continue; }
     for (int bit = 0; bit < 32; bit++) if (wd & (1u << bit)) { if (seen == want) { pair = 32 * i + bit; break; } seen++; }
   }
   int n = 0;
   if (pair >= 0) {
     Ct out[4];
-    n = collide_pair(C, sc.pair_i[2 * pair], sc.pair_i[2 * pair + 1], out);
+    n = collide_pair(C, gc(sc.pair_i)[2 * pair], gc(sc.pair_i)[2 * pair + 1], out);
     for (int i = 0; i < n; i++) {
       float* c = tmp + 1 + CT_W * i;
       c[CT_FA] = int_as_float(out[i].fa); c[CT_FB] = int_as_float(out[i].fb);
@@ -537,25 +564,25 @@ DG_FN void phase_append(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   int nc = WSI(C)[sc.W_HDR + WH_NCONTACT];
   for (int l = 0; l < nt; l++) {
-    const float* tmp = C.ws + sc.X_CTMP + sc.ctmp_stride * l; int n = float_as_int(tmp[0]);
-    for (int i = 0; i < n && nc < sc.maxc; i++, nc++) { float* dst = C.ws + sc.X_CON + CT_W * nc; const float* src = tmp + 1 + CT_W * i; for (int j = 0; j < CT_W; j++) dst[j] = src[j]; }
+    const float* tmp = WSG(C, sc.X_CTMP) + sc.ctmp_stride * l; int n = float_as_int(tmp[0]);
+    for (int i = 0; i < n && nc < sc.maxc; i++, nc++) { float* dst = WSP(C, sc.X_CON) + CT_W * nc; const float* src = tmp + 1 + CT_W * i; for (int j = 0; j < CT_W; j++) dst[j] = src[j]; }
   }
   WSI(C)[sc.W_HDR + WH_NCONTACT] = nc;
 }
 
 // ------------------------------------------------------------------ constraint rows ----------------------------
-DG_HD int body_of_frame(const DevScene& sc, int f) { return f < sc.nb ? f : sc.link_i[DG_LINK_I_W * (f - sc.nb)]; }
+DG_HD int body_of_frame(const Env& C, int f) { return f < C.sc->nb ? f : shc(C.link_i)[DG_LINK_I_W * (f - C.sc->nb)]; }
 // generalized force per unit force along dir at world point p on frame f (compact coordinates of its body)
 DG_FN void point_jacobian(const Env& C, int f, const float* p, const float* dir, float* J) {
   const DevScene& sc = SC;
-  int b = body_of_frame(sc, f); const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
+  int b = body_of_frame(C, f); const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
   int g = bp[BP_GDIM], d0 = bi[3], s0 = bp[BP_SLOT], l0 = bi[1];
   for (int i = 0; i < g; i++) J[i] = 0.f;
   int jo = 0;
   if (bi[0] == 2) { float rel[3]; v_sub(rel, p, KIN(s0) + 9); v_cross(J, rel, dir); v_cpy(J + 3, dir); jo = 6; }
   int gl = f < sc.nb ? -1 : f - sc.nb;
   while (gl >= 0) {
-    const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl; const float* K = KIN(s0 + 1 + gl - l0);
+    const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl; const float* K = KIN(s0 + 1 + gl - l0);
     if (li[2] == 1) {
       float aw[3], dw[3], o[3], rel[3], t[3];
       m_vec(aw, K, lf + 10); m_vec(dw, K, lf + 7); v_sub(o, K + 9, dw);
@@ -565,50 +592,63 @@ DG_FN void point_jacobian(const Env& C, int f, const float* p, const float* dir,
   }
 }
 DG_FN void body_genvel(const Env& C, int b, float* gv) {
-  const int* bi = SC.body_i + DG_BODY_I_W * b; int jo = 0;
-  if (bi[0] == 2) { const float* bs = BST(SC.body_plan[BP_W * b + BP_DI]); v_cpy(gv, bs + 10); v_cpy(gv + 3, bs + 7); jo = 6; }
+  const int* bi = gc(SC.body_i) + DG_BODY_I_W * b; int jo = 0;
+  if (bi[0] == 2) { const float* bs = BST(gc(SC.body_plan)[BP_W * b + BP_DI]); v_cpy(gv, bs + 10); v_cpy(gv + 3, bs + 7); jo = 6; }
   for (int i = 0; i < bi[4]; i++) gv[jo + i] = DOF(D_QD, bi[3] + i);
 }
 // joint-limit rows (only when violated) then motor rows of every dynamic body, lane per body
 DG_FN void phase_unit_rows(const Env& C, int ln, int nt, float h) {
   const DevScene& sc = SC;
   for (int di = ln; di < sc.ndyn; di += nt) {
-    int b = sc.dyn_body[di]; const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
-    int l0 = bi[1], nlb = bi[2], d0 = bi[3], g = bp[BP_GDIM], jo = bi[0] == 2 ? 6 : 0;
-    const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
-    float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW]; int n = 0;
+    int b = gc(sc.dyn_body)[di]; const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
+    int l0 = bi[1], nlb = bi[2], d0 = bi[3], g = bp[BP_GDIM], gs = bp[BP_GS], jo = bi[0] == 2 ? 6 : 0;
+    const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF];
+    float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW]; int n = 0;
     for (int k = 0; k < nlb; k++) {
-      const int* li = sc.link_i + DG_LINK_I_W * (l0 + k); const float* lf = sc.link_f + DG_LINK_F_W * (l0 + k);
+      const int* li = shc(C.link_i) + DG_LINK_I_W * (l0 + k); const float* lf = shc(C.link_f) + DG_LINK_F_W * (l0 + k);
       int d = li[3];
       if (d < 0 || !li[4]) continue;
       for (int side = 0; side < 2; side++) {
         float pen = side == 0 ? DOF(D_Q, d) - lf[20] : lf[21] - DOF(D_Q, d);
         if (pen > 0) continue;
         int col = jo + d - d0; float sg = side == 0 ? 1.f : -1.f;
-        float den = Minv[col * g + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, rel = sg * DOF(D_QD, d);
+        float den = Minv[col * gs + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, rel = sg * DOF(D_QD, d);
         float* r = rows + UR_W * n++;
         r[UR_RHS] = (-rel + (-pen) * sc.erp / h) * dinv; r[UR_DINV] = dinv; r[UR_LO] = 0.f; r[UR_HI] = sc.limit_max_impulse; r[UR_APPLIED] = 0.f;
         r[UR_COL] = int_as_float(side == 0 ? col : -1 - col); r[UR_MOTOR] = int_as_float(-1);
       }
     }
     for (int k = 0; k < nlb; k++) {
-      int d = sc.link_i[DG_LINK_I_W * (l0 + k) + 3];
+      int d = shc(C.link_i)[DG_LINK_I_W * (l0 + k) + 3];
       if (d < 0) continue;
-      float maxf = DOF(D_MAXF, d);
+      float maxf = ST(S_MMAXF)[d];
       DOF(D_APPLIED, d) = 0.f;
       if (maxf <= 0) continue;
       int col = jo + d - d0;
-      float den = Minv[col * g + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, qd = DOF(D_QD, d);
-      float desired = DOF(D_KP, d) * (DOF(D_TPOS, d) - DOF(D_Q, d)) / h + qd + DOF(D_KD, d) * (DOF(D_TVEL, d) - qd);
+      float den = Minv[col * gs + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, qd = DOF(D_QD, d);
+      float desired = ST(S_MKP)[d] * (ST(S_MTPOS)[d] - DOF(D_Q, d)) / h + qd + ST(S_MKD)[d] * (ST(S_MTVEL)[d] - qd);
       float* r = rows + UR_W * n++;
       r[UR_RHS] = (desired - qd) * dinv; r[UR_DINV] = dinv; r[UR_LO] = -maxf * sc.dt; r[UR_HI] = maxf * sc.dt; r[UR_APPLIED] = 0.f;
       r[UR_COL] = int_as_float(col); r[UR_MOTOR] = int_as_float(d);
     }
     WSI(C)[sc.W_UCNT + di] = n;
-    float* dv = C.ws + sc.W_DV + bp[BP_GVOFF];
-    for (int i = 0; i < g; i++) dv[i] = 0.f;
+    float* dv = WSH(C, sc.W_DV) + bp[BP_GVOFF];
+    for (int i = 0; i < gs; i++) dv[i] = 0.f;
+    // row-space system A[r][s] = J_r M^-1 J_s^T for the register-resident sweep (pgs_unit_fast)
+    int nrs = bp[BP_NRS];
+    if (n <= nrs) {
+      float* A = WSH(C, sc.X_AMAT) + bp[BP_AOFF];
+      for (int r = 0; r < n; r++) {
+        int cr = float_as_int(rows[UR_W * r + UR_COL]); float sr = 1.f; if (cr < 0) { cr = -1 - cr; sr = -1.f; }
+        for (int s2 = 0; s2 < nrs; s2++) {
+          float a = 0.f;
+          if (s2 < n) { int cs = float_as_int(rows[UR_W * s2 + UR_COL]); float ss = 1.f; if (cs < 0) { cs = -1 - cs; ss = -1.f; } a = sr * ss * Minv[cr * gs + cs]; }
+          A[r * nrs + s2] = a;
+        }
+      }
+    }
   }
-  if (ln == 0) WSI(C)[sc.W_HDR + WH_NCROW] = 3 * WSI(C)[sc.W_HDR + WH_NCONTACT];
+  if (ln == 0) { WSI(C)[sc.W_HDR + WH_NCROW] = 3 * WSI(C)[sc.W_HDR + WH_NCONTACT]; WSI(C)[sc.W_HDR + WH_COUPLED] = 0; }
 }
 DG_FN void plane_space(const float* n, float* p, float* q) {
   if (fabsf(n[2]) > 0.7071067811865475244f) { float a = n[1] * n[1] + n[2] * n[2], k = 1.0f / sqrtf(a); p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k; q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1]; }
@@ -620,32 +660,34 @@ DG_FN void phase_contact_rows(const Env& C, int ln, int nt, float h) {
   int nc = WSI(C)[sc.W_HDR + WH_NCONTACT];
   for (int r = ln; r < 3 * nc; r += nt) {
     int k = r < nc ? r : (r - nc) >> 1, dirk = r < nc ? -1 : (r - nc) & 1;
-    const float* c = C.ws + sc.X_CON + CT_W * k;
+    const float* c = WSP(C, sc.X_CON) + CT_W * k;
     int fa = float_as_int(c[CT_FA]), fb = float_as_int(c[CT_FB]);
     float dir[3];
     if (dirk < 0) v_cpy(dir, c + CT_N); else { float t1[3], t2[3]; plane_space(c + CT_N, t1, t2); v_cpy(dir, dirk == 0 ? t1 : t2); }
-    float* row = C.ws + sc.X_CROW + sc.crow_stride * r; float* J = row + CR_HDR; float* M = J + sc.GP;
-    int ba = body_of_frame(sc, fa), bb = body_of_frame(sc, fb);
-    int dia = sc.body_plan[BP_W * ba + BP_DI], dib = sc.body_plan[BP_W * bb + BP_DI];
+    float* row = WSP(C, sc.X_CROW) + sc.crow_stride * r; float* J = row + CR_HDR; float* M = J + sc.GP;
+    int ba = body_of_frame(C, fa), bb = body_of_frame(C, fb);
+    int dia = gc(sc.body_plan)[BP_W * ba + BP_DI], dib = gc(sc.body_plan)[BP_W * bb + BP_DI];
     float den = 0.f, rel = 0.f; int ga = 0;
     if (dia >= 0) {
-      const int* bp = sc.body_plan + BP_W * ba; ga = bp[BP_GDIM]; const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
+      const int* bp = gc(sc.body_plan) + BP_W * ba; ga = bp[BP_GDIM]; const int gsa = bp[BP_GS]; const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF];
       point_jacobian(C, fa, c + CT_PA, dir, J);
       body_genvel(C, ba, M);   // M doubles as scratch for the generalized velocity
       for (int i = 0; i < ga; i++) rel += J[i] * M[i];
-      for (int i = 0; i < ga; i++) { float s = 0.f; for (int j = 0; j < ga; j++) s += Minv[j * ga + i] * J[j]; M[i] = s; }
+      for (int i = 0; i < ga; i++) { float s = 0.f; for (int j = 0; j < ga; j++) s += Minv[j * gsa + i] * J[j]; M[i] = s; }
       for (int i = 0; i < ga; i++) den += J[i] * M[i];
     }
     if (dib >= 0) {
-      const int* bp = sc.body_plan + BP_W * bb; int gb = bp[BP_GDIM]; const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF];
+      const int* bp = gc(sc.body_plan) + BP_W * bb; int gb = bp[BP_GDIM]; const int gsb = bp[BP_GS]; const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF];
       float nd_[3]; v_scale(nd_, dir, -1.0f);
       float *JB = J + ga, *MB = M + ga;
       point_jacobian(C, fb, c + CT_PB, nd_, JB);
       body_genvel(C, bb, MB);
       for (int i = 0; i < gb; i++) rel += JB[i] * MB[i];
-      for (int i = 0; i < gb; i++) { float s = 0.f; for (int j = 0; j < gb; j++) s += Minv[j * gb + i] * JB[j]; MB[i] = s; }
+      for (int i = 0; i < gb; i++) { float s = 0.f; for (int j = 0; j < gb; j++) s += Minv[j * gsb + i] * JB[j]; MB[i] = s; }
       for (int i = 0; i < gb; i++) den += JB[i] * MB[i];
     }
+    { int used = ga + (dib >= 0 ? gc(sc.body_plan)[BP_W * bb + BP_GDIM] : 0); for (int i = used; i < sc.GP; i++) { J[i] = 0.f; M[i] = 0.f; } }
+    if (dia >= 0 && dib >= 0) WSI(C)[sc.W_HDR + WH_COUPLED] = 1;   // a row couples two dynamic bodies: lock-step sweeps needed
     float dinv = den > 1e-30f ? 1.0f / den : 0.f;
     row[CR_DINV] = dinv; row[CR_APPLIED] = 0.f; row[CR_MU] = c[CT_MU];
     row[CR_DA] = int_as_float(dia); row[CR_DB] = int_as_float(dib);
@@ -662,9 +704,9 @@ DG_FN void phase_contact_rows(const Env& C, int ln, int nt, float h) {
 // ------------------------------------------------------------------ projected Gauss-Seidel ---------------------
 DG_FN void pgs_unit_sweep(const Env& C, int b, int di, int it) {
   const DevScene& sc = SC;
-  const int* bp = sc.body_plan + BP_W * b; int g = bp[BP_GDIM], n = WSI(C)[sc.W_UCNT + di];
-  const float* Minv = C.ws + sc.W_MINV + bp[BP_MINVOFF]; float* dv = C.ws + sc.W_DV + bp[BP_GVOFF];
-  float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW];
+  const int* bp = gc(sc.body_plan) + BP_W * b; int g = bp[BP_GDIM], gs = bp[BP_GS], n = WSI(C)[sc.W_UCNT + di];
+  const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF]; float* dv = WSH(C, sc.W_DV) + bp[BP_GVOFF];
+  float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW];
   for (int j = 0; j < n; j++) {
     float* r = rows + UR_W * ((it & 1) ? j : n - 1 - j);
     int colc = float_as_int(r[UR_COL]); float sg = 1.f; int col = colc;
@@ -673,23 +715,171 @@ DG_FN void pgs_unit_sweep(const Env& C, int b, int di, int it) {
     float ap = r[UR_APPLIED], sum = ap + d, lo = r[UR_LO], hi = r[UR_HI];
     if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
     r[UR_APPLIED] = sum;
-    float sd = sg * d; const float* Mc = Minv + col * g;
+    float sd = sg * d; const float* Mc = Minv + col * gs;
     for (int i = 0; i < g; i++) dv[i] = fmaf(Mc[i], sd, dv[i]);
+  }
+}
+// Register-resident sweeps over the unit rows of one body, iterations [it0, it1): same Gauss-Seidel order and
+// clamps as pgs_unit_sweep, carried out in row space (y_r = J_r dv) so that every index is a compile-time constant.
+// NR >= number of rows; the padding rows carry zeros (rhs = dinv = lo = hi = 0, zero A row) and change nothing.
+// For NR <= 8 the row-space matrix A lives in registers as well, so the 150 sweeps touch no memory at all.
+template <int NR>
+DG_FN void pgs_unit_fast(const Env& C, int b, int di, int it0, int it1) {
+  const DevScene& sc = SC;
+  const int* bp = gc(sc.body_plan) + BP_W * b; const int g = bp[BP_GDIM], gs = bp[BP_GS], nrs = bp[BP_NRS], n = WSI(C)[sc.W_UCNT + di];
+  const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF]; float* dv = WSH(C, sc.W_DV) + bp[BP_GVOFF];
+  float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW]; const float* A = WSH(C, sc.X_AMAT) + bp[BP_AOFF];
+  constexpr bool kRegA = NR <= 8;
+  float rhs[NR], dinv[NR], lo[NR], hi[NR], ap[NR], ap0[NR], y[NR], Ar[kRegA ? NR * NR : 1];
+#pragma unroll
+  for (int r = 0; r < NR; r++) {
+    rhs[r] = 0.f; dinv[r] = 0.f; lo[r] = 0.f; hi[r] = 0.f; ap[r] = 0.f; y[r] = 0.f;
+    if (r < n) {
+      const float* rw = rows + UR_W * r;
+      rhs[r] = rw[UR_RHS]; dinv[r] = rw[UR_DINV]; lo[r] = rw[UR_LO]; hi[r] = rw[UR_HI]; ap[r] = rw[UR_APPLIED];
+      int c = float_as_int(rw[UR_COL]);
+      y[r] = c < 0 ? -dv[-1 - c] : dv[c];
+    }
+    ap0[r] = ap[r];
+    if (kRegA) {
+#pragma unroll
+      for (int s2 = 0; s2 < NR; s2++) Ar[kRegA ? r * NR + s2 : 0] = (r < n && s2 < n) ? A[r * nrs + s2] : 0.f;
+    }
+  }
+#define DG_PGS_ROW(r)                                                                        \
+  {                                                                                          \
+    float d = rhs[r] - y[r] * dinv[r];                                                       \
+    float sum = ap[r] + d;                                                                   \
+    const bool below = sum < lo[r], above = sum > hi[r];                                     \
+    d = below ? lo[r] - ap[r] : (above ? hi[r] - ap[r] : d);                                 \
+    ap[r] = below ? lo[r] : (above ? hi[r] : sum);                                           \
+    if (kRegA) {                                                                             \
+      _Pragma("unroll") for (int s2 = 0; s2 < NR; s2++) y[s2] = fmaf(Ar[kRegA ? (r) * NR + s2 : 0], d, y[s2]); \
+    } else if ((r) < n) {                                                                    \
+      const float* Am = A + (r) * nrs;                                                       \
+      _Pragma("unroll") for (int s2 = 0; s2 < NR; s2++) y[s2] = fmaf(Am[s2], d, y[s2]);      \
+    }                                                                                        \
+  }
+  for (int it = it0; it < it1; it++) {
+    if (it & 1) {
+#pragma unroll
+      for (int r = 0; r < NR; r++) DG_PGS_ROW(r)
+    } else {
+#pragma unroll
+      for (int r = NR - 1; r >= 0; r--) DG_PGS_ROW(r)
+    }
+  }
+#undef DG_PGS_ROW
+#pragma unroll
+  for (int r = 0; r < NR; r++) if (r < n) {
+    float* rw = rows + UR_W * r;
+    rw[UR_APPLIED] = ap[r];
+    float dl = ap[r] - ap0[r];
+    int c = float_as_int(rw[UR_COL]); if (c < 0) { c = -1 - c; dl = -dl; }
+    const float* Mc = Minv + c * gs;
+    for (int i = 0; i < g; i++) dv[i] = fmaf(Mc[i], dl, dv[i]);
+  }
+}
+DG_FN void pgs_unit_any(const Env& C, int b, int di, int it0, int it1) {
+  const int nrs = gc(SC.body_plan)[BP_W * b + BP_NRS], n = WSI(C)[SC.W_UCNT + di];
+  if (n == 0) return;
+  if (n <= nrs) {   // the A matrix was built (phase_unit_rows); nrs is a multiple of 4, so the padded reads stay inside it
+    if (n <= 4) { pgs_unit_fast<4>(C, b, di, it0, it1); return; }
+    if (n <= 6 && nrs >= 8) { pgs_unit_fast<6>(C, b, di, it0, it1); return; }
+    if (n <= 8) { pgs_unit_fast<8>(C, b, di, it0, it1); return; }
+    if (n <= 12) { pgs_unit_fast<12>(C, b, di, it0, it1); return; }
+    if (n <= 16) { pgs_unit_fast<16>(C, b, di, it0, it1); return; }
+  }
+  for (int it = it0; it < it1; it++) pgs_unit_sweep(C, b, di, it);
+}
+// All solver sweeps of ONE body whose contact rows touch no other dynamic body: unit rows then its contact rows,
+// every iteration, with the generalized velocity change dv held in registers (G >= padded coordinate count).
+struct F4 { float x, y, z, w; };
+DG_HD F4 ld4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float4 v = *reinterpret_cast<const float4*>(p); F4 o = {v.x, v.y, v.z, v.w}; return o;
+#else
+  F4 o = {p[0], p[1], p[2], p[3]}; return o;
+#endif
+}
+template <int G>
+DG_FN void pgs_body_full(const Env& C, int b, int di) {
+  const DevScene& sc = SC;
+  const int* bp = gc(sc.body_plan) + BP_W * b; const int gs = bp[BP_GS], n = WSI(C)[sc.W_UCNT + di];
+  const int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
+  const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF]; float* dvs = WSH(C, sc.W_DV) + bp[BP_GVOFF];
+  float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW];
+  float dv[G];
+#pragma unroll
+  for (int i = 0; i < G; i++) dv[i] = 0.f;
+  for (int it = 0; it < sc.iters; it++) {
+    for (int j = 0; j < n; j++) {
+      float* r = rows + UR_W * ((it & 1) ? j : n - 1 - j);
+      int col = float_as_int(r[UR_COL]); float sg = 1.f;
+      if (col < 0) { col = -1 - col; sg = -1.f; }
+      float x = 0.f;
+#pragma unroll
+      for (int i = 0; i < G; i++) x = (i == col) ? dv[i] : x;
+      float d = r[UR_RHS] - sg * x * r[UR_DINV];
+      float ap = r[UR_APPLIED], sum = ap + d, lo = r[UR_LO], hi = r[UR_HI];
+      if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
+      r[UR_APPLIED] = sum;
+      float sd = sg * d; const float* Mc = Minv + col * gs;
+#pragma unroll
+      for (int c4 = 0; c4 < G / 4; c4++) if (4 * c4 < gs) {
+        F4 m = ld4(Mc + 4 * c4);
+        dv[4 * c4] = fmaf(m.x, sd, dv[4 * c4]); dv[4 * c4 + 1] = fmaf(m.y, sd, dv[4 * c4 + 1]);
+        dv[4 * c4 + 2] = fmaf(m.z, sd, dv[4 * c4 + 2]); dv[4 * c4 + 3] = fmaf(m.w, sd, dv[4 * c4 + 3]);
+      }
+    }
+    for (int rr = 0; rr < ncr; rr++) {
+      float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr;
+      if (float_as_int(row[CR_DA]) != di && float_as_int(row[CR_DB]) != di) continue;
+      const float* J = row + CR_HDR; const float* M = J + sc.GP;
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < G / 4; c4++) if (4 * c4 < gs) {
+        F4 jv = ld4(J + 4 * c4);
+        d0 = fmaf(jv.x, dv[4 * c4], d0); d1 = fmaf(jv.y, dv[4 * c4 + 1], d1); d2 = fmaf(jv.z, dv[4 * c4 + 2], d2); d3 = fmaf(jv.w, dv[4 * c4 + 3], d3);
+      }
+      F4 h = ld4(row);   // rhs, dinv, lo, hi
+      float d = h.x - ((d0 + d1) + (d2 + d3)) * h.y;
+      float lo = h.z, hi = h.w;
+      int par = float_as_int(row[CR_PARENT]);
+      if (par >= 0) { hi = row[CR_MU] * (WSP(C, sc.X_CROW) + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
+      float ap = row[CR_APPLIED], sum = ap + d;
+      if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
+      row[CR_APPLIED] = sum;
+#pragma unroll
+      for (int c4 = 0; c4 < G / 4; c4++) if (4 * c4 < gs) {
+        F4 m = ld4(M + 4 * c4);
+        dv[4 * c4] = fmaf(m.x, d, dv[4 * c4]); dv[4 * c4 + 1] = fmaf(m.y, d, dv[4 * c4 + 1]);
+        dv[4 * c4 + 2] = fmaf(m.z, d, dv[4 * c4 + 2]); dv[4 * c4 + 3] = fmaf(m.w, d, dv[4 * c4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < G; i++) if (i < gs) dvs[i] = dv[i];
+}
+DG_FN void phase_pgs_full(const Env& C, int ln, int nt) {
+  for (int di = ln; di < SC.ndyn; di += nt) {
+    int b = gc(SC.dyn_body)[di], gs = gc(SC.body_plan)[BP_W * b + BP_GS];
+    if (gs <= 8) pgs_body_full<8>(C, b, di); else if (gs <= 16) pgs_body_full<16>(C, b, di); else pgs_body_full<32>(C, b, di);
   }
 }
 DG_FN void pgs_contact_sweep(const Env& C) {
   const DevScene& sc = SC;
   int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
   for (int r = 0; r < ncr; r++) {
-    float* row = C.ws + sc.X_CROW + sc.crow_stride * r; const float* J = row + CR_HDR; const float* M = J + sc.GP;
+    float* row = WSP(C, sc.X_CROW) + sc.crow_stride * r; const float* J = row + CR_HDR; const float* M = J + sc.GP;
     int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
     float dot = 0.f; int ga = 0; float *dva = nullptr, *dvb = nullptr; int gb = 0;
-    if (dia >= 0) { const int* bp = sc.body_plan + BP_W * sc.dyn_body[dia]; ga = bp[BP_GDIM]; dva = C.ws + sc.W_DV + bp[BP_GVOFF]; for (int i = 0; i < ga; i++) dot += J[i] * dva[i]; }
-    if (dib >= 0) { const int* bp = sc.body_plan + BP_W * sc.dyn_body[dib]; gb = bp[BP_GDIM]; dvb = C.ws + sc.W_DV + bp[BP_GVOFF]; for (int i = 0; i < gb; i++) dot += J[ga + i] * dvb[i]; }
+    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; ga = bp[BP_GDIM]; dva = WSH(C, sc.W_DV) + bp[BP_GVOFF]; for (int i = 0; i < ga; i++) dot += J[i] * dva[i]; }
+    if (dib >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; gb = bp[BP_GDIM]; dvb = WSH(C, sc.W_DV) + bp[BP_GVOFF]; for (int i = 0; i < gb; i++) dot += J[ga + i] * dvb[i]; }
     float d = row[CR_RHS] - dot * row[CR_DINV];
     float lo = row[CR_LO], hi = row[CR_HI];
     int par = float_as_int(row[CR_PARENT]);
-    if (par >= 0) { hi = row[CR_MU] * (C.ws + sc.X_CROW + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
+    if (par >= 0) { hi = row[CR_MU] * (WSP(C, sc.X_CROW) + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
     float ap = row[CR_APPLIED], sum = ap + d;
     if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
     row[CR_APPLIED] = sum;
@@ -698,7 +888,7 @@ DG_FN void pgs_contact_sweep(const Env& C) {
   }
 }
 DG_FN void phase_pgs_unit(const Env& C, int ln, int nt, int it0, int it1) {
-  for (int di = ln; di < SC.ndyn; di += nt) for (int it = it0; it < it1; it++) pgs_unit_sweep(C, SC.dyn_body[di], di, it);
+  for (int di = ln; di < SC.ndyn; di += nt) pgs_unit_any(C, gc(SC.dyn_body)[di], di, it0, it1);
 }
 DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_contact_sweep(C); }
 
@@ -713,10 +903,10 @@ DG_FN void integrate_base_quat(float* q, const float* om, float h) {
 DG_FN void phase_integrate(const Env& C, int ln, int nt, float h) {
   const DevScene& sc = SC;
   for (int di = ln; di < sc.ndyn; di += nt) {
-    int b = sc.dyn_body[di]; const int* bi = sc.body_i + DG_BODY_I_W * b; const int* bp = sc.body_plan + BP_W * b;
-    const float* dv = C.ws + sc.W_DV + bp[BP_GVOFF]; int jo = 0;
+    int b = gc(sc.dyn_body)[di]; const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
+    const float* dv = WSH(C, sc.W_DV) + bp[BP_GVOFF]; int jo = 0;
     // record the motor impulses of this sub-step
-    int n = WSI(C)[sc.W_UCNT + di]; const float* rows = C.ws + sc.X_UROW + UR_W * bp[BP_UROW];
+    int n = WSI(C)[sc.W_UCNT + di]; const float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW];
     for (int j = 0; j < n; j++) { int md = float_as_int(rows[UR_W * j + UR_MOTOR]); if (md >= 0) DOF(D_APPLIED, md) = rows[UR_W * j + UR_APPLIED]; }
     if (bi[0] == 2) {
       float* bs = BST(di);
@@ -733,13 +923,13 @@ DG_FN void phase_integrate(const Env& C, int ln, int nt, float h) {
   }
 }
 DG_FN void phase_final_kin(const Env& C, int ln, int nt) {
-  for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body(C, SC.dyn_body[di]);
+  for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body(C, gc(SC.dyn_body)[di]);
 }
 // write the dynamic state back, refresh the link pose / velocity cache the sensors read, clear applied wrenches
 DG_FN void phase_store(const Env& C, int ln, int nt, int clear_forces) {
   const DevScene& sc = SC;
   for (int i = ln; i < 13 * sc.ndyn; i += nt) {
-    int di = i / 13, k = i - 13 * di, b = sc.dyn_body[di]; float v = BST(di)[k];
+    int di = i / 13, k = i - 13 * di, b = gc(sc.dyn_body)[di]; float v = BST(di)[k];
     if (k < 3) ST(S_BPOS)[3 * b + k] = v;
     else if (k < 7) ST(S_BQUAT)[4 * b + k - 3] = v;
     else if (k < 10) ST(S_BVEL)[3 * b + k - 7] = v;
@@ -750,16 +940,17 @@ DG_FN void phase_store(const Env& C, int ln, int nt, int clear_forces) {
     if (clear_forces) ST(S_JTORQUE)[d] = 0.f;
   }
   for (int gl = ln; gl < sc.nl; gl += nt) {
-    int s = sc.frame_slot[sc.nb + gl];
+    int s = gc(sc.frame_slot)[sc.nb + gl];
     if (s < 0) continue;
     const float* K = KIN(s); float q[4], t[3];
     v_cpy(ST(S_LPOS) + 3 * gl, K + 9);
     mat_to_q(q, K); for (int i = 0; i < 4; i++) ST(S_LQUAT)[4 * gl + i] = q[i];
-    m_vec(t, K, K + 15); v_cpy(ST(S_LVEL) + 3 * gl, t);
-    m_vec(t, K, K + 12); v_cpy(ST(S_LOMEGA) + 3 * gl, t);
+    const float* V = ABA(s) + 39;
+    m_vec(t, K, V + 3); v_cpy(ST(S_LVEL) + 3 * gl, t);
+    m_vec(t, K, V); v_cpy(ST(S_LOMEGA) + 3 * gl, t);
   }
   if (clear_forces) for (int f = ln; f < sc.nframes; f += nt) {
-    if (sc.frame_slot[f] < 0) continue;
+    if (gc(sc.frame_slot)[f] < 0) continue;
     for (int i = 0; i < 3; i++) { ST(S_EXTF)[3 * f + i] = 0.f; ST(S_EXTT)[3 * f + i] = 0.f; }
   }
 }
@@ -777,7 +968,7 @@ DG_FN void frame_link_pose(const Env& C, int f, float* pos, float* quat) {
   float v[3], o[3];
   frame_com_state(C, f, pos, quat, v, o);
   if (f >= SC.nb) {
-    const float* lf = SC.link_f + DG_LINK_F_W * (f - SC.nb);
+    const float* lf = C.link_f + DG_LINK_F_W * (f - SC.nb);
     float R[9], t[3], qi[4] = {-lf[16], -lf[17], -lf[18], lf[19]}, qo[4];
     q_to_mat(R, quat); m_vec(t, R, lf + 7); v_sub(pos, pos, t);
     q_mul(qo, quat, qi); for (int i = 0; i < 4; i++) quat[i] = qo[i];
@@ -802,7 +993,7 @@ DG_FN int solve_dense(float* A, float* bvec, int n) {
 DG_FN void ik_solve(const Env& C, int b, int ee_gl, const float* tpos_w, const float* torn_w, int use_orn, int nullspace,
                     const float* lower, const float* upper, const float* range, const float* rest, float* scr) {
   const DevScene& sc = SC;
-  const int* bi = sc.body_i + DG_BODY_I_W * b; int d0 = bi[3], ndb = bi[4];
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; int d0 = bi[3], ndb = bi[4];
   int mc = sc.max_depth + 2;
   float* qb = scr; float* nullv = qb + ndb; float* dth = nullv + ndb; float* J = dth + ndb;     // J: 6 x ndb
   float* A = J + 6 * ndb; int asz = ndb * ndb > 36 ? ndb * ndb : 36;
@@ -820,27 +1011,27 @@ DG_FN void ik_solve(const Env& C, int b, int ee_gl, const float* tpos_w, const f
     nullv[i] = nv;
   }
   int nc = 0;
-  for (int gl = ee_gl; gl >= 0; gl = sc.link_i[DG_LINK_I_W * gl + 1]) chain[nc++] = gl;
+  for (int gl = ee_gl; gl >= 0; gl = shc(C.link_i)[DG_LINK_I_W * gl + 1]) chain[nc++] = gl;
   int m = use_orn ? 6 : 3;
   float diff = 1e30f;
   for (int it = 0; it < sc.ik_iters && diff > sc.ik_threshold; it++) {
     // forward kinematics of the chain in base coordinates + geometric Jacobian
     float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pc[3] = {0, 0, 0};
     for (int i = nc - 1; i >= 0; i--) {
-      int gl = chain[i]; const int* li = sc.link_i + DG_LINK_I_W * gl; const float* lf = sc.link_f + DG_LINK_F_W * gl;
+      int gl = chain[i]; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl;
       float E[9], r[3], t[3], Rn[9];
-      joint_xform(sc, gl, li[3] >= 0 ? qb[li[3] - d0] : 0.0f, E, r);
+      joint_xform(C, gl, li[3] >= 0 ? qb[li[3] - d0] : 0.0f, E, r);
       m_vec(t, Rc, r); v_add(pc, pc, t); m_mulT(Rn, Rc, E); m_cpy(Rc, Rn);
       m_vec(axw + 3 * i, Rc, lf + 10);
       float dw[3]; m_vec(dw, Rc, lf + 7); v_sub(orgw + 3 * i, pc, dw);
     }
-    const float* lfe = sc.link_f + DG_LINK_F_W * ee_gl;
+    const float* lfe = shc(C.link_f) + DG_LINK_F_W * ee_gl;
     float pos[3], R[9], dw[3], Rli[9], qi[4] = {-lfe[16], -lfe[17], -lfe[18], lfe[19]};
     m_vec(dw, Rc, lfe + 7); v_sub(pos, pc, dw);
     q_to_mat(Rli, qi); m_mul(R, Rc, Rli);
     for (int i = 0; i < 6 * ndb; i++) J[i] = 0.f;
     for (int i = 0; i < nc; i++) {
-      const int* li = sc.link_i + DG_LINK_I_W * chain[i];
+      const int* li = shc(C.link_i) + DG_LINK_I_W * chain[i];
       if (li[3] < 0) continue;
       int jd = li[3] - d0;
       if (li[2] == 1) { float rel[3], t[3]; v_sub(rel, pos, orgw + 3 * i); v_cross(t, axw + 3 * i, rel); for (int k = 0; k < 3; k++) { J[k * ndb + jd] = t[k]; J[(3 + k) * ndb + jd] = axw[3 * i + k]; } }
@@ -879,13 +1070,140 @@ DG_FN void ik_solve(const Env& C, int b, int ee_gl, const float* tpos_w, const f
   }
 }
 
+// Register-resident form of ik_solve for bodies with at most MAXD DoF and M = 3 (position) or 6 (pose) task rows.
+// Both damping variants reduce to  dth = J^T (J J^T + lam I)^-1 (e - J n) + n  (n = 0 without null-space terms, by
+// the push-through identity (J^T J + lam I)^-1 J^T = J^T (J J^T + lam I)^-1), so only an M x M SPD system is solved.
+template <int MAXD, int M>
+DG_FN void ik_solve_fast(const Env& C, int b, int ee_gl, const float* tpos_w, const float* torn_w, int nullspace,
+                         const float* lower, const float* upper, const float* range, const float* rest, float* scr) {
+  const DevScene& sc = SC;
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int d0 = bi[3], ndb = bi[4];
+  const int mc = sc.max_depth + 2;
+  float* qb = scr; float* axw = scr + MAXD; float* orgw = axw + 3 * mc;
+  int* chain = (int*)(orgw + 3 * mc); int* cpos = chain + mc;
+  float nullv[MAXD];
+#pragma unroll
+  for (int k = 0; k < MAXD; k++) { nullv[k] = 0.f; if (k < ndb) { qb[k] = ST(S_Q)[d0 + k]; cpos[k] = -1; } }
+  const float *bp = ST(S_BPOS) + 3 * b, *bq = ST(S_BQUAT) + 4 * b;
+  float Rb[9], tp[3], d[3], tq[4] = {0, 0, 0, 1};
+  q_to_mat(Rb, bq); v_sub(d, tpos_w, bp); mT_vec(tp, Rb, d);
+  if (M == 6) { float bqi[4] = {-bq[0], -bq[1], -bq[2], bq[3]}; q_mul(tq, bqi, torn_w); }
+  if (nullspace) {
+#pragma unroll
+    for (int k = 0; k < MAXD; k++) if (k < ndb) {
+      float q = qb[k], nv = 0.001f * (rest[k] - q);
+      if (q > upper[k]) nv += 10.0f * (upper[k] - q) / range[k];
+      if (q < lower[k]) nv += 10.0f * (lower[k] - q) / range[k];
+      nullv[k] = nv;
+    }
+  }
+  int nc = 0;
+  for (int gl = ee_gl; gl >= 0; gl = shc(C.link_i)[DG_LINK_I_W * gl + 1]) { int dof = shc(C.link_i)[DG_LINK_I_W * gl + 3]; if (dof >= 0) cpos[dof - d0] = nc; chain[nc++] = gl; }
+  const float lam = nullspace ? sc.ik_null_lambda_sq : sc.ik_damping;
+  const float* lfe = shc(C.link_f) + DG_LINK_F_W * ee_gl;
+  float Rli[9]; { float qi[4] = {-lfe[16], -lfe[17], -lfe[18], lfe[19]}; q_to_mat(Rli, qi); }
+  float diff = 1e30f;
+  for (int it = 0; it < sc.ik_iters && diff > sc.ik_threshold; it++) {
+    float Rc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pc[3] = {0, 0, 0};
+    for (int i = nc - 1; i >= 0; i--) {
+      int gl = chain[i]; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl;
+      float E[9], r[3], t[3], Rn[9];
+      joint_xform(C, gl, li[3] >= 0 ? qb[li[3] - d0] : 0.0f, E, r);
+      m_vec(t, Rc, r); v_add(pc, pc, t); m_mulT(Rn, Rc, E); m_cpy(Rc, Rn);
+      if (li[3] >= 0) { m_vec(axw + 3 * i, Rc, lf + 10); float dw[3]; m_vec(dw, Rc, lf + 7); v_sub(orgw + 3 * i, pc, dw); }
+    }
+    float pos[3], dw[3];
+    m_vec(dw, Rc, lfe + 7); v_sub(pos, pc, dw);
+    float J[M][MAXD];
+#pragma unroll
+    for (int k = 0; k < MAXD; k++) {
+#pragma unroll
+      for (int r = 0; r < M; r++) J[r][k] = 0.f;
+      if (k < ndb && cpos[k] >= 0) {
+        int i = cpos[k]; const float* ax = axw + 3 * i;
+        if (shc(C.link_i)[DG_LINK_I_W * chain[i] + 2] == 1) {
+          float rel[3], t[3]; v_sub(rel, pos, orgw + 3 * i); v_cross(t, ax, rel);
+          J[0][k] = t[0]; J[1][k] = t[1]; J[2][k] = t[2];
+          if (M == 6) { J[M - 3][k] = ax[0]; J[M - 2][k] = ax[1]; J[M - 1][k] = ax[2]; }
+        } else { J[0][k] = ax[0]; J[1][k] = ax[1]; J[2][k] = ax[2]; }
+      }
+    }
+    float e[M];
+    { float e3[3]; v_sub(e3, tp, pos); diff = v_len(e3); e[0] = e3[0]; e[1] = e3[1]; e[2] = e3[2]; }
+    if (M == 6) {
+      float R[9], qc[4], qci[4], dq[4]; m_mul(R, Rc, Rli); mat_to_q(qc, R); qci[0] = -qc[0]; qci[1] = -qc[1]; qci[2] = -qc[2]; qci[3] = qc[3];
+      q_mul(dq, tq, qci);
+      float vn = v_len(dq), ax[3];
+      float ang = 2 * atan2f(vn, dq[3]);
+      if (vn * vn < 10 * 2.220446049250313e-16f) v_set(ax, 1, 0, 0); else v_scale(ax, dq, 1.0f / vn);
+      if (ang > kPi) ang -= 2 * kPi; else if (ang < -kPi) ang += 2 * kPi;
+      e[M - 3] = ax[0] * ang; e[M - 2] = ax[1] * ang; e[M - 1] = ax[2] * ang;
+    }
+    // y = e - J n ;  U = J J^T + lam I (lower triangle) ; solve U x = y by LDL^T without pivoting (U is SPD)
+    float x[M], U[M][M];
+#pragma unroll
+    for (int r = 0; r < M; r++) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int k = 0; k < MAXD; k++) sdot = fmaf(J[r][k], nullv[k], sdot);
+      x[r] = e[r] - sdot;
+#pragma unroll
+      for (int c = 0; c <= r; c++) {
+        float u = 0.f;
+#pragma unroll
+        for (int k = 0; k < MAXD; k++) u = fmaf(J[r][k], J[c][k], u);
+        U[r][c] = u + (r == c ? lam : 0.f);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < M; c++) {            // forward elimination on the lower triangle (columns below the pivot)
+      float inv = 1.0f / U[c][c];
+#pragma unroll
+      for (int r = c + 1; r < M; r++) {
+        float urc = U[r][c], f = urc * inv;
+#pragma unroll
+        for (int c2 = c + 1; c2 < r; c2++) U[r][c2] -= urc * U[c2][c];   // U[c2][c] already holds L[c2][c]
+        U[r][r] -= urc * f;
+        x[r] -= f * x[c];
+        U[r][c] = f;                          // keep L for the back substitution
+      }
+    }
+#pragma unroll
+    for (int r = M - 1; r >= 0; r--) {        // back substitution with U^T = D L^T
+      float sdot = x[r] / U[r][r];
+#pragma unroll
+      for (int r2 = r + 1; r2 < M; r2++) sdot -= U[r2][r] * x[r2];
+      x[r] = sdot;
+    }
+    float dth[MAXD], mx = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXD; k++) {
+      float sdot = nullv[k];
+#pragma unroll
+      for (int r = 0; r < M; r++) sdot = fmaf(J[r][k], x[r], sdot);
+      dth[k] = sdot; mx = fmaxf(mx, fabsf(sdot));
+    }
+    const float cap = 45.0f * kPi / 180.0f;
+    float sc_ = mx > cap ? cap / mx : 1.0f;
+#pragma unroll
+    for (int k = 0; k < MAXD; k++) if (k < ndb) qb[k] += dth[k] * sc_;
+  }
+}
+DG_FN void ik_solve_any(const Env& C, int b, int ee_gl, const float* tpos_w, const float* torn_w, int use_orn, int nullspace,
+                        const float* lower, const float* upper, const float* range, const float* rest, float* scr) {
+  const int ndb = gc(SC.body_i)[DG_BODY_I_W * b + 4];
+  if (ndb <= 6) { if (use_orn) ik_solve_fast<6, 6>(C, b, ee_gl, tpos_w, torn_w, nullspace, lower, upper, range, rest, scr); else ik_solve_fast<6, 3>(C, b, ee_gl, tpos_w, torn_w, nullspace, lower, upper, range, rest, scr); }
+  else if (ndb <= 12) { if (use_orn) ik_solve_fast<12, 6>(C, b, ee_gl, tpos_w, torn_w, nullspace, lower, upper, range, rest, scr); else ik_solve_fast<12, 3>(C, b, ee_gl, tpos_w, torn_w, nullspace, lower, upper, range, rest, scr); }
+  else ik_solve(C, b, ee_gl, tpos_w, torn_w, use_orn, nullspace, lower, upper, range, rest, scr);
+}
+
 // ------------------------------------------------------------------ add-on ops ---------------------------------
 // controllers: update() bodies of /root/reference/diy_gym/addons/controllers/
 DG_FN void phase_actions(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   int ik_seen = 0;
   for (int k = 0; k < sc.nop; k++) {
-    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    const int* op = gc(sc.op_i) + DG_OP_I_W * k; const int* ia = gc(sc.oparg_i) + op[1]; const float* fa = gc(sc.oparg_f) + op[2];
     const float* a = op[3] >= 0 ? C.act + op[3] : nullptr;
     if (k < 128 && !((C.opmask[k >> 6] >> (k & 63)) & 1ull)) { if (op[0] == OP_IK_CTRL) ik_seen++; continue; }
     if (op[0] == OP_JOINT_CTRL && ln == 0) {                 // joint_controller.py:40-58
@@ -906,14 +1224,14 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
     } else if (op[0] == OP_IK_CTRL) {                         // ik_controller.py:51-80
       int mine = (ik_seen++ % nt) == ln;
       if (!mine) continue;
-      int b = ia[0], ee = ia[1], n = ia[2], use_orn = ia[3], nsp = ia[4]; int ndb = sc.body_i[DG_BODY_I_W * b + 4];
+      int b = ia[0], ee = ia[1], n = ia[2], use_orn = ia[3], nsp = ia[4]; int ndb = gc(sc.body_i)[DG_BODY_I_W * b + 4];
       float pos[3], quat[4], v[3], o[3], tq[4] = {0, 0, 0, 1};
       frame_com_state(C, sc.nb + ee, pos, quat, v, o);
       float tpos[3] = {pos[0] + a[0], pos[1] + a[1], pos[2] + a[2]};
       if (use_orn) { float dq[4]; q_from_euler(dq, a + 3); q_mul(tq, quat, dq); }
       const float* lim = fa + 2 + n;
-      float* scr = C.ws + sc.W_X + sc.ik_stride * (ln % (sc.n_ik < nt ? sc.n_ik : nt));
-      ik_solve(C, b, ee, tpos, tq, use_orn, nsp, lim, lim + ndb, lim + 2 * ndb, lim + 3 * ndb, scr);
+      float* scr = WSG(C, sc.X_IK) + sc.ik_stride * (ln % (sc.n_ik < nt ? sc.n_ik : nt));
+      ik_solve_any(C, b, ee, tpos, tq, use_orn, nsp, lim, lim + ndb, lim + 2 * ndb, lim + 3 * ndb, scr);
       for (int i = 0; i < n; i++) {
         int d = ia[5 + i];
         ST(S_MKP)[d] = fa[0]; ST(S_MKD)[d] = fa[1]; ST(S_MMAXF)[d] = fa[2 + i]; ST(S_MTPOS)[d] = scr[i]; ST(S_MTVEL)[d] = 0.f;
@@ -926,7 +1244,7 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
 DG_FN void phase_observe(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   for (int k = ln; k < sc.nop; k += nt) {
-    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    const int* op = gc(sc.op_i) + DG_OP_I_W * k; const int* ia = gc(sc.oparg_i) + op[1]; const float* fa = gc(sc.oparg_f) + op[2];
     float* o = op[4] >= 0 ? C.obs + op[4] : nullptr;
     if (op[0] == OP_JOINT_SENSOR) {                     // joint_state_sensor.py:46-57
       int n = ia[0], flags = ia[1], j = 0;
@@ -951,13 +1269,13 @@ DG_FN void phase_observe(const Env& C, int ln, int nt) {
       float dist = v_len(d);
       C.rew[op[5]] = -dist * fa[0]; C.term[op[6]] = dist < fa[1];
     } else if (op[0] == OP_ELECTRICITY) {               // electricity_cost.py:15-18
-      const int* bi = sc.body_i + DG_BODY_I_W * ia[0]; float s = 0.f;
+      const int* bi = gc(sc.body_i) + DG_BODY_I_W * ia[0]; float s = 0.f;
       for (int i = 0; i < bi[4]; i++) s += fabsf(ST(S_MAPPLIED)[bi[3] + i] / sc.dt * ST(S_QD)[bi[3] + i]);
       C.rew[op[5]] = -s * fa[0];
     } else if (op[0] == OP_STUCK_JOINT) {               // stuck_joint_cost.py:19-21 (intent; the reference raises NameError)
-      const int* bi = sc.body_i + DG_BODY_I_W * ia[0]; int stuck = 0;
+      const int* bi = gc(sc.body_i) + DG_BODY_I_W * ia[0]; int stuck = 0;
       for (int l = 0; l < bi[2]; l++) {
-        const int* li = sc.link_i + DG_LINK_I_W * (bi[1] + l); const float* lf = sc.link_f + DG_LINK_F_W * (bi[1] + l);
+        const int* li = shc(C.link_i) + DG_LINK_I_W * (bi[1] + l); const float* lf = shc(C.link_f) + DG_LINK_F_W * (bi[1] + l);
         if (li[3] < 0) continue;
         float qq = ST(S_Q)[li[3]];
         if (fminf(fabsf(lf[20] - qq), fabsf(lf[21] - qq)) < 0.01f) stuck = 1;
@@ -977,7 +1295,7 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
   ST(S_STEP)[0] = 0.f;
   uint32_t epoch = (uint32_t)ST(S_RESETS)[0];
   for (int k = 0; k < sc.nop; k++) {
-    const int* op = sc.op_i + DG_OP_I_W * k; const int* ia = sc.oparg_i + op[1]; const float* fa = sc.oparg_f + op[2];
+    const int* op = gc(sc.op_i) + DG_OP_I_W * k; const int* ia = gc(sc.oparg_i) + op[1]; const float* fa = gc(sc.oparg_f) + op[2];
     if (op[0] == OP_JOINT_RESET) {                      // joint_controller.py:36-38, ik_controller.py:47-49
       for (int i = 0; i < ia[0]; i++) { ST(S_Q)[ia[1 + i]] = fa[i]; ST(S_QD)[ia[1 + i]] = 0.f; }
     } else if (op[0] == OP_RESPAWN) {                   // respawn.py:31-39
@@ -988,17 +1306,17 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
       q_from_euler(dq, e); q_mul(qo, ip + 3, dq); for (int i = 0; i < 4; i++) ST(S_BQUAT)[4 * b + i] = qo[i];
       v_set(ST(S_BVEL) + 3 * b, 0, 0, 0); v_set(ST(S_BOMEGA) + 3 * b, 0, 0, 0);
     } else if (op[0] == OP_DYN_RANDOMIZE) {             // dynamics_randomizer.py:24-32 (log-uniform on nominal values)
-      int b = ia[0]; const int* bi = sc.body_i + DG_BODY_I_W * b;
+      int b = ia[0]; const int* bi = gc(sc.body_i) + DG_BODY_I_W * b;
       for (int l = -1; l < bi[2]; l++) {
-        int f = l < 0 ? b : sc.nb + bi[1] + l; int d = l < 0 ? -1 : sc.link_i[DG_LINK_I_W * (bi[1] + l) + 3];
+        int f = l < 0 ? b : sc.nb + bi[1] + l; int d = l < 0 ? -1 : shc(C.link_i)[DG_LINK_I_W * (bi[1] + l) + 3];
         if (l >= 0 && d < 0) continue;
         if (l < 0 && bi[4] > 0) continue;
         float u1 = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 64 + 2 * (l + 1)));
         float u2 = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 65 + 2 * (l + 1)));
         float ms = expf(logf(fa[0]) + u1 * (logf(fa[1]) - logf(fa[0]))), ds = expf(logf(fa[2]) + u2 * (logf(fa[3]) - logf(fa[2])));
-        PR(P_MASS)[f] = sc.param_def[DG_PO(C.sc, P_MASS) + f] * ms;
-        for (int i = 0; i < 3; i++) PR(P_INERTIA)[3 * f + i] = sc.param_def[DG_PO(C.sc, P_INERTIA) + 3 * f + i] * ms;
-        if (d >= 0) PR(P_JDAMP)[d] = sc.param_def[DG_PO(C.sc, P_JDAMP) + d] * ds;
+        PR(P_MASS)[f] = gc(sc.param_def)[DG_PO(C.sc, P_MASS) + f] * ms;
+        for (int i = 0; i < 3; i++) PR(P_INERTIA)[3 * f + i] = gc(sc.param_def)[DG_PO(C.sc, P_INERTIA) + 3 * f + i] * ms;
+        if (d >= 0) PR(P_JDAMP)[d] = gc(sc.param_def)[DG_PO(C.sc, P_JDAMP) + d] * ds;
       }
     }
   }
@@ -1024,7 +1342,7 @@ DG_HD void team_sync(unsigned tmask) {
 #endif
 
 // p.stepSimulation() (diy_gym.py:146,207); nsub = 0 only refreshes the link cache
-DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {
+DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {
   const DevScene& sc = SC;
   float h = sc.dt / (float)sc.substeps;
   DG_PHASE(phase_load(C, ln, nt));
@@ -1047,9 +1365,13 @@ DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE
       DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
     } else {
       DG_PHASE(phase_contact_rows(C, ln, nt, h));
-      for (int it = 0; it < sc.iters; it++) {
-        DG_PHASE(phase_pgs_unit(C, ln, nt, it, it + 1));
-        DG_PHASE(phase_pgs_contact(C, ln, nt));
+      if (WSI(C)[sc.W_HDR + WH_COUPLED] == 0) {
+        DG_PHASE(phase_pgs_full(C, ln, nt));        // no row couples two dynamic bodies: every body solves on its own
+      } else {
+        for (int it = 0; it < sc.iters; it++) {
+          DG_PHASE(phase_pgs_unit(C, ln, nt, it, it + 1));
+          DG_PHASE(phase_pgs_contact(C, ln, nt));
+        }
       }
     }
     DG_PHASE(phase_integrate(C, ln, nt, h));

@@ -21,6 +21,7 @@ struct LaunchArgs {
   float* state; float* param; const float* act; float* obs; float* rew; uint8_t* term;
   const uint8_t* mask; int n_envs; int mode; uint32_t seed; int env_off;
   unsigned long long opmask[2];
+  float* gws;   // cold workspace: one slot of sc.g_total floats per resident team
 };
 
 template <int T>
@@ -31,7 +32,16 @@ __global__ void __launch_bounds__(128) dg_step_kernel(const __grid_constant__ De
   const unsigned lane = threadIdx.x & 31u;
   const unsigned tmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(unsigned)(T - 1)));
   Env C;
-  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.seed = a.seed; C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
+  // the block's copy of the link tables sits behind the team workspaces
+  int* s_link_i = reinterpret_cast<int*>(smem + (size_t)teams_per_block * sc.w_total);
+  float* s_link_f = reinterpret_cast<float*>(s_link_i + ((DG_LINK_I_W * sc.nl + 3) & ~3));
+  float* s_link_x = s_link_f + DG_LINK_F_W * sc.nl;
+  for (int i = threadIdx.x; i < DG_LINK_I_W * sc.nl; i += blockDim.x) s_link_i[i] = sc.link_i[i];
+  for (int i = threadIdx.x; i < DG_LINK_F_W * sc.nl; i += blockDim.x) s_link_f[i] = sc.link_f[i];
+  for (int i = threadIdx.x; i < 16 * sc.nl; i += blockDim.x) s_link_x[i] = sc.link_x[i];
+  __syncthreads();
+  C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
+  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * teams_per_block + team) * sc.g_total; C.seed = a.seed; C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
   for (int e = blockIdx.x * teams_per_block + team; e < a.n_envs; e += gridDim.x * teams_per_block) {
     if (a.mask != nullptr && a.mask[e] == 0) continue;
     C.st = a.state + (size_t)e * sc.S; C.pr = a.param + (size_t)e * sc.P;
@@ -94,13 +104,41 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 
 // per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1) = 21 floats
 #define VS_W 21
-__global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth, int tiles_per_env) {
-  extern __shared__ __align__(16) float vs[];
+#define DG_TILE 32   // square pixel tile per block; 256 threads, 4 pixels each
+__global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
+                                                        int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) float vs[];       // [nv][VS_W] then the candidate bit set
   __shared__ float camRp[12];
-  const int e = blockIdx.x / tiles_per_env, tile = blockIdx.x % tiles_per_env;
+  __shared__ float cone[5];                          // unit axis of the tile (3), tan and 1/cos of its half angle
+  const int tiles = tiles_x * tiles_y;
+  const int e = blockIdx.x / tiles, tile = blockIdx.x % tiles, ty = tile / tiles_x, tx = tile % tiles_x;
   const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
   const int width = ci[1], height = ci[2];
-  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.pr = nullptr;
+  unsigned* cand = reinterpret_cast<unsigned*>(vs + VS_W * sc.nv);
+  const int ncw = (sc.nv + 31) / 32;
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr;
+  C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
+  const float fov = cf[7], nearp = cf[8], farp = cf[9];
+  const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
+  if (threadIdx.x < ncw) cand[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) {
+    float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0}, Rl[9], t[3];
+    if (ci[0] >= 0) { float q[4]; frame_link_pose(C, ci[0], pp, q); q_to_mat(Rp, q); }
+    q_to_mat(Rl, cf + 3); m_mul(camRp, Rp, Rl); m_vec(t, Rp, cf); v_add(camRp + 9, pp, t);
+    // cone around the tile: axis through the tile centre, half angle to the farthest corner
+    float x0 = tx * DG_TILE, x1 = fminf((float)width, x0 + DG_TILE), y0 = ty * DG_TILE, y1 = fminf((float)height, y0 + DG_TILE);
+    float dcc[3] = {((0.5f * (x0 + x1)) / width * 2 - 1) * th * aspect, (1 - (0.5f * (y0 + y1)) / height * 2) * th, -1.0f}, axis[3];
+    m_vec(axis, camRp, dcc); float an = 1.0f / v_len(axis); v_scale(axis, axis, an);
+    float cmin = 1.0f;
+    for (int k = 0; k < 4; k++) {
+      float cx = (k & 1) ? x1 : x0, cy = (k & 2) ? y1 : y0;
+      float dk[3] = {(cx / width * 2 - 1) * th * aspect, (1 - cy / height * 2) * th, -1.0f}, dw[3];
+      m_vec(dw, camRp, dk); cmin = fminf(cmin, v_dot(dw, axis) / v_len(dw));
+    }
+    cmin = fmaxf(cmin * 0.9999f, 0.05f);
+    cone[0] = axis[0]; cone[1] = axis[1]; cone[2] = axis[2]; cone[3] = sqrtf(fmaxf(1.0f - cmin * cmin, 0.f)) / cmin; cone[4] = 1.0f / cmin;
+  }
+  __syncthreads();
   for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
     const int* vi = sc.vis_i + DG_VIS_I_W * s; const float* vf = sc.vis_f + DG_VIS_F_W * s; float* o = vs + VS_W * s;
     if (vi[2]) { for (int i = 0; i < 12; i++) o[i] = sc.vis_wb[12 * s + i]; }
@@ -112,34 +150,36 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
     for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
     for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
     o[19] = int_as_float(vi[1]); o[20] = vf[15];
-  }
-  if (threadIdx.x == 0) {
-    float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0}, Rl[9], t[3];
-    if (ci[0] >= 0) { float q[4]; frame_link_pose(C, ci[0], pp, q); q_to_mat(Rp, q); }
-    q_to_mat(Rl, cf + 3); m_mul(camRp, Rp, Rl); m_vec(t, Rp, cf); v_add(camRp + 9, pp, t);
+    // bounding sphere against the tile cone (conservative): perpendicular distance <= depth * tan(a) + r / cos(a)
+    float vc[3]; v_sub(vc, o + 9, camRp + 9);
+    float t_ax = v_dot(vc, cone), perp2 = fmaxf(v_dot(vc, vc) - t_ax * t_ax, 0.f), r = o[20];
+    float lim = fmaxf(t_ax, 0.f) * cone[3] + r * cone[4];
+    if (t_ax > -r && perp2 <= lim * lim) atomicOr(&cand[s >> 5], 1u << (s & 31));
   }
   __syncthreads();
-  const float fov = cf[7], nearp = cf[8], farp = cf[9];
-  const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
-  const int npx = width * height, per_tile = (npx + tiles_per_env - 1) / tiles_per_env;
-  const int p0 = tile * per_tile, p1 = min(npx, p0 + per_tile);
+  const int npx = width * height;
   float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx;
-  for (int px = p0 + threadIdx.x; px < p1; px += blockDim.x) {
-    int j = px / width, i = px - j * width;
+  for (int k = threadIdx.x; k < DG_TILE * DG_TILE; k += blockDim.x) {
+    int i = tx * DG_TILE + (k % DG_TILE), j = ty * DG_TILE + (k / DG_TILE);
+    if (i >= width || j >= height) continue;
+    int px = j * width + i;
     float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f}, dw[3];
     m_vec(dw, camRp, dc);
     float dd = v_dot(dw, dw);
     float best = farp; int hs = -1; float hn[3] = {0, 0, 1};
-    for (int s = 0; s < sc.nv; s++) {
-      const float* o = vs + VS_W * s;
-      float oc[3]; v_sub(oc, camRp + 9, o + 9);
-      // bounding-sphere reject: closest approach of the ray to the shape centre
-      float b = v_dot(oc, dw), c2 = v_dot(oc, oc) - o[20] * o[20];
-      if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
-      float ol[3], dl[3], tt, nn[3];
-      mT_vec(ol, o, oc); mT_vec(dl, o, dw);
-      if (ray_shape(float_as_int(o[19]), o + 12, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, o, nn); }
+    for (int wd = 0; wd < ncw; wd++) {
+      unsigned bits = cand[wd];
+      while (bits) {
+        int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1;
+        const float* o = vs + VS_W * s;
+        float oc[3]; v_sub(oc, camRp + 9, o + 9);
+        float b = v_dot(oc, dw), c2 = v_dot(oc, oc) - o[20] * o[20];   // per-ray bounding-sphere reject
+        if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
+        float ol[3], dl[3], tt, nn[3];
+        mT_vec(ol, o, oc); mT_vec(dl, o, dw);
+        if (ray_shape(float_as_int(o[19]), o + 12, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, o, nn); }
+      }
     }
     float r, g, bl, dz;
     if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
@@ -161,11 +201,12 @@ struct DgWorld {
   DevScene dev;            // pointers re-targeted to device memory
   int* d_ints = nullptr; float* d_floats = nullptr;
   int n_envs = 0, device = 0, team = 1, block_threads = 64, grid = 1, sm_count = 148;
-  size_t smem = 0;
+  size_t smem = 0, smem_cap = 0;
   DgBufferTable buf{};
   bool bound = false;
   uint32_t seed = 1234u; int env_off = 0;
   unsigned long long opmask[2] = {~0ull, ~0ull};
+  float* gws = nullptr;
   int64_t launches = 0;
   std::string err;
 };
@@ -174,7 +215,8 @@ static std::string g_create_err;
 #define CK(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (w)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DG_E_CUDA; } } while (0)
 
 template <int T> static cudaError_t configure(DgWorld* w) {
-  cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem);
+  // the attribute is per function, not per world: always allow the device maximum so that worlds of different sizes coexist
+  cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap);
   if (e != cudaSuccess) return e;
   int occ = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dg_step_kernel<T>, w->block_threads, w->smem);
@@ -215,24 +257,39 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   if (e != cudaSuccess) { g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
   w->sm_count = prop.multiProcessorCount;
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
+  w->smem_cap = smem_cap;
   if (team == 0) {
-    // built-in choice: enough lanes for the per-item phases, few enough that many environments stay resident
+    // built-in choice: 4 lanes per environment (two lanes carry the per-body phases of a two-arm scene, the rest
+    // help in the per-column / per-pair / per-row phases); DG_TEAM overrides
     const char* env_team = getenv("DG_TEAM");
     team = env_team ? atoi(env_team) : 4;
     if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
   }
   const char* env_block = getenv("DG_BLOCK");
-  int block = env_block ? atoi(env_block) : 64;
+  int block = env_block ? atoi(env_block) : 128;
+  if (!env_block) {
+    // enough blocks to spread over all SMs a few times: shrink the block while the grid would be smaller than 3 waves
+    while (block > 32 && block / 2 >= team && (n_envs + (block / team) - 1) / (block / team) < 3 * w->sm_count) block /= 2;
+  }
   if (block < team) block = team;
   if (block > 128) block = 128;
   block = (block / team) * team;
-  for (;;) {
-    if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+  // workspace placement (dg_scene.h): frames / joint transforms / articulated-body transients always live in the
+  // L2-backed cold workspace and the solver state in shared memory; the contact arrays default to the cold workspace
+  // too (mode 3: measured faster on every example scene because more environments stay resident per SM);
+  // DG_WS_MODE=2 keeps them in shared memory.
+  const char* env_mode = getenv("DG_WS_MODE");
+  int ws_mode = env_mode ? atoi(env_mode) : 3;
+  if (ws_mode != 2 && ws_mode != 3) ws_mode = 3;
+  if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+  {
     size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
+    const int nl_ = w->hs.dev.nl;
+    size_t tables = (size_t)(((DG_LINK_I_W * nl_ + 3) & ~3) + (DG_LINK_F_W + 16) * nl_ + 4) * sizeof(float);   // block-shared link tables
     int teams = block / team;
-    while (teams > 1 && per_team * teams > smem_cap) teams--;
-    if (per_team * teams <= smem_cap) { w->block_threads = teams * team; w->smem = per_team * teams; break; }
-    g_create_err = "scene workspace (" + std::to_string(per_team) + " B per environment) exceeds shared memory"; delete w; return DG_E_NOMEM;
+    while (teams > 1 && per_team * teams + tables > smem_cap) teams--;
+    if (per_team * teams + tables > smem_cap) { g_create_err = "scene workspace (" + std::to_string(per_team) + " B per environment) exceeds shared memory"; delete w; return DG_E_NOMEM; }
+    w->block_threads = teams * team; w->smem = per_team * teams + tables;
   }
   w->team = team;
   // upload the constant tables
@@ -244,6 +301,12 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   w->hs.point(w->dev, w->d_ints, w->d_floats);
   e = configure_any(w);
   if (e != cudaSuccess) { g_create_err = std::string("kernel configuration: ") + cudaGetErrorString(e); dg_world_destroy(w); return DG_E_CUDA; }
+  {
+    size_t slots = (size_t)w->grid * (w->block_threads / w->team);
+    size_t bytes = std::max<size_t>(slots * (size_t)w->hs.dev.g_total * sizeof(float), 16);
+    if (cudaMalloc(&w->gws, bytes) != cudaSuccess) { g_create_err = "cudaMalloc of the cold workspace failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
+    w->dev.g_total = w->hs.dev.g_total;
+  }
   *out = w;
   return DG_OK;
 }
@@ -252,6 +315,7 @@ void dg_world_destroy(DgWorld* w) {
   if (!w) return;
   if (w->d_ints) cudaFree(w->d_ints);
   if (w->d_floats) cudaFree(w->d_floats);
+  if (w->gws) cudaFree(w->gws);
   delete w;
 }
 
@@ -301,7 +365,7 @@ int dg_init_state(DgWorld* w, void* stream) {
 static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "buffers not bound"; return DG_E_UNBOUND; }
-  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}};
+  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws};
   CK(w, launch_any(w, a, (cudaStream_t)stream));
   return DG_OK;
 }
@@ -314,14 +378,11 @@ int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* strea
   const DevScene& d = w->dev;
   if (cam < 0 || cam >= d.ncam) { w->err = "dg_render: no such camera"; return DG_E_ARG; }
   const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
-  int npx = ci[1] * ci[2];
-  int tiles = std::max(1, std::min((npx + 2047) / 2048, 64));
-  size_t smem = (size_t)std::max(d.nv, 1) * VS_W * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
-  attr_set = true;
+  int tiles_x = (ci[1] + DG_TILE - 1) / DG_TILE, tiles_y = (ci[2] + DG_TILE - 1) / DG_TILE;
+  size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)(d.nv + 31) / 32 + 4) * sizeof(float);
+  if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   w->launches++;
-  dg_render_kernel<<<w->n_envs * tiles, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, tiles);
+  dg_render_kernel<<<w->n_envs * tiles_x * tiles_y, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, tiles_x, tiles_y);
   CK(w, cudaGetLastError());
   return DG_OK;
 }

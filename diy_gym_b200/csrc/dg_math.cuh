@@ -7,7 +7,9 @@
 #if defined(__CUDACC__)
 #define DG_HD __host__ __device__ __forceinline__
 #define DG_FN __host__ __device__ inline
+#define DG_NOINLINE __noinline__
 #else
+#define DG_NOINLINE
 #define DG_HD inline
 #define DG_FN inline
 #endif

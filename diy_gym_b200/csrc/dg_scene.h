@@ -14,15 +14,15 @@
 
 namespace dg {
 
-// number of per-dof hot arrays in the workspace (q, qd, kp, kd, tpos, tvel, maxf, applied, jtorque, tdamp, qdd)
-enum { D_Q = 0, D_QD, D_KP, D_KD, D_TPOS, D_TVEL, D_MAXF, D_APPLIED, D_JTQ, D_TDAMP, D_QDD, D_COUNT };
+// per-dof hot arrays in the workspace: q, qd, applied motor impulse, joint torque (applied + damping, fixed for the step)
+enum { D_Q = 0, D_QD, D_APPLIED, D_TAU, D_COUNT };
 // body plan columns
-enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_W };
+enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_NRS, BP_AOFF, BP_GS, BP_W };
 // workspace header ints
-enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_FLAGS, WH_COUNT = 8 };
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_COUNT = 8 };
 // row record strides
 enum { UR_RHS = 0, UR_DINV, UR_LO, UR_HI, UR_APPLIED, UR_COL, UR_MOTOR, UR_W = 8 };
-enum { CR_RHS = 0, CR_DINV, CR_LO, CR_HI, CR_APPLIED, CR_MU, CR_DA, CR_DB, CR_PARENT, CR_HDR = 10 };
+enum { CR_RHS = 0, CR_DINV, CR_LO, CR_HI, CR_APPLIED, CR_MU, CR_DA, CR_DB, CR_PARENT, CR_HDR = 12 };
 enum { CT_FA = 0, CT_FB, CT_PA = 2, CT_PB = 5, CT_N = 8, CT_DIST = 11, CT_MU = 12, CT_W = 13 };
 
 struct DevScene {
@@ -43,13 +43,20 @@ struct DevScene {
   const float* shape_wb;  // [ns][12] world rotation (9) + centre (3) of baked shapes
   const float* vis_wb;    // [nv][12] same for baked visual shapes
   const float* link_x;    // [nl][16] joint rest rotation R0 (9), motion subspace angular (3) / linear (3), pad
+  // broad-phase groups: all candidate pairs between one baked static shape and one dynamic body share a
+  // (static shape) x (body bounding sphere) pre-test; the remaining pairs are tested one by one
+  int ngrp, nloose;
+  const int* grp_i;       // [ngrp][4] static shape, dynamic body, first entry in grp_pairs, count
+  const int* grp_pairs;   // pair indices, grouped
+  const int* loose_pairs; // [nloose] pair indices outside any group
+  const float* body_reach;// [nb] radius about the base COM that contains every collision shape of the body
   // ---- workspace layout (float offsets) ----
-  int w_total;
+  int w_total, g_total, ws_mode;   // hot (shared) and cold (global) floats per team
   int W_HDR, W_BST, W_DOF, W_EXT, W_KIN, W_LINK, W_MINV, W_DV, W_I0, W_UCNT, W_X;
   // region X, articulated-body phase
   int X_ABA, X_LNK, X_I0T;
   // region X, constraint phase
-  int X_SHW, X_CON, X_SURV, X_CTMP, X_UROW, X_CROW, X_MSCR;
+  int X_SHW, X_CON, X_SURV, X_CTMP, X_UROW, X_CROW, X_MSCR, X_AMAT, X_IK;
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
 };
 
@@ -75,8 +82,8 @@ struct HostScene {
   std::string error;
 
   // offsets of every table inside ints / floats (so a device copy can be re-pointed)
-  struct Off { size_t body_i, link_i, shape_i, pair_i, vis_i, op_i, oparg_i, cam_i, dyn_body, body_plan, frame_slot, link_depth, shape_slot;
-               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x; } off;
+  struct Off { size_t body_i, link_i, shape_i, pair_i, vis_i, op_i, oparg_i, cam_i, dyn_body, body_plan, frame_slot, link_depth, shape_slot, grp_i, grp_pairs, loose_pairs;
+               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x, body_reach; } off;
 
   static void quat_to_mat(const double* q, double* m) {
     double x = q[0], y = q[1], z = q[2], w = q[3];
@@ -91,12 +98,13 @@ struct HostScene {
     d.vis_i = ib + off.vis_i; d.op_i = ib + off.op_i; d.oparg_i = ib + off.oparg_i; d.cam_i = ib + off.cam_i;
     d.dyn_body = ib + off.dyn_body; d.body_plan = ib + off.body_plan; d.frame_slot = ib + off.frame_slot;
     d.link_depth = ib + off.link_depth; d.shape_slot = ib + off.shape_slot;
+    d.grp_i = ib + off.grp_i; d.grp_pairs = ib + off.grp_pairs; d.loose_pairs = ib + off.loose_pairs; d.body_reach = fb + off.body_reach;
     d.body_f = fb + off.body_f; d.link_f = fb + off.link_f; d.shape_f = fb + off.shape_f; d.vis_f = fb + off.vis_f;
     d.oparg_f = fb + off.oparg_f; d.cam_f = fb + off.cam_f; d.param_def = fb + off.param_def; d.state_def = fb + off.state_def;
     d.shape_wb = fb + off.shape_wb; d.vis_wb = fb + off.vis_wb; d.link_x = fb + off.link_x;
   }
 
-  bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team) {
+  bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team, int ws_mode = 0) {
     if (ni < 2 + 3 * DG_NSECTIONS || ibuf[0] != (int32_t)DG_SCENE_MAGIC || ibuf[1] != DG_NSECTIONS) { error = "bad scene magic / section count"; return false; }
     auto sec_off = [&](int s) { return (size_t)ibuf[2 + 3 * s + 1]; };
     auto sec_len = [&](int s) { return (size_t)ibuf[2 + 3 * s + 2]; };
@@ -139,7 +147,7 @@ struct HostScene {
 
     // ---- plan tables ----
     std::vector<int> dyn_body, body_plan((size_t)d.nb * BP_W, 0), frame_slot(d.nframes, -1), link_depth(std::max(d.nl, 1), 0), shape_slot(std::max(d.ns, 1), -1);
-    int nslot = 0, gv = 0, minv = 0, i0 = 0, nfloat = 0, GD = 1, max_depth = 0, max_nlb = 0;
+    int nslot = 0, gv = 0, minv = 0, i0 = 0, nfloat = 0, GD = 1, max_depth = 0, max_nlb = 0, amat = 0;
     for (int b = 0; b < d.nb; b++) {
       const int32_t* bi = body_i + DG_BODY_I_W * b; int* bp = &body_plan[(size_t)b * BP_W];
       int kind = bi[0], l0 = bi[1], nlb = bi[2], ndb = bi[4], baked = bi[7];
@@ -147,8 +155,12 @@ struct HostScene {
       if (kind != 0) {
         bp[BP_DI] = (int)dyn_body.size(); dyn_body.push_back(b);
         int gdim = (kind == 2 ? 6 : 0) + ndb;
-        bp[BP_GDIM] = gdim; bp[BP_GVOFF] = gv; bp[BP_MINVOFF] = minv; gv += gdim; minv += gdim * gdim; GD = std::max(GD, gdim);
+        int gs = (gdim + 3) & ~3;   // M^-1 rows are padded to a multiple of 4 floats (zero filled) for 128-bit loads
+        bp[BP_GDIM] = gdim; bp[BP_GS] = gs; bp[BP_GVOFF] = gv; bp[BP_MINVOFF] = minv; gv += gs; minv += gdim * gs; GD = std::max(GD, gdim);
         if (kind == 2) { bp[BP_I0OFF] = 36 * nfloat; nfloat++; i0 += 36; }
+        // register-resident solver path: at most nrs unit rows (every motor + a couple of active limits)
+        int nrs = std::min(2 * ndb, ((ndb + 2 + 3) / 4) * 4); nrs = std::min(((nrs + 3) / 4) * 4, 16);
+        bp[BP_NRS] = ndb > 0 ? nrs : 0; bp[BP_AOFF] = amat; amat += bp[BP_NRS] * bp[BP_NRS];
         max_nlb = std::max(max_nlb, nlb);
       }
       if (kind != 0 || !baked) {
@@ -192,6 +204,43 @@ struct HostScene {
         } else if (jt == 2) for (int i = 0; i < 3; i++) link_x[16 * gl + 12 + i] = (float)a[i];
       }
     }
+    // ---- broad-phase groups and body bounding radii ----
+    std::vector<float> body_reach(d.nb, 0.f);
+    {
+      const double* link_f = fbuf + sec_off(SEC_LINK_F);
+      std::vector<double> lreach(std::max(d.nl, 1), 0.0);
+      auto norm3 = [](const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+      for (int gl = 0; gl < d.nl; gl++) {
+        const double* lf = link_f + DG_LINK_F_W * gl; const int32_t* li = link_i + DG_LINK_I_W * gl;
+        double travel = li[2] == 2 ? std::max(std::fabs(lf[20]), std::fabs(lf[21])) : 0.0;
+        lreach[gl] = (li[1] < 0 ? 0.0 : lreach[li[1]]) + norm3(lf + 4) + norm3(lf + 7) + travel;
+      }
+      for (int s = 0; s < d.ns; s++) {
+        int b = shape_i[DG_SHAPE_I_W * s], f = shape_i[DG_SHAPE_I_W * s + 1];
+        double r = (f < d.nb ? 0.0 : lreach[f - d.nb]) + norm3(shape_f + DG_SHAPE_F_W * s) + shape_f[DG_SHAPE_F_W * s + 11];
+        body_reach[b] = std::max(body_reach[b], (float)(r * 1.0001 + 1e-6));
+      }
+    }
+    std::vector<int> grp_i, grp_pairs, loose_pairs;
+    {
+      std::vector<std::vector<int>> members;   // per group
+      std::vector<long long> keys;
+      for (int k = 0; k < d.npair; k++) {
+        int sa = pair_i[2 * k], sb = pair_i[2 * k + 1];
+        bool ba = shape_i[DG_SHAPE_I_W * sa + 3] != 0, bb = shape_i[DG_SHAPE_I_W * sb + 3] != 0;
+        int stat = -1, dynb = -1;
+        if (ba && !bb) { stat = sa; dynb = shape_i[DG_SHAPE_I_W * sb]; } else if (bb && !ba) { stat = sb; dynb = shape_i[DG_SHAPE_I_W * sa]; }
+        if (stat < 0 || body_i[DG_BODY_I_W * dynb] == 0) { loose_pairs.push_back(k); continue; }
+        long long key = (long long)stat * d.nb + dynb; size_t g = 0;
+        for (; g < keys.size(); g++) if (keys[g] == key) break;
+        if (g == keys.size()) { keys.push_back(key); members.emplace_back(); }
+        members[g].push_back(k);
+      }
+      for (size_t g = 0; g < keys.size(); g++) {
+        grp_i.push_back((int)(keys[g] / d.nb)); grp_i.push_back((int)(keys[g] % d.nb)); grp_i.push_back((int)grp_pairs.size()); grp_i.push_back((int)members[g].size());
+        grp_pairs.insert(grp_pairs.end(), members[g].begin(), members[g].end());
+      }
+    }
     int GP = 1;
     auto gdim_of_shape = [&](int s) { int b = shape_i[DG_SHAPE_I_W * s]; return body_plan[(size_t)b * BP_W + BP_GDIM]; };
     for (int k = 0; k < d.npair; k++) GP = std::max(GP, gdim_of_shape(pair_i[2 * k]) + gdim_of_shape(pair_i[2 * k + 1]));
@@ -202,53 +251,67 @@ struct HostScene {
     auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };
     off.dyn_body = put_vi(dyn_body); off.body_plan = put_vi(body_plan); off.frame_slot = put_vi(frame_slot);
     off.link_depth = put_vi(link_depth); off.shape_slot = put_vi(shape_slot);
-    off.shape_wb = put_vf(shape_wb); off.vis_wb = put_vf(vis_wb); off.link_x = put_vf(link_x);
+    off.shape_wb = put_vf(shape_wb); off.vis_wb = put_vf(vis_wb); off.link_x = put_vf(link_x); off.body_reach = put_vf(body_reach);
+    off.grp_i = put_vi(grp_i); off.grp_pairs = put_vi(grp_pairs); off.loose_pairs = put_vi(loose_pairs);
     point(d, ints.data(), floats.data());
 
     d.ndyn = (int)dyn_body.size(); d.nslot = nslot; d.nshw = nshw; d.nfloat = nfloat; d.GD = GD; d.GP = GP;
-    d.max_depth = max_depth; d.max_nlb = max_nlb; d.n_ik = n_ik;
+    d.max_depth = max_depth; d.max_nlb = max_nlb; d.n_ik = n_ik; d.ngrp = (int)grp_i.size() / 4; d.nloose = (int)loose_pairs.size();
 
     // ---- workspace layout ----
-    int o = 0;
-    auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };   // keep 16-byte alignment of every region
-    d.W_HDR = take(WH_COUNT);
-    d.W_BST = take(13 * d.ndyn);
-    d.W_DOF = take(D_COUNT * d.nd);
-    d.W_EXT = take(6 * nslot);
-    d.W_KIN = take(18 * nslot);
-    d.W_LINK = take(19 * d.nl);
-    d.W_MINV = take(minv);
-    d.W_DV = take(gv);
-    d.W_I0 = take(i0);
-    d.W_UCNT = take(d.ndyn);
-    d.W_X = o;
-    // phase A (articulated-body algorithm)
-    int xa = 0;
-    auto takex = [&](int& x, int n) { int r = d.W_X + x; x += (n + 3) & ~3; return r; };
-    d.X_ABA = takex(xa, 39 * nslot);
-    d.X_LNK = takex(xa, 7 * d.nl);
-    d.X_I0T = takex(xa, 36 * nfloat);
-    // phase B (collision, rows, solver)
-    int xb = 0;
-    d.crow_stride = 2 * GP + CR_HDR;
+    // Every region goes either to the HOT workspace (shared memory, offset >= 0) or to the COLD workspace (one
+    // global-memory slot per resident team, L1/L2 resident, offset encoded as ~offset < 0).  Inside each memory the
+    // articulated-body transients (phase A), the constraint-phase arrays (phase B) and the IK scratch (phase C)
+    // alias each other.  ws_mode: 2 = contacts, contact rows and shape poses in shared memory (bodies that rest on
+    // contacts), 3 = in the cold workspace (scenes whose bodies rarely touch).
+    enum { RC_SMALL = 0, RC_KIN, RC_ABA, RC_SOLVE, RC_CONTACT, RC_SCRATCH };
+    auto is_cold = [&](int rc) {
+      if (rc == RC_SMALL || rc == RC_SOLVE) return false;                  // header, base state, q / qd, dv, M^-1, unit rows, A: shared
+      if (rc == RC_KIN || rc == RC_ABA || rc == RC_SCRATCH) return true;   // frames, joint transforms, ABA transients, scratch: global
+      return ws_mode == 3;                                                 // contacts, contact rows, shape poses: per scene
+    };
+    int fix[2] = {0, 0};                      // persistent part, per memory
+    int ph[2][3] = {{0, 0, 0}, {0, 0, 0}};    // phase A / B / C parts, per memory
+    // only the contact regions are addressed through the hot/cold selector (negative = cold); the others have a fixed home
+    auto enc_rc = [&](int rc, int cold, int off) { return (rc == RC_CONTACT && cold) ? ~off : off; };
+    auto take = [&](int rc, int n) { int c = is_cold(rc); int r = fix[c]; fix[c] += (n + 3) & ~3; return std::make_pair(c, r); };
+    auto fixed = [&](int rc, int n) { auto pr = take(rc, n); return enc_rc(rc, pr.first, pr.second); };
+    d.W_HDR = fixed(RC_SMALL, WH_COUNT);
+    d.W_BST = fixed(RC_SMALL, 13 * d.ndyn);
+    d.W_DOF = fixed(RC_SMALL, D_COUNT * d.nd);
+    d.W_DV = fixed(RC_SMALL, gv);
+    d.W_UCNT = fixed(RC_SMALL, d.ndyn);
+    d.W_MINV = fixed(RC_SOLVE, minv);
+    d.W_KIN = fixed(RC_KIN, 12 * nslot);
+    d.W_LINK = fixed(RC_KIN, 19 * d.nl);
+    d.W_I0 = fixed(RC_KIN, i0);
+    d.W_EXT = 0; d.W_X = 0;
+    // phase regions: offsets are relative to the end of the persistent part of their memory, fixed up below
+    struct Pending { int* field; int cold, phase, rel, rc; };
+    std::vector<Pending> pend;
+    auto phase_take = [&](int* field, int rc, int phase, int n) { int c = is_cold(rc); pend.push_back({field, c, phase, ph[c][phase], rc}); ph[c][phase] += (n + 3) & ~3; };
+    d.crow_stride = 2 * (d.GP = GP = (GP + 3) & ~3) + CR_HDR;
     d.ctmp_stride = 1 + 4 * CT_W;
     d.mscr_stride = max_nlb + 6 * (max_depth + 2);
-    d.X_SHW = takex(xb, 12 * nshw);
-    d.X_CON = takex(xb, CT_W * d.maxc);
-    d.X_UROW = takex(xb, UR_W * 2 * d.nd);
-    d.X_SURV = takex(xb, (d.npair + 31) / 32 + 1);
-    int xb_rows = xb, xb_tmp = xb, xb_scr = xb;
-    d.X_CROW = takex(xb_rows, d.crow_stride * 3 * d.maxc);
-    d.X_CTMP = takex(xb_tmp, d.ctmp_stride * team);     // aliases the contact rows (rows are built after collision)
-    d.X_MSCR = takex(xb_scr, d.mscr_stride * team);     // aliases the contact rows (M^-1 columns precede the rows)
-    xb = std::max(xb_rows, std::max(xb_tmp, xb_scr));
-    // phase C (inverse kinematics scratch, used before the physics step)
     int gj = 1;
     for (int b = 0; b < d.nb; b++) gj = std::max(gj, (int)body_i[DG_BODY_I_W * b + 4]);
     d.ik_stride = (9 * (max_depth + 2) + 6 * gj + std::max(gj * gj, 36) + 8 * gj + 32 + 3) & ~3;
-    int xc = d.ik_stride * std::min(team, std::max(n_ik, 1));
-    if (n_ik == 0) xc = 0;
-    d.w_total = d.W_X + std::max(xa, std::max(xb, xc));
+    phase_take(&d.X_ABA, RC_ABA, 0, 45 * nslot);
+    phase_take(&d.X_LNK, RC_ABA, 0, 7 * d.nl);
+    phase_take(&d.X_I0T, RC_ABA, 0, 36 * nfloat);
+    phase_take(&d.X_SHW, RC_CONTACT, 1, 12 * nshw);
+    phase_take(&d.X_CON, RC_CONTACT, 1, CT_W * d.maxc);
+    phase_take(&d.X_SURV, RC_CONTACT, 1, (d.npair + 31) / 32 + 1);
+    phase_take(&d.X_UROW, RC_SOLVE, 1, UR_W * 2 * d.nd);
+    phase_take(&d.X_AMAT, RC_SOLVE, 1, amat);
+    phase_take(&d.X_CROW, RC_CONTACT, 1, d.crow_stride * 3 * d.maxc);
+    phase_take(&d.X_CTMP, RC_SCRATCH, 1, d.ctmp_stride * team);
+    phase_take(&d.X_MSCR, RC_SCRATCH, 1, d.mscr_stride * team);
+    phase_take(&d.X_IK, RC_SCRATCH, 2, n_ik ? d.ik_stride * std::min(team, n_ik) : 0);
+    for (auto& pd : pend) *pd.field = enc_rc(pd.rc, pd.cold, fix[pd.cold] + pd.rel);
+    d.w_total = fix[0] + std::max(ph[0][0], std::max(ph[0][1], ph[0][2]));
+    d.g_total = fix[1] + std::max(ph[1][0], std::max(ph[1][1], ph[1][2]));
+    d.ws_mode = ws_mode;
     return true;
   }
 };

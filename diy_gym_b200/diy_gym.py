@@ -47,7 +47,7 @@ class DIYGym(Receptor):
         iterations = config.get('solver_iterations', 150)
         gravity = config.get('gravity', [0.0, 0.0, -9.81])
         self.builder = SceneBuilder(timestep=timestep, substeps=max(sub_steps, 1), iterations=iterations, gravity=gravity,
-                                    hot_start=self.hot_start, max_contacts=int(config.get('max_contacts', 16)))
+                                    hot_start=self.hot_start, max_contacts=int(config.get('max_contacts', 0)))
         self.world = None
 
         self.models = OrderedDict(sorted({child.name: Model(child, env=self) for child in config.find_all('model')}.items(),

@@ -14,18 +14,18 @@ using namespace dg;
 struct EmulWorld {
   HostScene hs;
   int n_envs, team;
-  std::vector<float> state, param, ws;
+  std::vector<float> state, param, ws, wg;
   uint32_t seed = 1234u; int env_off = 0;
   unsigned long long opmask[2] = {~0ull, ~0ull};
 };
 
 extern "C" {
-EmulWorld* dge_create(const int32_t* ibuf, int ni, const double* fbuf, int nf, int n_envs, int team) {
+EmulWorld* dge_create(const int32_t* ibuf, int ni, const double* fbuf, int nf, int n_envs, int team, int ws_mode) {
   EmulWorld* w = new EmulWorld();
-  if (!w->hs.build(ibuf, ni, fbuf, nf, team)) { delete w; return nullptr; }
+  if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode)) { delete w; return nullptr; }
   w->n_envs = n_envs; w->team = team;
   const DevScene& d = w->hs.dev;
-  w->state.resize((size_t)n_envs * d.S + 1); w->param.resize((size_t)n_envs * d.P + 1); w->ws.assign((size_t)d.w_total + 16, 0.f);
+  w->state.resize((size_t)n_envs * d.S + 1); w->param.resize((size_t)n_envs * d.P + 1); w->ws.assign((size_t)d.w_total + 16, 0.f); w->wg.assign((size_t)d.g_total + 16, 0.f);
   for (int e = 0; e < n_envs; e++) {
     for (int i = 0; i < d.S; i++) w->state[(size_t)e * d.S + i] = d.state_def[i];
     for (int i = 0; i < d.P; i++) w->param[(size_t)e * d.P + i] = d.param_def[i];
@@ -36,11 +36,12 @@ void dge_destroy(EmulWorld* w) { delete w; }
 float* dge_state(EmulWorld* w) { return w->state.data(); }
 float* dge_param(EmulWorld* w) { return w->param.data(); }
 int dge_ws_floats(EmulWorld* w) { return w->hs.dev.w_total; }
+int dge_cold_floats(EmulWorld* w) { return w->hs.dev.g_total; }
 void dge_set_action_mask(EmulWorld* w, const uint8_t* en, int n) { w->opmask[0] = w->opmask[1] = ~0ull; for (int k = 0; k < n && k < 128; k++) if (!en[k]) w->opmask[k >> 6] &= ~(1ull << (k & 63)); }
 void dge_set_seed(EmulWorld* w, uint32_t seed, int env_off) { w->seed = seed; w->env_off = env_off; }
 static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* rew, uint8_t* term) {
   const DevScene& d = w->hs.dev; Env C;
-  C.sc = &d; C.ws = w->ws.data(); C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
+  C.sc = &d; C.ws = w->ws.data(); C.wg = w->wg.data(); C.link_i = d.link_i; C.link_f = d.link_f; C.link_x = d.link_x; C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
   C.act = act ? act + (size_t)e * d.n_act : nullptr; C.obs = obs + (size_t)e * d.n_obs; C.rew = rew + (size_t)e * d.n_rew;
   C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;

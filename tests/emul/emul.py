@@ -26,7 +26,9 @@ def lib():
         fp, ip, dp, vp, u8 = (ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double),
                               ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8))
         L.dge_create.restype = vp
-        L.dge_create.argtypes = [ip, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.dge_create.argtypes = [ip, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.dge_cold_floats.restype = ctypes.c_int
+        L.dge_cold_floats.argtypes = [vp]
         L.dge_destroy.argtypes = [vp]
         L.dge_state.restype = fp
         L.dge_state.argtypes = [vp]
@@ -48,19 +50,20 @@ def _fp(a):
 
 
 class EmulWorld:
-    def __init__(self, scene, n_envs=1, team=1, seed=1234, env_off=0):
+    def __init__(self, scene, n_envs=1, team=1, seed=1234, env_off=0, ws_mode=2):
         L = lib()
         self.scene, self.h, self.n = scene, scene.hdr, n_envs
         ib = np.ascontiguousarray(scene.ibuf, np.int32)
         fb = np.ascontiguousarray(scene.fbuf, np.float64)
         self._w = L.dge_create(ib.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), ib.size, fb.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
-                               fb.size, n_envs, team)
+                               fb.size, n_envs, team, ws_mode)
         if not self._w:
             raise RuntimeError('emulation rejected the scene')
         S, P = self.h['S'], self.h['P']
         self.state = np.ctypeslib.as_array(L.dge_state(self._w), shape=(n_envs * S + 1, ))[:n_envs * S].reshape(n_envs, S)
         self.param = np.ctypeslib.as_array(L.dge_param(self._w), shape=(n_envs * P + 1, ))[:n_envs * P].reshape(n_envs, P)
         self.ws_floats = L.dge_ws_floats(self._w)
+        self.cold_floats = L.dge_cold_floats(self._w)
         L.dge_set_seed(self._w, seed, env_off)
 
     def __del__(self):

@@ -116,3 +116,20 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib.dg_last_error.restype = ctypes.c_char_p
     assert lib.dg_world_create(None, 0, None, 0, 1, 0, 0, None) == -1
     assert b'bad argument' in lib.dg_last_error(None)
+
+
+@pytest.mark.parametrize("ws_mode", [2, 3])
+def test_workspace_placement_does_not_change_results(ws_mode):
+    """Hot (shared memory) / cold (global) placement of the workspace regions is pure layout: bit-identical results."""
+    for name, scale in (('from_the_readme', 0.01), ('r2d2_maze', 10.0)):
+        sc = scene_of(name)
+        rng = np.random.default_rng(4)
+        acts = [action_batch(sc, rng, 2, scale) for _ in range(3)]
+        ref = EmulWorld(sc, 2, 4, ws_mode=2)
+        cur = EmulWorld(sc, 2, 4, ws_mode=ws_mode)
+        ref.reset()
+        cur.reset()
+        for a in acts:
+            o1 = ref.step(a)
+            o2 = cur.step(a)
+        assert np.array_equal(ref.state, cur.state) and np.array_equal(o1[0], o2[0])

@@ -47,9 +47,13 @@ for r in rows[2:]:
 ts, ti = sum(samp.values()), sum(inst.values())
 print('total samples %d, warp instructions %d, thread instr %d' % (ts, ti, sum(thr.values())))
 src_cache = {}
+SRC_DIRS = [os.environ['NCU_SRC']] if os.environ.get('NCU_SRC') else []
+SRC_DIRS += [os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', d) for d in ('diy_gym_b200/csrc', 'include')]
+
+
 def src(f, n):
-    for d in ('diy_gym_b200/csrc', 'include'):
-        p = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', d, f)
+    for d in SRC_DIRS:
+        p = os.path.join(d, f)
         if os.path.isfile(p):
             if p not in src_cache:
                 src_cache[p] = open(p).read().splitlines()
