@@ -349,6 +349,8 @@ class SceneBuilder:
         # points at once, fixed-base arms only touch occasionally - their scenes keep the solver workspace small
         if self.max_contacts <= 0:
             self.max_contacts = 16 if any(b.kind == 2 for b in B) else 8
+        if self.max_contacts > 21:
+            raise ValueError('max_contacts is limited to 21 (the solver tracks at most 63 contact rows per environment)')
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
                    max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn)

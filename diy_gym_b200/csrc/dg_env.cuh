@@ -56,9 +56,9 @@ template <class P> DG_HD const P* shc(const P* p) { return p; }
 #define WSP(C, off) ((off) >= 0 ? (C).ws + (off) : (C).wg + ~(off))
 #define WSIP(C, off) ((int*)WSP(C, off))
 #define KIN(s) (WSG(C, SC.W_KIN) + 12 * (s))
-#define LNK(gl) (WSG(C, SC.W_LINK) + 19 * (gl))
-#define ABA(s) (WSG(C, SC.X_ABA) + 45 * (s))   // pA6 IA27 acc6 w3 v3
-#define LNX(gl) (WSG(C, SC.X_LNK) + 7 * (gl))
+#define LNK(gl) (WSG(C, SC.W_LINK) + LK_W * (gl))       // E9 r3 U6 D1 pad
+#define ABA(s) (WSG(C, SC.X_ABA) + AB_W * (s))        // pA6 w3 v3 | A9 B9 C9 pad | acc6 pad2
+#define LNX(gl) (WSG(C, SC.X_LNK) + LX_W * (gl))       // c6 u1 pad
 #define DOF(k, d) (as_shared(C.ws)[SC.W_DOF + (k) * SC.nd + (d)])
 #define BST(di) (WSH(C, SC.W_BST) + 13 * (di))
 #define ST(name) (as_global(C.st) + DG_SO(C.sc, name))
@@ -108,29 +108,99 @@ DG_FN void joint_xform(const Env& C, int gl, float q, float* E, float* r) {
 }
 DG_HD int parent_slot(const int* li, int l0, int s0) { return li[1] < 0 ? s0 : s0 + 1 + (li[1] - l0); }
 
-// world pose and body-frame spatial velocity of every frame of dynamic body b
+// ---- register-block loads / stores (128-bit when the address is 16-byte aligned, which every region base and
+// every per-slot stride below guarantees) -------------------------------------------------------------------------
+struct F4 { float x, y, z, w; };
+DG_HD F4 ld4(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float4 v = *reinterpret_cast<const float4*>(p); F4 o = {v.x, v.y, v.z, v.w}; return o;
+#else
+  F4 o = {p[0], p[1], p[2], p[3]}; return o;
+#endif
+}
+DG_HD void st4(float* p, float x, float y, float z, float w) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float4*>(p) = make_float4(x, y, z, w);
+#else
+  p[0] = x; p[1] = y; p[2] = z; p[3] = w;
+#endif
+}
+template <int N> DG_HD void ldn(const float* p, float* o) {   // N multiple of 4
+#pragma unroll
+  for (int c = 0; c < N / 4; c++) { F4 v = ld4(p + 4 * c); o[4 * c] = v.x; o[4 * c + 1] = v.y; o[4 * c + 2] = v.z; o[4 * c + 3] = v.w; }
+}
+template <int N> DG_HD void stn(float* p, const float* v) {
+#pragma unroll
+  for (int c = 0; c < N / 4; c++) st4(p + 4 * c, v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+}
+
+// world pose and body-frame spatial velocity of every frame of dynamic body b; with BIAS also the first ABA pass
+// (bias forces, rigid-body inertias, velocity-product accelerations), fused so that nothing is re-read
+template <bool BIAS>
 DG_FN void fk_vel_body(const Env& C, int b) {
   const DevScene& sc = SC;
   const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
-  int l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT];
+  const int kind = bi[0], l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT];
   const float* bs = BST(bp[BP_DI]);
-  float* K0 = KIN(s0); float* V0 = ABA(s0) + 39;
-  q_to_mat(K0, bs + 3); v_cpy(K0 + 9, bs);
-  mT_vec(V0, K0, bs + 10); mT_vec(V0 + 3, K0, bs + 7);
-  for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lx = shc(C.link_x) + 16 * gl;
-    float* L = LNK(gl); float* K = KIN(s0 + 1 + k); const int psl = parent_slot(li, l0, s0); const float* Kp = KIN(psl); const float* Vp = ABA(psl) + 39;
-    int dof = li[3];
-    float E[9], r[3], t[3], t2[3];
-    joint_xform(C, gl, dof >= 0 ? DOF(D_Q, dof) : 0.f, E, r);
-    m_cpy(L, E); v_cpy(L + 9, r);
-    float Rw[9]; m_mulT(Rw, Kp, E); m_cpy(K, Rw);
-    m_vec(t, Kp, r); v_add(K + 9, Kp + 9, t);
-    float w[3], v[3];
-    m_vec(w, E, Vp);
-    v_cross(t, Vp, r); v_add(t2, Vp + 3, t); m_vec(v, E, t2);
-    if (dof >= 0) { float qd = DOF(D_QD, dof); v_madd(w, lx + 9, qd); v_madd(v, lx + 12, qd); }
-    float* V = ABA(s0 + 1 + k) + 39; v_cpy(V, w); v_cpy(V + 3, v);
+  const float *mass = PR(P_MASS), *inertia = PR(P_INERTIA);
+  const float kl = PR(P_LINDAMP)[b], ka = PR(P_ANGDAMP)[b];
+  float Kp[12], Vp[6];      // pose (R 9, p 3) and velocity (w 3, v 3) of the previously visited frame
+  q_to_mat(Kp, bs + 3); v_cpy(Kp + 9, bs);
+  mT_vec(Vp, Kp, bs + 10); mT_vec(Vp + 3, Kp, bs + 7);
+  int prev = s0;
+  for (int k = -1; k < nlb; k++) {
+    const int s = s0 + 1 + k, f = k < 0 ? b : sc.nb + l0 + k;
+    float K[12], V[6], cacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (k < 0) {
+      for (int i = 0; i < 12; i++) K[i] = Kp[i];
+      for (int i = 0; i < 6; i++) V[i] = Vp[i];
+    } else {
+      const int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lx = shc(C.link_x) + 16 * gl;
+      const int ps = parent_slot(li, l0, s0), dof = li[3];
+      if (ps != prev) { ldn<12>(KIN(ps), Kp); const float* pv = ABA(ps) + AB_WV; for (int i = 0; i < 6; i++) Vp[i] = pv[i]; }
+      float E[9], r[3], t[3], t2[3];
+      joint_xform(C, gl, dof >= 0 ? DOF(D_Q, dof) : 0.f, E, r);
+      float* L = LNK(gl);
+      st4(L, E[0], E[1], E[2], E[3]); st4(L + 4, E[4], E[5], E[6], E[7]); st4(L + 8, E[8], r[0], r[1], r[2]);
+      m_mulT(K, Kp, E);
+      m_vec(t, Kp, r); v_add(K + 9, Kp + 9, t);
+      m_vec(V, E, Vp);
+      v_cross(t, Vp, r); v_add(t2, Vp + 3, t); m_vec(V + 3, E, t2);
+      if (dof >= 0) {
+        const float qd = DOF(D_QD, dof);
+        if (BIAS) { float sa[3], sl[3]; v_scale(sa, lx + 9, qd); v_scale(sl, lx + 12, qd); v_cross(cacc, V, sa); v_cross(cacc + 3, V, sl); v_cross(t2, V + 3, sa); v_add(cacc + 3, cacc + 3, t2); }
+        v_madd(V, lx + 9, qd); v_madd(V + 3, lx + 12, qd);
+      }
+      if (BIAS) stn<8>(LNX(gl), cacc);
+    }
+    stn<12>(KIN(s), K);
+    float* X = ABA(s);
+    if (!BIAS) {
+      for (int i = 0; i < 6; i++) X[AB_WV + i] = V[i];
+    } else if (k < 0 && kind != 2) {
+      float z[40]; for (int i = 0; i < 40; i++) z[i] = 0.f;
+      for (int i = 0; i < 6; i++) z[AB_WV + i] = V[i];
+      stn<40>(X, z);
+    } else {
+      const float* ef = ST(S_EXTF) + 3 * f; const float* et = ST(S_EXTT) + 3 * f;
+      const float m = mass[f]; const float* I = inertia + 3 * f; const float *w = V, *v = V + 3;
+      float Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]}, t[3], fw[3], pa[3], pl[3];
+      v_cross(pa, w, Iw);
+      v_cross(t, w, v); v_scale(pl, t, m);
+      fw[0] = sc.g[0] * m + ef[0]; fw[1] = sc.g[1] * m + ef[1]; fw[2] = sc.g[2] * m + ef[2];
+      mT_vec(t, K, fw); v_sub(pl, pl, t);
+      mT_vec(t, K, et); v_sub(pa, pa, t);
+      const float wn = v_len(w), vn = v_len(v);
+      v_madd(pa, Iw, ka + ka * wn);
+      float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, kl + kl * vn);
+      float z[40]; for (int i = 0; i < 40; i++) z[i] = 0.f;
+      for (int i = 0; i < 3; i++) { z[AB_PA + i] = pa[i]; z[AB_PA + 3 + i] = pl[i]; z[AB_WV + i] = w[i]; z[AB_WV + 3 + i] = v[i]; }
+      z[AB_A] = I[0]; z[AB_A + 4] = I[1]; z[AB_A + 8] = I[2]; z[AB_C] = m; z[AB_C + 4] = m; z[AB_C + 8] = m;
+      stn<40>(X, z);
+    }
+    for (int i = 0; i < 12; i++) Kp[i] = K[i];
+    for (int i = 0; i < 6; i++) Vp[i] = V[i];
+    prev = s;
   }
 }
 
@@ -156,116 +226,100 @@ DG_FN int invert_small(float* M, int n, float* inv) {
   return 0;
 }
 
-// forward dynamics of dynamic body b, then the velocity half of the semi-implicit Euler step
+// forward dynamics of dynamic body b (passes 2 and 3 of the ABA; pass 1 ran inside fk_vel_body<true>), then the
+// velocity half of the semi-implicit Euler step.  Every per-link record is pulled into registers with 128-bit loads,
+// worked on there, and written back once.
 DG_FN void aba_body(const Env& C, int b, float h) {
   const DevScene& sc = SC;
   const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
-  int kind = bi[0], l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT], di = bp[BP_DI];
-  const float *mass = PR(P_MASS), *inertia = PR(P_INERTIA);
-  float kl = PR(P_LINDAMP)[b], ka = PR(P_ANGDAMP)[b];
-  // pass 1: bias forces and rigid-body inertias
-  for (int k = -1; k < nlb; k++) {
-    int s = s0 + 1 + k, f = k < 0 ? b : sc.nb + l0 + k;
-    float* X = ABA(s);
-    if (k < 0 && kind != 2) { for (int i = 0; i < 33; i++) X[i] = 0.f; continue; }
-    const float* K = KIN(s); const float *w = X + 39, *v = X + 42; const float* ef = ST(S_EXTF) + 3 * f; const float* et = ST(S_EXTT) + 3 * f;
-    float m = mass[f]; const float* I = inertia + 3 * f;
-    float Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]}, t[3], fw[3], pa[3], pl[3];
-    v_cross(pa, w, Iw);
-    v_cross(t, w, v); v_scale(pl, t, m);
-    fw[0] = sc.g[0] * m + ef[0]; fw[1] = sc.g[1] * m + ef[1]; fw[2] = sc.g[2] * m + ef[2];
-    mT_vec(t, K, fw); v_sub(pl, pl, t);
-    mT_vec(t, K, et); v_sub(pa, pa, t);
-    float wn = v_len(w), vn = v_len(v);
-    v_madd(pa, Iw, ka + ka * wn);
-    float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, kl + kl * vn);
-    v_cpy(X, pa); v_cpy(X + 3, pl);
-    for (int i = 6; i < 33; i++) X[i] = 0.f;
-    X[6] = I[0]; X[10] = I[1]; X[14] = I[2]; X[24] = m; X[28] = m; X[32] = m;
-    if (k >= 0) {
-      int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; float* c = LNX(gl);
-      if (li[3] >= 0) {
-        const float* lx = shc(C.link_x) + 16 * gl;
-        float qd = DOF(D_QD, li[3]), sa[3], sl[3], t2[3];
-        v_scale(sa, lx + 9, qd); v_scale(sl, lx + 12, qd);
-        v_cross(c, w, sa); v_cross(c + 3, w, sl); v_cross(t2, v, sa); v_add(c + 3, c + 3, t2);
-      } else for (int i = 0; i < 6; i++) c[i] = 0.f;
-    }
-  }
+  const int kind = bi[0], l0 = bi[1], nlb = bi[2], s0 = bp[BP_SLOT], di = bp[BP_DI];
   // pass 2: articulated inertias, leaves to root
   for (int k = nlb - 1; k >= 0; k--) {
-    int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
-    int ps = parent_slot(li, l0, s0);
-    float* X = ABA(s); float* L = LNK(gl); float* cx = LNX(gl);
-    float Aa[9], Ba[9], Ca[9], pa[6], n[3], fo[3];
-    m_cpy(Aa, X + 6); m_cpy(Ba, X + 15); m_cpy(Ca, X + 24);
+    const int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+    const int ps = parent_slot(li, l0, s0);
+    float Xr[40], Lr[12], cx[8];
+    ldn<40>(ABA(s), Xr); ldn<12>(LNK(gl), Lr); ldn<8>(LNX(gl), cx);
+    float* Aa = Xr + AB_A; float* Ba = Xr + AB_B; float* Ca = Xr + AB_C; const float* pA = Xr + AB_PA;
+    float pa[6], n[3], fo[3];
     if (li[3] >= 0) {
       const float* lx = shc(C.link_x) + 16 * gl; const float *sa = lx + 9, *sl = lx + 12;
       float U[6];
       ia_mul(Aa, Ba, Ca, sa, sl, U, U + 3);
-      float D = v_dot(sa, U) + v_dot(sl, U + 3);
-      float tau = DOF(D_TAU, li[3]);
-      float uu = tau - (v_dot(sa, X) + v_dot(sl, X + 3));
-      for (int i = 0; i < 6; i++) L[12 + i] = U[i];
-      L[18] = D; cx[6] = uu;
-      float Dinv = 1.0f / D;
-      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-        Aa[3 * i + j] -= U[i] * U[j] * Dinv; Ba[3 * i + j] -= U[i] * U[3 + j] * Dinv; Ca[3 * i + j] -= U[3 + i] * U[3 + j] * Dinv;
-      }
+      const float D = v_dot(sa, U) + v_dot(sl, U + 3);
+      const float uu = DOF(D_TAU, li[3]) - (v_dot(sa, pA) + v_dot(sl, pA + 3));
+      float* L = LNK(gl);
+      st4(L + 12, U[0], U[1], U[2], U[3]); st4(L + 16, U[4], U[5], D, 0.f);
+      LNX(gl)[6] = uu;
+      const float Dinv = 1.0f / D;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) { Aa[3 * i + j] -= U[i] * U[j] * Dinv; Ba[3 * i + j] -= U[i] * U[3 + j] * Dinv; Ca[3 * i + j] -= U[3 + i] * U[3 + j] * Dinv; }
       ia_mul(Aa, Ba, Ca, cx, cx + 3, n, fo);
-      for (int i = 0; i < 3; i++) { pa[i] = X[i] + n[i] + U[i] * uu * Dinv; pa[3 + i] = X[3 + i] + fo[i] + U[3 + i] * uu * Dinv; }
+      for (int i = 0; i < 3; i++) { pa[i] = pA[i] + n[i] + U[i] * uu * Dinv; pa[3 + i] = pA[3 + i] + fo[i] + U[3 + i] * uu * Dinv; }
     } else {
       ia_mul(Aa, Ba, Ca, cx, cx + 3, n, fo);
-      for (int i = 0; i < 3; i++) { pa[i] = X[i] + n[i]; pa[3 + i] = X[3 + i] + fo[i]; }
+      for (int i = 0; i < 3; i++) { pa[i] = pA[i] + n[i]; pa[3 + i] = pA[3 + i] + fo[i]; }
     }
     // transform to the parent: rotate the blocks by E^T (.) E, then shift by r
-    const float* E = L; const float* r = L + 9;
+    const float* E = Lr; const float* r = Lr + 9;
     float T1[9], Ar[9], Br[9], Cr[9];
     mT_mul(T1, E, Aa); m_mul(Ar, T1, E); mT_mul(T1, E, Ba); m_mul(Br, T1, E); mT_mul(T1, E, Ca); m_mul(Cr, T1, E);
-    float Kx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
+    const float Kx[9] = {0, -r[2], r[1], r[2], 0, -r[0], -r[1], r[0], 0};
     float KC[9], BK[9], KBt[9], KCK[9];
     m_mul(KC, Kx, Cr); m_mul(BK, Br, Kx); m_mulT(KBt, Kx, Br); m_mul(KCK, KC, Kx);
-    float* P = ABA(ps);
-    for (int i = 0; i < 9; i++) { P[6 + i] += Ar[i] - BK[i] + KBt[i] - KCK[i]; P[15 + i] += Br[i] + KC[i]; P[24 + i] += Cr[i]; }
     float fp[3], np_[3], t[3];
     mT_vec(fp, E, pa + 3); mT_vec(np_, E, pa); v_cross(t, r, fp); v_add(np_, np_, t);
-    v_add(P, P, np_); v_add(P + 3, P + 3, fp);
+    float* P = ABA(ps);
+    float Pr[40];
+    ldn<40>(P, Pr);
+    for (int i = 0; i < 9; i++) { Pr[AB_A + i] += Ar[i] - BK[i] + KBt[i] - KCK[i]; Pr[AB_B + i] += Br[i] + KC[i]; Pr[AB_C + i] += Cr[i]; }
+    for (int i = 0; i < 3; i++) { Pr[AB_PA + i] += np_[i]; Pr[AB_PA + 3 + i] += fp[i]; }
+    stn<40>(P, Pr);
   }
   // base acceleration
-  float* X0 = ABA(s0); float* a0 = X0 + 33;
+  float* X0 = ABA(s0); float* a0 = X0 + AB_ACC;
   if (kind == 2) {
     float* M = WSG(C, sc.X_I0T) + bp[BP_I0OFF]; float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
-    const float *A = X0 + 6, *B = X0 + 15, *Cm = X0 + 24;
+    const float *A = X0 + AB_A, *B = X0 + AB_B, *Cm = X0 + AB_C;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { M[6 * i + j] = A[3 * i + j]; M[6 * i + 3 + j] = B[3 * i + j]; M[6 * (3 + i) + j] = B[3 * j + i]; M[6 * (3 + i) + 3 + j] = Cm[3 * i + j]; }
     invert_small(M, 6, Iv);
-    for (int i = 0; i < 6; i++) { float s = 0.f; for (int j = 0; j < 6; j++) s -= Iv[6 * i + j] * X0[j]; a0[i] = s; }
+    for (int i = 0; i < 6; i++) { float sum = 0.f; for (int j = 0; j < 6; j++) sum -= Iv[6 * i + j] * X0[AB_PA + j]; a0[i] = sum; }
   } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
   // pass 3: accelerations, root to leaves
+  float ap[8]; int prev = s0;
+  ldn<8>(a0, ap);
   for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
-    const float* L = LNK(gl); const float* cx = LNX(gl); const float* ap = ABA(parent_slot(li, l0, s0)) + 33;
-    float* a = ABA(s) + 33; float t[3], t2[3], aa[3], al[3];
-    m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
-    v_add(aa, aa, cx); v_add(al, al, cx + 3);
+    const int gl = l0 + k, s = s0 + 1 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+    const int ps = parent_slot(li, l0, s0);
+    if (ps != prev) ldn<8>(ABA(ps) + AB_ACC, ap);
+    float Lr[20], cx[8];
+    ldn<20>(LNK(gl), Lr); ldn<8>(LNX(gl), cx);
+    float t[3], t2[3], acc[8];
+    m_vec(acc, Lr, ap); v_cross(t, ap, Lr + 9); v_add(t2, ap + 3, t); m_vec(acc + 3, Lr, t2);
+    v_add(acc, acc, cx); v_add(acc + 3, acc + 3, cx + 3);
     if (li[3] >= 0) {
       const float* lx = shc(C.link_x) + 16 * gl;
-      float qdd = (cx[6] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
+      const float qdd = (cx[6] - (v_dot(Lr + 12, acc) + v_dot(Lr + 15, acc + 3))) / Lr[18];
       DOF(D_QD, li[3]) += h * qdd;            // velocity half of the semi-implicit Euler step
-      v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
+      v_madd(acc, lx + 9, qdd); v_madd(acc + 3, lx + 12, qdd);
     }
-    v_cpy(a, aa); v_cpy(a + 3, al);
+    acc[6] = 0.f; acc[7] = 0.f;
+    stn<8>(ABA(s) + AB_ACC, acc);
+    for (int i = 0; i < 8; i++) ap[i] = acc[i];
+    prev = s;
   }
-  // velocity update
+  // velocity update of a floating base
   if (kind == 2) {
     const float* K0 = KIN(s0); float* bs = BST(di); float t[3], lin[3], aw[3];
-    v_cross(t, X0 + 39, X0 + 42); v_add(lin, a0 + 3, t);
+    v_cross(t, X0 + AB_WV, X0 + AB_WV + 3); v_add(lin, a0 + 3, t);
     m_vec(aw, K0, a0); v_madd(bs + 10, aw, h);
     m_vec(aw, K0, lin); v_madd(bs + 7, aw, h);
   }
 }
 
 DG_FN void phase_dynamics(const Env& C, int ln, int nt, float h) {
-  for (int di = ln; di < SC.ndyn; di += nt) { int b = gc(SC.dyn_body)[di]; fk_vel_body(C, b); aba_body(C, b, h); }
+  for (int di = ln; di < SC.ndyn; di += nt) { int b = gc(SC.dyn_body)[di]; fk_vel_body<true>(C, b); aba_body(C, b, h); }
 }
 
 // One column of M^-1 of body b: response of the generalized velocity to a unit generalized impulse at coordinate col.
@@ -273,8 +327,8 @@ DG_FN void phase_dynamics(const Env& C, int ln, int nt, float h) {
 DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
   const DevScene& sc = SC;
   const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
-  int kind = bi[0], l0 = bi[1], nlb = bi[2], d0 = bi[3], s0 = bp[BP_SLOT], g = bp[BP_GDIM], gs = bp[BP_GS];
-  int jo = kind == 2 ? 6 : 0;
+  const int kind = bi[0], l0 = bi[1], nlb = bi[2], d0 = bi[3], s0 = bp[BP_SLOT], g = bp[BP_GDIM], gs = bp[BP_GS];
+  const int jo = kind == 2 ? 6 : 0;
   float* out = WSH(C, sc.W_MINV) + bp[BP_MINVOFF] + col * gs;
   for (int i = g; i < gs; i++) out[i] = 0.f;
   float* uu = scr; float* ast = scr + sc.max_nlb;   // a-stack indexed by depth+1 (0 = base)
@@ -284,12 +338,13 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
     int k0 = -1;
     for (int k = 0; k < nlb; k++) if (shc(C.link_i)[DG_LINK_I_W * (l0 + k) + 3] == d0 + col - jo) { k0 = k; break; }
     for (int k = k0; k >= 0;) {
-      int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* L = LNK(gl);
+      const int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+      float L[20]; ldn<20>(LNK(gl), L);
       float pa[6] = {p[0], p[1], p[2], p[3], p[4], p[5]};
       if (li[3] >= 0) {
         const float* lx = shc(C.link_x) + 16 * gl;
-        float u1 = (k == k0 ? 1.f : 0.f) - (v_dot(lx + 9, pa) + v_dot(lx + 12, pa + 3));
-        uu[k] = u1; float s = u1 / L[18];
+        const float u1 = (k == k0 ? 1.f : 0.f) - (v_dot(lx + 9, pa) + v_dot(lx + 12, pa + 3));
+        uu[k] = u1; const float s = u1 / L[18];
         for (int i = 0; i < 6; i++) pa[i] += L[12 + i] * s;
       }
       float fp[3], np_[3], t[3];
@@ -298,28 +353,33 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
       k = li[1] < 0 ? -1 : li[1] - l0;
     }
   }
-  float* a0 = ast;
+  float a0[6];
   if (kind == 2) {
-    const float* K0 = KIN(s0); const float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
+    float K0[12]; ldn<12>(KIN(s0), K0); const float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
     float gen[6] = {0, 0, 0, 0, 0, 0}, rhs[6], t[3];
-    if (col < 6) gen[col] = 1.f;
+    for (int i = 0; i < 6; i++) gen[i] = (i == col) ? 1.f : 0.f;
     mT_vec(t, K0, gen); v_sub(rhs, t, p); mT_vec(t, K0, gen + 3); v_sub(rhs + 3, t, p + 3);
     for (int i = 0; i < 6; i++) { float s = 0.f; for (int j = 0; j < 6; j++) s += Iv[6 * i + j] * rhs[j]; a0[i] = s; }
     m_vec(out, K0, a0); m_vec(out + 3, K0, a0 + 3);
   } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
+  for (int i = 0; i < 6; i++) ast[i] = a0[i];
+  float ap[6] = {a0[0], a0[1], a0[2], a0[3], a0[4], a0[5]}; int prev_dep = -1;   // registers hold a of depth prev_dep
   for (int k = 0; k < nlb; k++) {
-    int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* L = LNK(gl);
-    int dep = gc(sc.link_depth)[gl];
-    const float* ap = ast + 6 * dep; float* ak = ast + 6 * (dep + 1);
+    const int gl = l0 + k; const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+    const int dep = gc(sc.link_depth)[gl];
+    if (dep - 1 != prev_dep) { const float* src = ast + 6 * dep; for (int i = 0; i < 6; i++) ap[i] = src[i]; }
+    float L[20]; ldn<20>(LNK(gl), L);
     float t[3], t2[3], aa[3], al[3];
     m_vec(aa, L, ap); v_cross(t, ap, L + 9); v_add(t2, ap + 3, t); m_vec(al, L, t2);
     if (li[3] >= 0) {
       const float* lx = shc(C.link_x) + 16 * gl;
-      float qdd = (uu[k] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
+      const float qdd = (uu[k] - (v_dot(L + 12, aa) + v_dot(L + 15, al))) / L[18];
       out[jo + li[3] - d0] = qdd;
       v_madd(aa, lx + 9, qdd); v_madd(al, lx + 12, qdd);
     }
+    float* ak = ast + 6 * (dep + 1);
     v_cpy(ak, aa); v_cpy(ak + 3, al);
+    v_cpy(ap, aa); v_cpy(ap + 3, al); prev_dep = dep;
   }
 }
 DG_FN void phase_minv(const Env& C, int ln, int nt) {
@@ -501,6 +561,13 @@ DG_HD void surv_set(int* word, int bit) {
   atomicOr(word, 1 << bit);
 #else
   *word |= 1 << bit;
+#endif
+}
+DG_HD int ffs64(unsigned long long x) {
+#if defined(__CUDA_ARCH__)
+  return __ffsll((long long)x);
+#else
+  return __builtin_ffsll((long long)x);
 #endif
 }
 DG_HD int popc32(unsigned x) {
@@ -689,7 +756,7 @@ DG_FN void phase_contact_rows(const Env& C, int ln, int nt, float h) {
     { int used = ga + (dib >= 0 ? gc(sc.body_plan)[BP_W * bb + BP_GDIM] : 0); for (int i = used; i < sc.GP; i++) { J[i] = 0.f; M[i] = 0.f; } }
     if (dia >= 0 && dib >= 0) WSI(C)[sc.W_HDR + WH_COUPLED] = 1;   // a row couples two dynamic bodies: lock-step sweeps needed
     float dinv = den > 1e-30f ? 1.0f / den : 0.f;
-    row[CR_DINV] = dinv; row[CR_APPLIED] = 0.f; row[CR_MU] = c[CT_MU];
+    row[CR_DINV] = dinv; row[CR_APPLIED] = 0.f; row[CR_MU] = c[CT_MU]; WSH(C, sc.W_CAPP)[r] = 0.f;
     row[CR_DA] = int_as_float(dia); row[CR_DB] = int_as_float(dib);
     if (dirk < 0) {
       float pen = c[CT_DIST] + sc.slop, pos_err = 0.f, vel_err = -rel;
@@ -794,14 +861,6 @@ DG_FN void pgs_unit_any(const Env& C, int b, int di, int it0, int it1) {
 }
 // All solver sweeps of ONE body whose contact rows touch no other dynamic body: unit rows then its contact rows,
 // every iteration, with the generalized velocity change dv held in registers (G >= padded coordinate count).
-struct F4 { float x, y, z, w; };
-DG_HD F4 ld4(const float* p) {
-#if defined(__CUDA_ARCH__)
-  float4 v = *reinterpret_cast<const float4*>(p); F4 o = {v.x, v.y, v.z, v.w}; return o;
-#else
-  F4 o = {p[0], p[1], p[2], p[3]}; return o;
-#endif
-}
 template <int G>
 DG_FN void pgs_body_full(const Env& C, int b, int di) {
   const DevScene& sc = SC;
@@ -809,6 +868,12 @@ DG_FN void pgs_body_full(const Env& C, int b, int di) {
   const int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
   const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF]; float* dvs = WSH(C, sc.W_DV) + bp[BP_GVOFF];
   float* rows = WSH(C, sc.X_UROW) + UR_W * bp[BP_UROW];
+  float* capp = WSH(C, sc.W_CAPP);
+  unsigned long long mine = 0ull;   // the contact rows that act on this body (at most 63 rows: max_contacts <= 21)
+  for (int rr = 0; rr < ncr && rr < 63; rr++) {
+    const float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr;
+    if (float_as_int(row[CR_DA]) == di || float_as_int(row[CR_DB]) == di) mine |= 1ull << rr;
+  }
   float dv[G];
 #pragma unroll
   for (int i = 0; i < G; i++) dv[i] = 0.f;
@@ -832,29 +897,35 @@ DG_FN void pgs_body_full(const Env& C, int b, int di) {
         dv[4 * c4 + 2] = fmaf(m.z, sd, dv[4 * c4 + 2]); dv[4 * c4 + 3] = fmaf(m.w, sd, dv[4 * c4 + 3]);
       }
     }
-    for (int rr = 0; rr < ncr; rr++) {
-      float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr;
-      if (float_as_int(row[CR_DA]) != di && float_as_int(row[CR_DB]) != di) continue;
+    for (unsigned long long m = mine; m != 0ull; m &= m - 1ull) {
+      const int rr = ffs64(m) - 1;
+      const float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr;
       const float* J = row + CR_HDR; const float* M = J + sc.GP;
+      // every load of the row is issued before the first use (one memory round trip per row instead of three)
+      const F4 h = ld4(row), h2 = ld4(row + 4), h3 = ld4(row + 8);   // rhs dinv lo hi | - mu da db | parent
+      F4 jv[G / 4], mv[G / 4];
+#pragma unroll
+      for (int c4 = 0; c4 < G / 4; c4++) {
+        if (4 * c4 < gs) { jv[c4] = ld4(J + 4 * c4); mv[c4] = ld4(M + 4 * c4); }
+        else { F4 z = {0.f, 0.f, 0.f, 0.f}; jv[c4] = z; mv[c4] = z; }
+      }
       float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-      for (int c4 = 0; c4 < G / 4; c4++) if (4 * c4 < gs) {
-        F4 jv = ld4(J + 4 * c4);
-        d0 = fmaf(jv.x, dv[4 * c4], d0); d1 = fmaf(jv.y, dv[4 * c4 + 1], d1); d2 = fmaf(jv.z, dv[4 * c4 + 2], d2); d3 = fmaf(jv.w, dv[4 * c4 + 3], d3);
+      for (int c4 = 0; c4 < G / 4; c4++) {
+        d0 = fmaf(jv[c4].x, dv[4 * c4], d0); d1 = fmaf(jv[c4].y, dv[4 * c4 + 1], d1); d2 = fmaf(jv[c4].z, dv[4 * c4 + 2], d2); d3 = fmaf(jv[c4].w, dv[4 * c4 + 3], d3);
       }
-      F4 h = ld4(row);   // rhs, dinv, lo, hi
       float d = h.x - ((d0 + d1) + (d2 + d3)) * h.y;
       float lo = h.z, hi = h.w;
-      int par = float_as_int(row[CR_PARENT]);
-      if (par >= 0) { hi = row[CR_MU] * (WSP(C, sc.X_CROW) + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
-      float ap = row[CR_APPLIED], sum = ap + d;
-      if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
-      row[CR_APPLIED] = sum;
+      const int par = float_as_int(h3.x);
+      if (par >= 0) { hi = h2.y * capp[par]; lo = -hi; }
+      const float ap = capp[rr]; float sum = ap + d;
+      const bool below = sum < lo, above = sum > hi;
+      d = below ? lo - ap : (above ? hi - ap : d);
+      capp[rr] = below ? lo : (above ? hi : sum);
 #pragma unroll
-      for (int c4 = 0; c4 < G / 4; c4++) if (4 * c4 < gs) {
-        F4 m = ld4(M + 4 * c4);
-        dv[4 * c4] = fmaf(m.x, d, dv[4 * c4]); dv[4 * c4 + 1] = fmaf(m.y, d, dv[4 * c4 + 1]);
-        dv[4 * c4 + 2] = fmaf(m.z, d, dv[4 * c4 + 2]); dv[4 * c4 + 3] = fmaf(m.w, d, dv[4 * c4 + 3]);
+      for (int c4 = 0; c4 < G / 4; c4++) {
+        dv[4 * c4] = fmaf(mv[c4].x, d, dv[4 * c4]); dv[4 * c4 + 1] = fmaf(mv[c4].y, d, dv[4 * c4 + 1]);
+        dv[4 * c4 + 2] = fmaf(mv[c4].z, d, dv[4 * c4 + 2]); dv[4 * c4 + 3] = fmaf(mv[c4].w, d, dv[4 * c4 + 3]);
       }
     }
   }
@@ -879,10 +950,11 @@ DG_FN void pgs_contact_sweep(const Env& C) {
     float d = row[CR_RHS] - dot * row[CR_DINV];
     float lo = row[CR_LO], hi = row[CR_HI];
     int par = float_as_int(row[CR_PARENT]);
-    if (par >= 0) { hi = row[CR_MU] * (WSP(C, sc.X_CROW) + sc.crow_stride * par)[CR_APPLIED]; lo = -hi; }
-    float ap = row[CR_APPLIED], sum = ap + d;
+    float* capp = WSH(C, sc.W_CAPP);
+    if (par >= 0) { hi = row[CR_MU] * capp[par]; lo = -hi; }
+    float ap = capp[r], sum = ap + d;
     if (sum < lo) { d = lo - ap; sum = lo; } else if (sum > hi) { d = hi - ap; sum = hi; }
-    row[CR_APPLIED] = sum;
+    capp[r] = sum;
     for (int i = 0; i < ga; i++) dva[i] = fmaf(M[i], d, dva[i]);
     for (int i = 0; i < gb; i++) dvb[i] = fmaf(M[ga + i], d, dvb[i]);
   }
@@ -923,7 +995,7 @@ DG_FN void phase_integrate(const Env& C, int ln, int nt, float h) {
   }
 }
 DG_FN void phase_final_kin(const Env& C, int ln, int nt) {
-  for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body(C, gc(SC.dyn_body)[di]);
+  for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body<false>(C, gc(SC.dyn_body)[di]);
 }
 // write the dynamic state back, refresh the link pose / velocity cache the sensors read, clear applied wrenches
 DG_FN void phase_store(const Env& C, int ln, int nt, int clear_forces) {
@@ -945,7 +1017,7 @@ DG_FN void phase_store(const Env& C, int ln, int nt, int clear_forces) {
     const float* K = KIN(s); float q[4], t[3];
     v_cpy(ST(S_LPOS) + 3 * gl, K + 9);
     mat_to_q(q, K); for (int i = 0; i < 4; i++) ST(S_LQUAT)[4 * gl + i] = q[i];
-    const float* V = ABA(s) + 39;
+    const float* V = ABA(s) + AB_WV;
     m_vec(t, K, V + 3); v_cpy(ST(S_LVEL) + 3 * gl, t);
     m_vec(t, K, V); v_cpy(ST(S_LOMEGA) + 3 * gl, t);
   }

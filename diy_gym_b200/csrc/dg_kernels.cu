@@ -259,10 +259,17 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   const size_t smem_cap = prop.sharedMemPerBlockOptin;
   w->smem_cap = smem_cap;
   if (team == 0) {
-    // built-in choice: 4 lanes per environment (two lanes carry the per-body phases of a two-arm scene, the rest
-    // help in the per-column / per-pair / per-row phases); DG_TEAM overrides
+    // built-in choice (from the team-size sweeps in profiles/): 4 lanes per environment for small scenes (two lanes
+    // carry the per-body phases of a two-arm scene, the others help in the per-column / per-pair / per-row phases),
+    // 8 lanes when the bodies have more than 12 generalized coordinates in total; DG_TEAM overrides
     const char* env_team = getenv("DG_TEAM");
-    team = env_team ? atoi(env_team) : 4;
+    if (env_team) team = atoi(env_team);
+    else {
+      const int32_t* bsec = ibuf + ibuf[2 + 3 * SEC_BODY_I + 1]; const int nb_ = ibuf[ibuf[2 + 3 * SEC_HDR_I + 1] + HI_nb];
+      int coords = 0;
+      for (int b = 0; b < nb_; b++) if (bsec[DG_BODY_I_W * b] != 0) coords += (bsec[DG_BODY_I_W * b] == 2 ? 6 : 0) + bsec[DG_BODY_I_W * b + 4];
+      team = coords > 12 ? 8 : 4;
+    }
     if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
   }
   const char* env_block = getenv("DG_BLOCK");

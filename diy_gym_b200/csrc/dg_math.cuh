@@ -92,7 +92,14 @@ DG_HD void mat_to_q(float* q, const float* m) {
 // rotation about unit axis a by angle (Rodrigues), row-major
 DG_HD void axis_angle_mat(float* m, const float* a, float ang) {
   float s, c;
+#if defined(__CUDA_ARCH__)
+  // SFU sine / cosine after reduction to [-pi, pi] (absolute error ~4e-7 there, the size of a few fp32 ulps of the
+  // rotation entries); the libm-accurate sincosf costs ~10x the instructions in the FK / IK inner loops
+  ang = fmaf(-6.283185307179586f, rintf(ang * 0.15915494309189535f), ang);
+  __sincosf(ang, &s, &c);
+#else
   sincosf(ang, &s, &c);
+#endif
   float t = 1 - c, x = a[0], y = a[1], z = a[2];
   m[0] = t * x * x + c; m[1] = t * x * y - s * z; m[2] = t * x * z + s * y;
   m[3] = t * x * y + s * z; m[4] = t * y * y + c; m[5] = t * y * z - s * x;

@@ -23,6 +23,8 @@ enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_COUNT = 8 };
 // row record strides
 enum { UR_RHS = 0, UR_DINV, UR_LO, UR_HI, UR_APPLIED, UR_COL, UR_MOTOR, UR_W = 8 };
 enum { CR_RHS = 0, CR_DINV, CR_LO, CR_HI, CR_APPLIED, CR_MU, CR_DA, CR_DB, CR_PARENT, CR_HDR = 12 };
+// per-slot record strides of the cold workspace (multiples of 4 floats, so that records load with 128-bit accesses)
+enum { LK_W = 20, AB_PA = 0, AB_WV = 6, AB_A = 12, AB_B = 21, AB_C = 30, AB_ACC = 40, AB_W = 48, LX_W = 8 };
 enum { CT_FA = 0, CT_FB, CT_PA = 2, CT_PB = 5, CT_N = 8, CT_DIST = 11, CT_MU = 12, CT_W = 13 };
 
 struct DevScene {
@@ -52,7 +54,7 @@ struct DevScene {
   const float* body_reach;// [nb] radius about the base COM that contains every collision shape of the body
   // ---- workspace layout (float offsets) ----
   int w_total, g_total, ws_mode;   // hot (shared) and cold (global) floats per team
-  int W_HDR, W_BST, W_DOF, W_EXT, W_KIN, W_LINK, W_MINV, W_DV, W_I0, W_UCNT, W_X;
+  int W_HDR, W_BST, W_DOF, W_EXT, W_KIN, W_LINK, W_MINV, W_DV, W_I0, W_UCNT, W_CAPP, W_X;
   // region X, articulated-body phase
   int X_ABA, X_LNK, X_I0T;
   // region X, constraint phase
@@ -281,9 +283,10 @@ struct HostScene {
     d.W_DOF = fixed(RC_SMALL, D_COUNT * d.nd);
     d.W_DV = fixed(RC_SMALL, gv);
     d.W_UCNT = fixed(RC_SMALL, d.ndyn);
+    d.W_CAPP = fixed(RC_SMALL, 3 * d.maxc);   // accumulated impulse of every contact / friction row (read by the friction bounds)
     d.W_MINV = fixed(RC_SOLVE, minv);
     d.W_KIN = fixed(RC_KIN, 12 * nslot);
-    d.W_LINK = fixed(RC_KIN, 19 * d.nl);
+    d.W_LINK = fixed(RC_KIN, LK_W * d.nl);
     d.W_I0 = fixed(RC_KIN, i0);
     d.W_EXT = 0; d.W_X = 0;
     // phase regions: offsets are relative to the end of the persistent part of their memory, fixed up below
@@ -296,8 +299,8 @@ struct HostScene {
     int gj = 1;
     for (int b = 0; b < d.nb; b++) gj = std::max(gj, (int)body_i[DG_BODY_I_W * b + 4]);
     d.ik_stride = (9 * (max_depth + 2) + 6 * gj + std::max(gj * gj, 36) + 8 * gj + 32 + 3) & ~3;
-    phase_take(&d.X_ABA, RC_ABA, 0, 45 * nslot);
-    phase_take(&d.X_LNK, RC_ABA, 0, 7 * d.nl);
+    phase_take(&d.X_ABA, RC_ABA, 0, AB_W * nslot);
+    phase_take(&d.X_LNK, RC_ABA, 0, LX_W * d.nl);
     phase_take(&d.X_I0T, RC_ABA, 0, 36 * nfloat);
     phase_take(&d.X_SHW, RC_CONTACT, 1, 12 * nshw);
     phase_take(&d.X_CON, RC_CONTACT, 1, CT_W * d.maxc);
