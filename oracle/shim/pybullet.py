@@ -31,6 +31,11 @@ class error(Exception):
     pass
 
 
+def _vec3(v):
+    """pybullet converts each element with PyFloat_AsDouble, so [0, 0, array([x])] is a valid vector."""
+    return np.array([float(np.asarray(e).reshape(-1)[0]) for e in v], float)
+
+
 class _Sim:
     def __init__(self):
         self.params = dict(timestep=1 / 240., substeps=1, iterations=50, gravity=(0, 0, 0))
@@ -227,7 +232,7 @@ def applyExternalForce(uid, link, forceObj, posObj, flags, **k):
     w, h = _sim.ensure(), _sim.scene.hdr
     f = _sim.scene.bodies[uid].frame(link)
     fs = w.frame_state(f)
-    F, P = np.array(forceObj, float).reshape(3), np.array(posObj, float).reshape(3)
+    F, P = _vec3(forceObj), _vec3(posObj)
     if flags == LINK_FRAME:
         R = _q_to_mat(fs['com_quat'])
         F, rel = R @ F, R @ P
@@ -240,7 +245,7 @@ def applyExternalForce(uid, link, forceObj, posObj, flags, **k):
 def applyExternalTorque(uid, link, torqueObj, flags, **k):
     w, h = _sim.ensure(), _sim.scene.hdr
     f = _sim.scene.bodies[uid].frame(link)
-    T = np.array(torqueObj, float).reshape(3)
+    T = _vec3(torqueObj)
     if flags == LINK_FRAME:
         T = _q_to_mat(w.frame_state(f)['com_quat']) @ T
     w.state[h['S_EXTT'] + 3 * f:h['S_EXTT'] + 3 * f + 3] += T
@@ -281,8 +286,9 @@ def getJointStates(uid, joints, **k):
 
 
 # ---------------------------------------------------------------- solvers ----------------------------------------
-def calculateInverseKinematics(uid, endEffectorLinkIndex, targetPosition, targetOrientation=None, lowerLimits=None, upperLimits=None,
+def calculateInverseKinematics(bodyUniqueId, endEffectorLinkIndex, targetPosition, targetOrientation=None, lowerLimits=None, upperLimits=None,
                                jointRanges=None, restPoses=None, **k):
+    uid = bodyUniqueId
     w = _sim.ensure()
     b = _sim.scene.bodies[uid]
     nd = b.n_dofs
