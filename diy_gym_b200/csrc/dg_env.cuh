@@ -1,10 +1,10 @@
 // dg_env.cuh - the per-environment step, written once for a TEAM of `nt` cooperating lanes.
 //
-// One environment is advanced by a team of nt lanes (nt = 1,2,4,...,32, a sub-warp group).  The code is a
-// sequence of PHASES; inside a phase every lane works on its own items (bodies, M^-1 columns, shape pairs,
-// constraint rows, add-on ops) and never reads what another lane writes in the same phase; between phases the
-// team synchronises (__syncwarp on the team mask).  The test-only CPU emulation (tests/emul) runs the same
-// phases lane after lane, which is exactly the barrier semantics.
+// One environment is advanced by a team of nt lanes (nt = 1,2,4,...,32).  The code is a sequence of PHASES; inside
+// a phase every lane works on its own items (bodies, M^-1 columns, shape pairs, constraint rows, add-on ops) and
+// never reads what another lane writes in the same phase; between phases the lanes synchronise (a block barrier:
+// see "the phase schedule" at the end of this file for how lanes map to threads).  The test-only CPU emulation
+// (tests/emul) runs the same phases lane after lane, which is exactly the barrier semantics.
 //
 // What it computes replaces, for N environments at once, the reference's
 //   DIYGym.step  (/root/reference/diy_gym/diy_gym.py:187-209):  add-on update -> p.stepSimulation() -> observe/reward/terminal
@@ -33,6 +33,7 @@ struct Env {
   const float* link_x;
   uint32_t seed;
   int env_id;
+  bool active;        // false: no environment for this slot in this launch (barriers only)
   unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
 };
 
@@ -1396,22 +1397,24 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
 }
 
 // ------------------------------------------------------------------ the phase schedule -------------------------
-// DG_PHASE(call): on the GPU every lane runs `call` with its own `ln`, then the team synchronises; the CPU
-// emulation runs `call` for ln = 0..nt-1 in turn.  Control flow between phases depends only on team-uniform values.
-DG_HD void team_sync(unsigned tmask) {
+// A block advances E environments at once, T lanes each.  Thread t is lane (t / E) of environment (t % E): the 32
+// threads of a warp are the SAME lane index of 32 different environments, so a phase in which only a few lanes per
+// environment have work (one lane per body, one per IK op ...) runs on a few FULL warps while the other warps wait
+// at the barrier without issuing anything.  Phases are separated by block barriers; therefore every decision that
+// changes the number of barriers (narrow-phase rounds, "is there any contact", "is any pair of bodies coupled") is
+// taken block-uniformly with block_any().  Environments without work in this launch (tail of the batch, reset mask
+// off) have C.active == false: they skip the phase bodies but keep the barriers.  T == 1 needs no barriers at all.
+// The CPU emulation runs one environment at a time, lane after lane - exactly the barrier semantics.
 #if defined(__CUDA_ARCH__)
-  if (tmask != 1u) __syncwarp(tmask);
-#else
-  (void)tmask;
-#endif
-}
-#if defined(__CUDA_ARCH__)
-#define DG_PHASE(call) do { call; team_sync(tmask); } while (0)
-#define DG_LANE_ARGS int ln, unsigned tmask
+#define DG_PHASE(call) do { if (C.active) { call; } if (nt > 1) __syncthreads(); } while (0)
+#define DG_LANE_ARGS int ln
+DG_HD bool block_any(bool p, int nt) { return nt > 1 ? (__syncthreads_or(p ? 1 : 0) != 0) : p; }
 #else
 #define DG_PHASE(call) do { for (int ln = 0; ln < nt; ln++) { call; } } while (0)
-#define DG_LANE_ARGS int, unsigned
+#define DG_LANE_ARGS int
+DG_HD bool block_any(bool p, int) { return p; }
 #endif
+#define HDRV(k) (C.active ? WSI(C)[SC.W_HDR + (k)] : 0)
 
 // p.stepSimulation() (diy_gym.py:146,207); nsub = 0 only refreshes the link cache
 DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {
@@ -1424,25 +1427,23 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
     if (sc.npair > 0) {
       DG_PHASE(phase_broad(C, ln, nt));
       DG_PHASE(phase_count_survivors(C, ln, nt));
-      int nsurv = WSI(C)[sc.W_HDR + WH_NSURV];
-      for (int rnd = 0; rnd * nt < nsurv; rnd++) {
+      for (int rnd = 0; block_any(rnd * nt < HDRV(WH_NSURV), nt); rnd++) {
         DG_PHASE(phase_narrow(C, ln, nt, rnd));
         DG_PHASE(phase_append(C, ln, nt));
       }
     }
     DG_PHASE(phase_minv(C, ln, nt));
     DG_PHASE(phase_unit_rows(C, ln, nt, h));
-    int ncr = WSI(C)[sc.W_HDR + WH_NCROW];
-    if (ncr == 0) {
+    if (!block_any(HDRV(WH_NCROW) > 0, nt)) {
       DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
     } else {
       DG_PHASE(phase_contact_rows(C, ln, nt, h));
-      if (WSI(C)[sc.W_HDR + WH_COUPLED] == 0) {
-        DG_PHASE(phase_pgs_full(C, ln, nt));        // no row couples two dynamic bodies: every body solves on its own
-      } else {
+      // environments in which no row couples two dynamic bodies: every body solves on its own, all sweeps at once
+      DG_PHASE(if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
+      if (block_any(HDRV(WH_COUPLED) != 0, nt)) {   // the others sweep in lock-step
         for (int it = 0; it < sc.iters; it++) {
-          DG_PHASE(phase_pgs_unit(C, ln, nt, it, it + 1));
-          DG_PHASE(phase_pgs_contact(C, ln, nt));
+          DG_PHASE(if (HDRV(WH_COUPLED) != 0) phase_pgs_unit(C, ln, nt, it, it + 1));
+          DG_PHASE(if (HDRV(WH_COUPLED) != 0) phase_pgs_contact(C, ln, nt));
         }
       }
     }
@@ -1456,11 +1457,11 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
 DG_FN void run_env_step(const Env& C, int nt, DG_LANE_ARGS) {
 #if defined(__CUDA_ARCH__)
   DG_PHASE(phase_actions(C, ln, nt));
-  run_physics(C, nt, SC.substeps, 1, ln, tmask);
+  run_physics(C, nt, SC.substeps, 1, ln);
   DG_PHASE(phase_observe(C, ln, nt));
 #else
   DG_PHASE(phase_actions(C, ln, nt));
-  run_physics(C, nt, SC.substeps, 1, 0, 0);
+  run_physics(C, nt, SC.substeps, 1, 0);
   DG_PHASE(phase_observe(C, ln, nt));
 #endif
 }
@@ -1468,13 +1469,13 @@ DG_FN void run_env_step(const Env& C, int nt, DG_LANE_ARGS) {
 DG_FN void run_env_reset(const Env& C, int nt, DG_LANE_ARGS) {
 #if defined(__CUDA_ARCH__)
   DG_PHASE(phase_reset_ops(C, ln, nt));
-  run_physics(C, nt, 0, 0, ln, tmask);
-  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, ln, tmask);
+  run_physics(C, nt, 0, 0, ln);
+  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, ln);
   DG_PHASE(phase_observe(C, ln, nt));
 #else
   DG_PHASE(phase_reset_ops(C, ln, nt));
-  run_physics(C, nt, 0, 0, 0, 0);
-  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, 0, 0);
+  run_physics(C, nt, 0, 0, 0);
+  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, 0);
   DG_PHASE(phase_observe(C, ln, nt));
 #endif
 }

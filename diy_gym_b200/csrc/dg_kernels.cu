@@ -25,15 +25,14 @@ struct LaunchArgs {
 };
 
 template <int T>
-__global__ void __launch_bounds__(128) dg_step_kernel(const __grid_constant__ DevScene sc, const LaunchArgs a) {
+__global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ DevScene sc, const LaunchArgs a) {
   extern __shared__ __align__(16) float smem[];
-  const int teams_per_block = blockDim.x / T;
-  const int team = threadIdx.x / T, ln = threadIdx.x % T;
-  const unsigned lane = threadIdx.x & 31u;
-  const unsigned tmask = T == 32 ? 0xffffffffu : (((1u << T) - 1u) << (lane & ~(unsigned)(T - 1)));
+  // thread t = lane (t / E) of the block's environment (t % E): a warp holds one lane index of 32 environments
+  const int E = blockDim.x / T;
+  const int ei = threadIdx.x % E, ln = threadIdx.x / E;
   Env C;
-  // the block's copy of the link tables sits behind the team workspaces
-  int* s_link_i = reinterpret_cast<int*>(smem + (size_t)teams_per_block * sc.w_total);
+  // the block's copy of the link tables sits behind the per-environment workspaces
+  int* s_link_i = reinterpret_cast<int*>(smem + (size_t)E * sc.w_total);
   float* s_link_f = reinterpret_cast<float*>(s_link_i + ((DG_LINK_I_W * sc.nl + 3) & ~3));
   float* s_link_x = s_link_f + DG_LINK_F_W * sc.nl;
   for (int i = threadIdx.x; i < DG_LINK_I_W * sc.nl; i += blockDim.x) s_link_i[i] = sc.link_i[i];
@@ -41,14 +40,18 @@ __global__ void __launch_bounds__(128) dg_step_kernel(const __grid_constant__ De
   for (int i = threadIdx.x; i < 16 * sc.nl; i += blockDim.x) s_link_x[i] = sc.link_x[i];
   __syncthreads();
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
-  C.sc = &sc; C.ws = smem + (size_t)team * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * teams_per_block + team) * sc.g_total; C.seed = a.seed; C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
-  for (int e = blockIdx.x * teams_per_block + team; e < a.n_envs; e += gridDim.x * teams_per_block) {
-    if (a.mask != nullptr && a.mask[e] == 0) continue;
-    C.st = a.state + (size_t)e * sc.S; C.pr = a.param + (size_t)e * sc.P;
-    C.act = a.act + (size_t)e * sc.n_act; C.obs = a.obs + (size_t)e * sc.n_obs; C.rew = a.rew + (size_t)e * sc.n_rew;
-    C.term = a.term + (size_t)e * sc.n_term; C.env_id = a.env_off + e;
-    if (a.mode == 0) run_env_step(C, T, ln, tmask); else run_env_reset(C, T, ln, tmask);
-    team_sync(tmask);
+  C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * E + ei) * sc.g_total; C.seed = a.seed;
+  C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
+  // block-uniform trip count: every thread of the block walks the same number of environment groups
+  for (int base = blockIdx.x * E; base < a.n_envs; base += gridDim.x * E) {
+    const int e = base + ei;
+    C.active = e < a.n_envs && (a.mask == nullptr || a.mask[e] != 0);
+    const int ec = e < a.n_envs ? e : a.n_envs - 1;
+    C.st = a.state + (size_t)ec * sc.S; C.pr = a.param + (size_t)ec * sc.P;
+    C.act = a.act + (size_t)ec * sc.n_act; C.obs = a.obs + (size_t)ec * sc.n_obs; C.rew = a.rew + (size_t)ec * sc.n_rew;
+    C.term = a.term + (size_t)ec * sc.n_term; C.env_id = a.env_off + ec;
+    if (a.mode == 0) run_env_step(C, T, ln); else run_env_reset(C, T, ln);
+    if (T > 1) __syncthreads();
   }
 }
 
@@ -102,8 +105,9 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
   return hit;
 }
 
-// per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1) = 21 floats
-#define VS_W 21
+// per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1), then the camera-relative part that
+// is the same for every pixel: M = R_shape^T R_cam (9), ray origin in the shape frame (3), |origin|^2 - radius^2 (1)
+#define VS_W 36
 #define DG_TILE 32   // square pixel tile per block; 256 threads, 4 pixels each
 __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
                                                         int tiles_x, int tiles_y) {
@@ -155,6 +159,9 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
     float t_ax = v_dot(vc, cone), perp2 = fmaxf(v_dot(vc, vc) - t_ax * t_ax, 0.f), r = o[20];
     float lim = fmaxf(t_ax, 0.f) * cone[3] + r * cone[4];
     if (t_ax > -r && perp2 <= lim * lim) atomicOr(&cand[s >> 5], 1u << (s & 31));
+    float oc[3], ol[3]; v_sub(oc, camRp + 9, o + 9); mT_vec(ol, o, oc);
+    mT_mul(o + 21, o, camRp);                                   // camera-space direction -> shape-frame direction
+    o[30] = ol[0]; o[31] = ol[1]; o[32] = ol[2]; o[33] = v_dot(ol, ol) - r * r;
   }
   __syncthreads();
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
@@ -164,23 +171,23 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
     int i = tx * DG_TILE + (k % DG_TILE), j = ty * DG_TILE + (k / DG_TILE);
     if (i >= width || j >= height) continue;
     int px = j * width + i;
-    float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f}, dw[3];
-    m_vec(dw, camRp, dc);
-    float dd = v_dot(dw, dw);
-    float best = farp; int hs = -1; float hn[3] = {0, 0, 1};
+    const float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f};
+    const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
+    float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
     for (int wd = 0; wd < ncw; wd++) {
       unsigned bits = cand[wd];
       while (bits) {
         int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1;
         const float* o = vs + VS_W * s;
-        float oc[3]; v_sub(oc, camRp + 9, o + 9);
-        float b = v_dot(oc, dw), c2 = v_dot(oc, oc) - o[20] * o[20];   // per-ray bounding-sphere reject
+        float dl[3]; m_vec(dl, o + 21, dc);
+        const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
         if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
-        float ol[3], dl[3], tt, nn[3];
-        mT_vec(ol, o, oc); mT_vec(dl, o, dw);
-        if (ray_shape(float_as_int(o[19]), o + 12, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, o, nn); }
+        float tt, nn[3];
+        if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
       }
     }
+    float hn[3] = {0, 0, 1};
+    if (hs >= 0) m_vec(hn, vs + VS_W * hs, hnl);
     float r, g, bl, dz;
     if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
     else {
@@ -272,15 +279,14 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
     }
     if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
   }
-  const char* env_block = getenv("DG_BLOCK");
-  int block = env_block ? atoi(env_block) : 128;
-  if (!env_block) {
-    // enough blocks to spread over all SMs a few times: shrink the block while the grid would be smaller than 3 waves
-    while (block > 32 && block / 2 >= team && (n_envs + (block / team) - 1) / (block / team) < 3 * w->sm_count) block /= 2;
-  }
-  if (block < team) block = team;
-  if (block > 128) block = 128;
-  block = (block / team) * team;
+  // environments per block: 32 (one warp per lane index) unless the block would exceed 256 threads or the batch is
+  // too small to give every SM a few blocks; DG_ENVS_PER_BLOCK overrides
+  const char* env_e = getenv("DG_ENVS_PER_BLOCK");
+  int epb = env_e ? atoi(env_e) : 32;
+  if (!env_e) while (epb > 8 && (n_envs + epb - 1) / epb < 2 * w->sm_count) epb /= 2;
+  while (epb * team > 256) epb /= 2;
+  if (epb < 1) epb = 1;
+  int block = epb * team;
   // workspace placement (dg_scene.h): frames / joint transforms / articulated-body transients always live in the
   // L2-backed cold workspace and the solver state in shared memory; the contact arrays default to the cold workspace
   // too (mode 3: measured faster on every example scene because more environments stay resident per SM);

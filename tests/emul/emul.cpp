@@ -43,18 +43,18 @@ static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* re
   const DevScene& d = w->hs.dev; Env C;
   C.sc = &d; C.ws = w->ws.data(); C.wg = w->wg.data(); C.link_i = d.link_i; C.link_f = d.link_f; C.link_x = d.link_x; C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
   C.act = act ? act + (size_t)e * d.n_act : nullptr; C.obs = obs + (size_t)e * d.n_obs; C.rew = rew + (size_t)e * d.n_rew;
-  C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
+  C.active = true; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;
 }
 void dge_step(EmulWorld* w, const float* act, float* obs, float* rew, uint8_t* term) {
-  for (int e = 0; e < w->n_envs; e++) { Env C = make_env(w, e, act, obs, rew, term); run_env_step(C, w->team, 0, 0); }
+  for (int e = 0; e < w->n_envs; e++) { Env C = make_env(w, e, act, obs, rew, term); run_env_step(C, w->team, 0); }
 }
 void dge_reset(EmulWorld* w, const uint8_t* mask, float* obs, float* rew, uint8_t* term) {
-  for (int e = 0; e < w->n_envs; e++) { if (mask && !mask[e]) continue; Env C = make_env(w, e, nullptr, obs, rew, term); run_env_reset(C, w->team, 0, 0); }
+  for (int e = 0; e < w->n_envs; e++) { if (mask && !mask[e]) continue; Env C = make_env(w, e, nullptr, obs, rew, term); run_env_reset(C, w->team, 0); }
 }
 // physics only (no add-on ops): nsub = 0 refreshes the link cache
 void dge_physics(EmulWorld* w, int nsub) {
   std::vector<float> o(w->hs.dev.n_obs + 1), r(w->hs.dev.n_rew + 1); std::vector<uint8_t> t(w->hs.dev.n_term + 1);
-  for (int e = 0; e < w->n_envs; e++) { Env C = make_env(w, 0, nullptr, o.data(), r.data(), t.data()); C.st = w->state.data() + (size_t)e * w->hs.dev.S; C.pr = w->param.data() + (size_t)e * w->hs.dev.P; run_physics(C, w->team, nsub, nsub > 0, 0, 0); }
+  for (int e = 0; e < w->n_envs; e++) { Env C = make_env(w, 0, nullptr, o.data(), r.data(), t.data()); C.st = w->state.data() + (size_t)e * w->hs.dev.S; C.pr = w->param.data() + (size_t)e * w->hs.dev.P; run_physics(C, w->team, nsub, nsub > 0, 0); }
 }
 }

@@ -1,4 +1,4 @@
-"""One timing per (config, team, block, ws mode, envs) given on the command line: name:team:block[:mode[:n_envs]]"""
+"""One timing per (config, team, block, ws mode, envs) given on the command line: name:team:envs_per_block[:mode[:n_envs]]"""
 import os
 import sys
 import torch
@@ -11,9 +11,9 @@ for spec in sys.argv[1:]:
     parts = spec.split(':')
     name, team, block = parts[0], int(parts[1]), int(parts[2])
     if block:
-        os.environ['DG_BLOCK'] = str(block)
+        os.environ['DG_ENVS_PER_BLOCK'] = str(block)
     else:
-        os.environ.pop('DG_BLOCK', None)
+        os.environ.pop('DG_ENVS_PER_BLOCK', None)
     os.environ['DG_WS_MODE'] = parts[3] if len(parts) > 3 else '2'
     n_envs = int(parts[4]) if len(parts) > 4 else CONFIGS[name][1]
     try:

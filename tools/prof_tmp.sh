@@ -1,4 +1,4 @@
-for c in r2d2_maze ur_high_5 from_the_readme drone_pilot ur_high_5_randomised basic_env; do python bench.py --config $c --steps 30 --warmup 5 > gpurun_out/bench1_$c.json 2> gpurun_out/bench1_$c.err; tail -c 300 gpurun_out/bench1_$c.err; done
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench1_ref.json 2>&1
-python bench.py --steps 20 --warmup 5 > gpurun_out/plain_bench.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-tail -2 gpurun_out/ncu_launch.log
+for lib in libdiygym_b200.so libdg_a.so libdg_b.so libdg_c.so; do
+echo "== $lib"
+DG_LIB=$PWD/diy_gym_b200/$lib timeout 300 python tools/gpu_probe3.py ur_high_5:4:32:0 ur_high_5:4:64:0 ur_high_5:8:32:0 r2d2_maze:8:0:0 r2d2_maze:8:32:0 from_the_readme:8:0:0 ur_high_5:4:64:0:65536 ur_high_5:8:32:0:65536
+done
