@@ -283,7 +283,13 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   // too small to give every SM a few blocks; DG_ENVS_PER_BLOCK overrides
   const char* env_e = getenv("DG_ENVS_PER_BLOCK");
   int epb = env_e ? atoi(env_e) : 32;
-  if (!env_e) while (epb > 8 && (n_envs + epb - 1) / epb < 2 * w->sm_count) epb /= 2;
+  if (!env_e) {
+    // measured (profiles/r1_block_size_sweep.log): scenes of small teams with articulated bodies (ur_high_5) run best with
+    // full 32-environment blocks as long as every SM gets ~1.5 of them; the others want at least 2 smaller blocks per SM
+    const int nd_ = ibuf[ibuf[2 + 3 * SEC_HDR_I + 1] + HI_nd];
+    const int num = (team <= 4 && nd_ >= 8) ? 3 : 4;   // blocks per SM x 2
+    while (epb > 8 && 2 * ((n_envs + epb - 1) / epb) < num * w->sm_count) epb /= 2;
+  }
   while (epb * team > 256) epb /= 2;
   if (epb < 1) epb = 1;
   int block = epb * team;

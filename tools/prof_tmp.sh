@@ -1,4 +1,2 @@
-for lib in libdiygym_b200.so libdg_a.so libdg_b.so libdg_c.so; do
-echo "== $lib"
-DG_LIB=$PWD/diy_gym_b200/$lib timeout 300 python tools/gpu_probe3.py ur_high_5:4:32:0 ur_high_5:4:64:0 ur_high_5:8:32:0 r2d2_maze:8:0:0 r2d2_maze:8:32:0 from_the_readme:8:0:0 ur_high_5:4:64:0:65536 ur_high_5:8:32:0:65536
-done
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4 > gpurun_out/pytest_gpu11.log; cat gpurun_out/pytest_gpu11.log
+timeout 600 python tools/gpu_probe3.py ur_high_5:0:0:3 r2d2_maze:0:0:3 r2d2_maze:8:8:3 from_the_readme:0:0:3 from_the_readme:8:8:3 drone_pilot:0:0:3 drone_pilot:4:8:3 basic_env:0:0:3 ur_high_5:0:0:3:65536 ur_high_5:0:0:3:1024 r2d2_maze:0:0:3:16384 2>&1 | tee gpurun_out/probe27.log
