@@ -239,6 +239,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # L2 flush between timed iterations: a buffer twice the size of the 126 MB L2 is overwritten before every timed
+    # step (outside the per-step CUDA-event brackets), so that every step starts with state, parameters and actions
+    # in HBM, not in L2
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
     for i in range(warmup):
         device_step(i)
     barrier()
@@ -252,14 +257,18 @@ def main():
         kev[i][0].record()
         step_plain()
         kev[i][1].record()
+    sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
+        flush_buf.fill_(float(i))               # L2 flush (a torch fill kernel: not counted in gpu_launches, not timed)
         w.step = lambda i=i: step_timed(i)      # CUDA events around the dominant kernel, on the launching stream
+        sev[i][0].record()
         device_step(warmup + i)
+        sev[i][1].record()
     e1.record()
     w.step = step_plain
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = float(sum(a.elapsed_time(b) for a, b in sev))   # the K timed steps, device time, flushes excluded
     launches = w.launches - l0
     clocks = sampler.stop() if sampler else None
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))   # average launch duration inside the timed region
@@ -339,8 +348,13 @@ def main():
     if not args.no_cpu_baseline:
         cpu = cpu_oracle_rate(sc, lo_np, hi_np)
     flops = cpu['flops_per_env_step'] if cpu else None
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one dg_step_kernel launch (ncu --set full), tools/ncu_traffic.py
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get('%s:%d' % (args.config, n_envs))
+    except Exception:
+        pass
     roofline = {'bound': 'hbm', 'kernel': 'dg_step_kernel<%d>' % w.team, 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback',
+                'frac': achieved / hbm_peak, 'traffic': traffic, 'peak_source': 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback',
                 'algorithmic_bytes_per_env_step': alg_bytes, 'kernel_ms': kernel_ms,
                 'note': 'physics-only configs are bound by FP32 issue / latency, not HBM: see fp32'}
     if flops:
@@ -350,7 +364,7 @@ def main():
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps, 'warmup': warmup,
             'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'config': dict(cfg_workload, team=w.team, block_threads=w.block_threads, grid_blocks=w.grid_blocks,
-                                                smem_bytes=w.smem_bytes, l2_policy='per-step inputs cycle through 8 pre-generated action batches; state is re-read and re-written every step'),
+                                                smem_bytes=w.smem_bytes, l2_policy='L2 flushed (256 MB buffer overwritten) before every timed step; per-step actions cycle through 8 pre-generated batches'),
             'e2e': {'value': e2e_v, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'api': 'dg_step_host (pinned host buffers)'},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line))
