@@ -214,11 +214,11 @@ class Camera(Addon):
         self.rpy = config.get('rpy', [0., 0., 0.])
         self.use_depth = bool(config.get('use_depth', True))
         self.use_seg_mask = bool(config.get('use_segmentation_mask', False))
-        if self.use_seg_mask:
-            raise NotImplementedError('camera: segmentation masks are a "next" row (SURVEY 8f-4)')
         self.observation_space = spaces.Dict({'rgb': spaces.Box(0., 1., shape=self.resolution + [3], dtype='float32')})
         if self.use_depth:
             self.observation_space.spaces['depth'] = spaces.Box(0., 10., shape=self.resolution, dtype='float32')
+        if self.use_seg_mask:   # camera.py:54-56
+            self.observation_space.spaces['segmentation_mask'] = spaces.Box(0., 10., shape=self.resolution, dtype='float32')
 
     def compile(self, sb):
         from ..compiler.mathutil import quat_from_euler
@@ -229,10 +229,12 @@ class Camera(Addon):
         self.env = env
 
     def observe(self):
-        rgb, depth = self.env.world.render(self.cam)
-        out = {'rgb': rgb}   # [N, H, W, 3]; the reference labels the same buffer (W, H, 3) (camera.py:77)
+        img = self.env.world.render(self.cam, seg=self.use_seg_mask)
+        out = {'rgb': img[0]}   # [N, H, W, 3]; the reference labels the same buffer (W, H, 3) (camera.py:77)
         if self.use_depth:
-            out['depth'] = depth
+            out['depth'] = img[1]
+        if self.use_seg_mask:   # unique id of the visible body per pixel, -1 = background (camera.py:89-90)
+            out['segmentation_mask'] = img[2]
         return out
 
 

@@ -51,6 +51,8 @@ def load_library():
     L.dg_reset.argtypes = [vp, vp, vp]
     L.dg_render.restype = ctypes.c_int
     L.dg_render.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    L.dg_render_seg.restype = ctypes.c_int
+    L.dg_render_seg.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     L.dg_set_action_mask.restype = ctypes.c_int
     L.dg_set_action_mask.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int]
     L.dg_step_host.restype = ctypes.c_int
@@ -140,12 +142,19 @@ class World:
         m = np.ascontiguousarray(enabled, np.uint8)
         self._check(self.L.dg_set_action_mask(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), m.size))
 
-    def render(self, cam=0):
+    def render(self, cam=0, seg=False):
         w, hgt = self.cams[cam]
         if cam not in self._img:
             self._img[cam] = (torch.empty((self.n_envs, hgt, w, 3), dtype=torch.float32, device=self.device),
                               torch.empty((self.n_envs, hgt, w), dtype=torch.float32, device=self.device))
         rgb, depth = self._img[cam]
+        if seg:
+            if ('seg', cam) not in self._img:
+                self._img[('seg', cam)] = torch.empty((self.n_envs, hgt, w), dtype=torch.float32, device=self.device)
+            mask = self._img[('seg', cam)]
+            self._check(self.L.dg_render_seg(self._h, cam, ctypes.c_void_p(rgb.data_ptr()), ctypes.c_void_p(depth.data_ptr()),
+                                             ctypes.c_void_p(mask.data_ptr()), self._stream()))
+            return rgb, depth, mask
         self._check(self.L.dg_render(self._h, cam, ctypes.c_void_p(rgb.data_ptr()), ctypes.c_void_p(depth.data_ptr()), self._stream()))
         return rgb, depth
 

@@ -251,7 +251,7 @@ class SceneBuilder:
                     if b.color is not None and k == 0:
                         rgba = [float(x) for x in b.color]
                     Tw = Transform(b.base_pos, b.base_quat) * T
-                    visuals.append(dict(frame=fr, type=SHAPE_TYPES[v['type']], pos=T.p, quat=T.q, dims=dims, rgba=rgba,
+                    visuals.append(dict(body=b.index, frame=fr, type=SHAPE_TYPES[v['type']], pos=T.p, quat=T.q, dims=dims, rgba=rgba,
                                         baked=int(b.kind == 0 and not b.per_env_pose), wpos=Tw.p, wquat=Tw.q))
 
         ns, nv = len(shapes), len(visuals)
@@ -268,7 +268,7 @@ class SceneBuilder:
         vis_i = np.zeros((nv, VIS_I_W), np.int32)
         vis_f = np.zeros((nv, VIS_F_W))
         for i, v in enumerate(visuals):
-            vis_i[i] = [v['frame'], v['type'], v['baked'], 0]
+            vis_i[i] = [v['frame'], v['type'], v['baked'], v['body']]   # body index = the uid pybullet's segmentation mask reports
             vis_f[i, 16:19], vis_f[i, 19:23] = v['wpos'], v['wquat']
             vis_f[i, 0:3], vis_f[i, 3:7], vis_f[i, 7:11], vis_f[i, 11:15] = v['pos'], v['quat'], v['dims'], v['rgba']
             d = v['dims']

@@ -110,7 +110,7 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_W 36
 #define DG_TILE 32   // square pixel tile per block; 256 threads, 4 pixels each
 __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
-                                                        int tiles_x, int tiles_y) {
+                                                        float* seg, int tiles_x, int tiles_y) {
   extern __shared__ __align__(16) float vs[];       // [nv][VS_W] then the candidate bit set
   __shared__ float camRp[12];
   __shared__ float cone[5];                          // unit axis of the tile (3), tan and 1/cos of its half angle
@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
       r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best;
     }
     rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
+    // segmentation mask (camera.py:89-90): unique id of the visible body, -1 where the ray hits nothing
+    if (seg != nullptr) seg[(size_t)e * npx + px] = hs < 0 ? -1.0f : (float)sc.vis_i[DG_VIS_I_W * hs + 3];
   }
 }
 
@@ -391,7 +393,7 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
 int dg_step(DgWorld* w, void* stream) { return run(w, 0, nullptr, stream); }
 int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream) { return run(w, 1, mask_dev, stream); }
 
-int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream) {
+int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream) {
   if (!w || !rgb_dev || !depth_dev) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_render: buffers not bound"; return DG_E_UNBOUND; }
   const DevScene& d = w->dev;
@@ -401,10 +403,11 @@ int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* strea
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)(d.nv + 31) / 32 + 4) * sizeof(float);
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   w->launches++;
-  dg_render_kernel<<<w->n_envs * tiles_x * tiles_y, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, tiles_x, tiles_y);
+  dg_render_kernel<<<w->n_envs * tiles_x * tiles_y, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y);
   CK(w, cudaGetLastError());
   return DG_OK;
 }
+int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream) { return dg_render_seg(w, cam, rgb_dev, depth_dev, nullptr, stream); }
 
 int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* reward_host, uint8_t* term_host, void* stream) {
   if (!w) return DG_E_ARG;

@@ -80,6 +80,9 @@ int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream);
 /* Camera add-on number `cam`: rgb [n_envs][H][W][3] float in [0,1], depth [n_envs][H][W] eye-space z (negative).
  * Replaces p.getCameraImage + post-processing (/root/reference/diy_gym/addons/sensors/camera.py:58-92). */
 int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream);
+/* The same with the segmentation mask of sensors/camera.py:54-56,89-90 (`use_segmentation_mask`): seg_dev [n_envs][H][W] gets
+ * the unique id (body index in load order) of the body visible in each pixel, -1 for the background; NULL = no mask. */
+int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream);
 
 /* Host-buffer form of dg_step (the reference-facing call when the caller keeps numpy arrays): copies the actions
  * host->device, steps, copies obs / reward / terminal device->host and waits.  Any output pointer may be NULL. */

@@ -1038,7 +1038,7 @@ static int ray_shape(int type, const double* d, const double* o, const double* d
 }
 /* camera.py:58-92: rgb (float in [0,1]) and eye-space depth (negative z, as the reference's linearisation yields).
  * Buffers are row-major image rows (height x width), which the reference then labels (W,H,...) (camera.py:77,82). */
-void dgo_render(DgoWorld* W, int cam, double* rgb, double* depth) {
+void dgo_render_seg(DgoWorld* W, int cam, double* rgb, double* depth, double* seg) {
   const int32_t* ci = W->cam_i + DG_CAM_I_W * cam; const double* cf = W->cam_f + DG_CAM_F_W * cam;
   int width = ci[1], height = ci[2];
   double Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0};
@@ -1066,6 +1066,7 @@ void dgo_render(DgoWorld* W, int cam, double* rgb, double* depth) {
       if (ray_shape(vi[1], vf + 7, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, VR + 12 * s, nn); }
     }
     int px = j * width + i;
+    if (seg) seg[px] = hs < 0 ? -1.0 : (double)W->vis_i[DG_VIS_I_W * hs + 3];   /* camera.py:89-90: unique id of the visible body */
     if (hs < 0) { rgb[3 * px] = rgb[3 * px + 1] = rgb[3 * px + 2] = 1.0; depth[px] = -farp; }
     else {
       const double* col = W->vis_f + DG_VIS_F_W * hs + 11; double nl = v_dot(hn, light); if (nl < 0) nl = 0;
@@ -1076,3 +1077,4 @@ void dgo_render(DgoWorld* W, int cam, double* rgb, double* depth) {
   }
   free(VR);
 }
+void dgo_render(DgoWorld* W, int cam, double* rgb, double* depth) { dgo_render_seg(W, cam, rgb, depth, (double*)0); }

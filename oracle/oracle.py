@@ -51,6 +51,7 @@ def lib():
         L.dgo_observe.argtypes = [vp, dp, dp, u8]
         L.dgo_env_step.argtypes = [vp, dp, dp, dp, u8]
         L.dgo_render.argtypes = [vp, ctypes.c_int, dp, dp]
+        L.dgo_render_seg.argtypes = [vp, ctypes.c_int, dp, dp, dp]
         L.dgo_batch_max_threads.restype = ctypes.c_int
         L.dgo_batch_step.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, dp, ctypes.c_int, dp,
                                      ctypes.c_int, u8, ctypes.c_int, ctypes.c_int]
@@ -142,10 +143,14 @@ class OracleWorld:
             out.append(dict(fa=int(c[0]), fb=int(c[1]), pa=c[2:5], pb=c[5:8], n=c[8:11], dist=c[11], mu=c[12]))
         return out
 
-    def render(self, cam=0):
+    def render(self, cam=0, seg=False):
         w, hgt = int(self.scene.sec['CAM_I'][cam][1]), int(self.scene.sec['CAM_I'][cam][2])
         rgb = np.zeros((hgt, w, 3))
         depth = np.zeros((hgt, w))
+        if seg:
+            mask = np.zeros((hgt, w))
+            lib().dgo_render_seg(self._w, cam, _dp(rgb), _dp(depth), _dp(mask))
+            return rgb, depth, mask
         lib().dgo_render(self._w, cam, _dp(rgb), _dp(depth))
         return rgb, depth
 

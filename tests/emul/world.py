@@ -47,17 +47,20 @@ class EmulTorchWorld:
             m = self._m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
         lib().dge_reset(self.e._w, m, *self._ptrs())
 
-    def render(self, cam=0):
+    def render(self, cam=0, seg=False):
         if self._oracle is None:
             self._oracle = OracleWorld(self.scene)
         w, hgt = self.cams[cam]
         rgb = np.zeros((self.n_envs, hgt, w, 3), np.float32)
         depth = np.zeros((self.n_envs, hgt, w), np.float32)
+        mask = np.zeros((self.n_envs, hgt, w), np.float32)
         for e in range(self.n_envs):
             self._oracle.state[:] = self.e.state[e]
-            r, d = self._oracle.render(cam)
-            rgb[e], depth[e] = r, d
-        return torch.from_numpy(rgb), torch.from_numpy(depth)
+            out = self._oracle.render(cam, seg=seg)
+            rgb[e], depth[e] = out[0], out[1]
+            if seg:
+                mask[e] = out[2]
+        return (torch.from_numpy(rgb), torch.from_numpy(depth)) + ((torch.from_numpy(mask), ) if seg else ())
 
     def set_action_mask(self, enabled):
         m = np.ascontiguousarray(enabled, np.uint8)

@@ -208,6 +208,11 @@ def test_camera_kernel_matches_oracle_ray_cast():
         same = close[..., None] & np.ones(3, bool)
         assert np.abs(rgb.cpu().numpy()[0] - rgb_o)[same].max() < 2e-3
         assert torch.equal(rgb[0], rgb[1])
+        # segmentation mask (camera.py:89-90): same body ids as the oracle, silhouette pixels aside
+        _, _, seg = env.world.render(0, seg=True)
+        torch.cuda.synchronize()
+        seg_o = o.render(0, seg=True)[2]
+        assert (seg.cpu().numpy()[0] == seg_o).mean() > 0.999 and set(np.unique(seg_o)) == set(np.unique(seg.cpu().numpy()[0]))
         env.close()
 
 

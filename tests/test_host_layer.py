@@ -66,6 +66,28 @@ def test_basic_env_episode_marble_moves_and_reset_restores():
     assert obs['basic_env']['camera']['rgb'].shape == (2, 50, 50, 3)
 
 
+def test_camera_segmentation_mask_reports_body_ids():
+    """sensors/camera.py:54-56,89-90: `use_segmentation_mask` adds a per-pixel unique-id image (-1 = background)."""
+    import copy
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(EX, 'basic_env', 'basic_env.yaml')))
+    cfg['camera']['use_segmentation_mask'] = True
+    path = os.path.join(os.path.dirname(__file__), '_tmp_seg.yaml')
+    with open(path, 'w') as f:
+        yaml.safe_dump(cfg, f)
+    try:
+        env = DIYGym(path, num_envs=1, world_factory=factory())
+        assert env.observation_space['_tmp_seg']['camera']['segmentation_mask'].shape == (50, 50)
+        obs = env.reset()
+        mask = obs['_tmp_seg']['camera']['segmentation_mask'][0].numpy()
+        ids = {int(v) for v in np.unique(mask)}
+        marbles = {env.models[m].body.index for m in ('red_marble', 'green_marble', 'blue_marble')}
+        assert marbles <= ids and env.models['plane'].body.index in ids      # the overhead camera sees the plane and the three marbles
+        assert ids <= marbles | {env.models['plane'].body.index, -1}
+    finally:
+        os.remove(path)
+
+
 # ---- reference tests/test_utils.py ----------------------------------------------------------------------------
 def test_flatten_unflatten_round_trip():
     env = make('basic_env')
