@@ -4,8 +4,9 @@
 // environment at a time with its whole working set (dg_scene.h workspace plan) in dynamic shared memory, and
 // walks the environment list with a grid stride.  Scene constants are read-only global arrays shared by all
 // environments (L1/L2 resident).  State rows are [env][S] so that a team's loads and stores are contiguous.
-// dg_render_kernel: one block per (environment, pixel tile); visual shapes are staged in shared memory once per
-// block and every thread ray-casts its pixels (camera.py:58-92 of the reference, TinyRenderer replaced).
+// dg_render_kernel: one block per environment (or per group of its pixel tiles when the batch is small); visual shapes
+// are staged in shared memory once per block, every tile is culled against them and every thread ray-casts its pixels
+// (camera.py:58-92 of the reference, TinyRenderer replaced).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -90,16 +91,20 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
     }
   }
   if (type == SHAPE_BOX) {
-    float t0 = -1e30f, t1 = 1e30f; int ax0 = 0; float sg0 = 1; bool ok = true;
+    // slab test without branches: the three axes are independent (reciprocals by the SFU, ~1 ulp: the depth tolerance
+    // is 1e-4); a ray parallel to a slab gets (-inf, +inf) inside it and an empty interval outside
+    float t0 = -1e30f, t1 = 1e30f; int ax0 = 0; float sg0 = 1;
+#pragma unroll
     for (int i = 0; i < 3; i++) {
-      if (fabsf(dir[i]) < 1e-18f) { if (fabsf(o[i]) > d[i]) ok = false; continue; }
-      float inv = 1.0f / dir[i];
-      float ta = (-d[i] - o[i]) * inv, tb = (d[i] - o[i]) * inv, sg = -1;
-      if (ta > tb) { float t = ta; ta = tb; tb = t; sg = 1; }
+      const bool par = fabsf(dir[i]) < 1e-18f, inside = fabsf(o[i]) <= d[i];
+      const float inv = __fdividef(1.0f, par ? 1.0f : dir[i]);
+      const float ua = (-d[i] - o[i]) * inv, ub = (d[i] - o[i]) * inv;
+      float ta = fminf(ua, ub), tb = fmaxf(ua, ub); const float sg = ua > ub ? 1.f : -1.f;
+      ta = par ? (inside ? -1e30f : 1e30f) : ta; tb = par ? (inside ? 1e30f : -1e30f) : tb;
       if (ta > t0) { t0 = ta; ax0 = i; sg0 = sg; }
-      if (tb < t1) t1 = tb;
+      t1 = fminf(t1, tb);
     }
-    if (ok && t0 <= t1 && t0 > 1e-9f && t0 < best) { best = t0; hit = true; nb_[0] = nb_[1] = nb_[2] = 0; if (ax0 == 0) nb_[0] = sg0; else if (ax0 == 1) nb_[1] = sg0; else nb_[2] = sg0; }
+    if (t0 <= t1 && t0 > 1e-9f && t0 < best) { best = t0; hit = true; nb_[0] = ax0 == 0 ? sg0 : 0.f; nb_[1] = ax0 == 1 ? sg0 : 0.f; nb_[2] = ax0 == 2 ? sg0 : 0.f; }
   }
   if (hit) { *t_out = best; v_cpy(n_out, nb_); }
   return hit;
@@ -108,14 +113,18 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 // per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1), then the camera-relative part that
 // is the same for every pixel: M = R_shape^T R_cam (9), ray origin in the shape frame (3), |origin|^2 - radius^2 (1)
 #define VS_W 36
+#ifndef DG_TILE
 #define DG_TILE 32   // square pixel tile per block; 256 threads, 4 pixels each
+#endif
 __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
-                                                        float* seg, int tiles_x, int tiles_y) {
+                                                        float* seg, int tiles_x, int tiles_y, int groups) {
+  // a block = one environment and every `groups`-th pixel tile of its image: the world pose and camera-relative
+  // constants of all visual shapes are worked out once per block, then the tiles are culled and ray-cast one by one
   extern __shared__ __align__(16) float vs[];       // [nv][VS_W] then the candidate bit set
   __shared__ float camRp[12];
   __shared__ float cone[5];                          // unit axis of the tile (3), tan and 1/cos of its half angle
   const int tiles = tiles_x * tiles_y;
-  const int e = blockIdx.x / tiles, tile = blockIdx.x % tiles, ty = tile / tiles_x, tx = tile % tiles_x;
+  const int e = blockIdx.x / groups, grp = blockIdx.x % groups;
   const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
   const int width = ci[1], height = ci[2];
   unsigned* cand = reinterpret_cast<unsigned*>(vs + VS_W * sc.nv);
@@ -124,23 +133,10 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
   const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
-  if (threadIdx.x < ncw) cand[threadIdx.x] = 0u;
   if (threadIdx.x == 0) {
     float Rp[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, pp[3] = {0, 0, 0}, Rl[9], t[3];
     if (ci[0] >= 0) { float q[4]; frame_link_pose(C, ci[0], pp, q); q_to_mat(Rp, q); }
     q_to_mat(Rl, cf + 3); m_mul(camRp, Rp, Rl); m_vec(t, Rp, cf); v_add(camRp + 9, pp, t);
-    // cone around the tile: axis through the tile centre, half angle to the farthest corner
-    float x0 = tx * DG_TILE, x1 = fminf((float)width, x0 + DG_TILE), y0 = ty * DG_TILE, y1 = fminf((float)height, y0 + DG_TILE);
-    float dcc[3] = {((0.5f * (x0 + x1)) / width * 2 - 1) * th * aspect, (1 - (0.5f * (y0 + y1)) / height * 2) * th, -1.0f}, axis[3];
-    m_vec(axis, camRp, dcc); float an = 1.0f / v_len(axis); v_scale(axis, axis, an);
-    float cmin = 1.0f;
-    for (int k = 0; k < 4; k++) {
-      float cx = (k & 1) ? x1 : x0, cy = (k & 2) ? y1 : y0;
-      float dk[3] = {(cx / width * 2 - 1) * th * aspect, (1 - cy / height * 2) * th, -1.0f}, dw[3];
-      m_vec(dw, camRp, dk); cmin = fminf(cmin, v_dot(dw, axis) / v_len(dw));
-    }
-    cmin = fmaxf(cmin * 0.9999f, 0.05f);
-    cone[0] = axis[0]; cone[1] = axis[1]; cone[2] = axis[2]; cone[3] = sqrtf(fmaxf(1.0f - cmin * cmin, 0.f)) / cmin; cone[4] = 1.0f / cmin;
   }
   __syncthreads();
   for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
@@ -154,49 +150,73 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
     for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
     for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
     o[19] = int_as_float(vi[1]); o[20] = vf[15];
-    // bounding sphere against the tile cone (conservative): perpendicular distance <= depth * tan(a) + r / cos(a)
-    float vc[3]; v_sub(vc, o + 9, camRp + 9);
-    float t_ax = v_dot(vc, cone), perp2 = fmaxf(v_dot(vc, vc) - t_ax * t_ax, 0.f), r = o[20];
-    float lim = fmaxf(t_ax, 0.f) * cone[3] + r * cone[4];
-    if (t_ax > -r && perp2 <= lim * lim) atomicOr(&cand[s >> 5], 1u << (s & 31));
+    const float r = o[20];
     float oc[3], ol[3]; v_sub(oc, camRp + 9, o + 9); mT_vec(ol, o, oc);
     mT_mul(o + 21, o, camRp);                                   // camera-space direction -> shape-frame direction
     o[30] = ol[0]; o[31] = ol[1]; o[32] = ol[2]; o[33] = v_dot(ol, ol) - r * r;
   }
-  __syncthreads();
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
   const int npx = width * height;
   float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx;
-  for (int k = threadIdx.x; k < DG_TILE * DG_TILE; k += blockDim.x) {
-    int i = tx * DG_TILE + (k % DG_TILE), j = ty * DG_TILE + (k / DG_TILE);
-    if (i >= width || j >= height) continue;
-    int px = j * width + i;
-    const float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f};
-    const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
-    float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
-    for (int wd = 0; wd < ncw; wd++) {
-      unsigned bits = cand[wd];
-      while (bits) {
-        int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1;
-        const float* o = vs + VS_W * s;
-        float dl[3]; m_vec(dl, o + 21, dc);
-        const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
-        if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
-        float tt, nn[3];
-        if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
+  for (int tile = grp; tile < tiles; tile += groups) {
+    const int ty = tile / tiles_x, tx = tile % tiles_x;
+    __syncthreads();                                   // shapes staged / the previous tile's candidates no longer read
+    if (threadIdx.x < ncw) cand[threadIdx.x] = 0u;
+    if (threadIdx.x == 32) {
+      // cone around the tile: axis through the tile centre, half angle to the farthest corner
+      float x0 = tx * DG_TILE, x1 = fminf((float)width, x0 + DG_TILE), y0 = ty * DG_TILE, y1 = fminf((float)height, y0 + DG_TILE);
+      float dcc[3] = {((0.5f * (x0 + x1)) / width * 2 - 1) * th * aspect, (1 - (0.5f * (y0 + y1)) / height * 2) * th, -1.0f}, axis[3];
+      m_vec(axis, camRp, dcc); float an = 1.0f / v_len(axis); v_scale(axis, axis, an);
+      float cmin = 1.0f;
+      for (int k = 0; k < 4; k++) {
+        float cx = (k & 1) ? x1 : x0, cy = (k & 2) ? y1 : y0;
+        float dk[3] = {(cx / width * 2 - 1) * th * aspect, (1 - cy / height * 2) * th, -1.0f}, dw[3];
+        m_vec(dw, camRp, dk); cmin = fminf(cmin, v_dot(dw, axis) / v_len(dw));
       }
+      cmin = fmaxf(cmin * 0.9999f, 0.05f);
+      cone[0] = axis[0]; cone[1] = axis[1]; cone[2] = axis[2]; cone[3] = sqrtf(fmaxf(1.0f - cmin * cmin, 0.f)) / cmin; cone[4] = 1.0f / cmin;
     }
-    float hn[3] = {0, 0, 1};
-    if (hs >= 0) m_vec(hn, vs + VS_W * hs, hnl);
-    float r, g, bl, dz;
-    if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
-    else {
-      const float* col = vs + VS_W * hs + 16; float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
-      r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best;
+    __syncthreads();
+    for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
+      // bounding sphere against the tile cone (conservative): perpendicular distance <= depth * tan(a) + r / cos(a)
+      const float* o = vs + VS_W * s;
+      float vc[3]; v_sub(vc, o + 9, camRp + 9);
+      float t_ax = v_dot(vc, cone), perp2 = fmaxf(v_dot(vc, vc) - t_ax * t_ax, 0.f), r = o[20];
+      float lim = fmaxf(t_ax, 0.f) * cone[3] + r * cone[4];
+      if (t_ax > -r && perp2 <= lim * lim) atomicOr(&cand[s >> 5], 1u << (s & 31));
     }
-    rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
-    // segmentation mask (camera.py:89-90): unique id of the visible body, -1 where the ray hits nothing
-    if (seg != nullptr) seg[(size_t)e * npx + px] = hs < 0 ? -1.0f : (float)sc.vis_i[DG_VIS_I_W * hs + 3];
+    __syncthreads();
+    for (int k = threadIdx.x; k < DG_TILE * DG_TILE; k += blockDim.x) {
+      int i = tx * DG_TILE + (k % DG_TILE), j = ty * DG_TILE + (k / DG_TILE);
+      if (i >= width || j >= height) continue;
+      int px = j * width + i;
+      const float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f};
+      const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
+      float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
+      for (int wd = 0; wd < ncw; wd++) {
+        unsigned bits = cand[wd];
+        while (bits) {
+          int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1;
+          const float* o = vs + VS_W * s;
+          float dl[3]; m_vec(dl, o + 21, dc);
+          const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
+          if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
+          float tt, nn[3];
+          if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
+        }
+      }
+      float hn[3] = {0, 0, 1};
+      if (hs >= 0) m_vec(hn, vs + VS_W * hs, hnl);
+      float r, g, bl, dz;
+      if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
+      else {
+        const float* col = vs + VS_W * hs + 16; float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
+        r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best;
+      }
+      rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
+      // segmentation mask (camera.py:89-90): unique id of the visible body, -1 where the ray hits nothing
+      if (seg != nullptr) seg[(size_t)e * npx + px] = hs < 0 ? -1.0f : (float)sc.vis_i[DG_VIS_I_W * hs + 3];
+    }
   }
 }
 
@@ -402,8 +422,10 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   int tiles_x = (ci[1] + DG_TILE - 1) / DG_TILE, tiles_y = (ci[2] + DG_TILE - 1) / DG_TILE;
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)(d.nv + 31) / 32 + 4) * sizeof(float);
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
+  // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
+  int groups = std::max(1, std::min(tiles_x * tiles_y, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
   w->launches++;
-  dg_render_kernel<<<w->n_envs * tiles_x * tiles_y, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y);
+  dg_render_kernel<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
   CK(w, cudaGetLastError());
   return DG_OK;
 }

@@ -1,2 +1,2 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/pytest_gpu13.log; cat gpurun_out/pytest_gpu13.log
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+python -m pytest tests -m gpu -x -q -k "camera or golden or example" 2>&1 | tail -3
+python tools/render_probe.py from_the_readme 4096 2>&1 | grep -v Warn; python tools/render_probe.py basic_env 4096 2>&1 | grep -v Warn
