@@ -965,6 +965,213 @@ DG_FN void phase_pgs_unit(const Env& C, int ln, int nt, int it0, int it1) {
 }
 DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_contact_sweep(C); }
 
+// ------------------------------------------------------------------ row-space team solver ----------------------
+// Environments with contacts are solved by the WHOLE team in row space: y_r = J_r dv is carried for every unit and
+// contact row, A[r][s] = J_s M^-1 J_r^T is built once per sub-step by all lanes, and one Gauss-Seidel update of row r
+// is  d = clamp(rhs_r - y_r dinv_r),  y_s += A[r][s] d  with the rows s dealt round-robin to the lanes (row r lives
+// in lane r % nt, register r / nt).  Row order, clamps and friction bounds are those of the dv-space sweeps
+// (pgs_body_full / pgs_contact_sweep): unit rows (direction alternating with the iteration), normal rows, friction rows
+// bounded by mu x (normal impulse after this sweep's normal rows).  Rows that couple two dynamic bodies need no special
+// case: their A entries simply have two body terms.
+// Setup scatters every row's J and M^-1 J^T into DENSE vectors over the generalized coordinates of all dynamic bodies
+// (the layout of W_DV), so that building A and folding the impulses back into dv are plain dense products.
+// home of A: shared memory (compact stride) when it fits the per-environment budget, else the cold workspace
+DG_FN float* rs_amat(const Env& C, int R, int Rp, int* stride) {
+  if (R > 0 && R * Rp + RS_KMAX * SC.team <= SC.rs_ashared) { *stride = Rp; return WSH(C, SC.X_RSAS); }   // (slack: a row is read to a full register block)
+  *stride = SC.rs_cap; return WSG(C, SC.X_RSA);
+}
+// row records + dense vectors, lane per row; WH_RS_R = 0 sends the environment to the dv-space sweeps (no contact,
+// one-lane team, too many rows or coordinates)
+DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW], GV = sc.GV;
+  int nu = 0;
+  for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
+  const int R = nu + ncr;
+  const bool use = sc.solver == 1 && nt >= 2 && ncr > 0 && R <= sc.rs_cap;
+  if (ln == 0) { hdr[WH_RS_R] = use ? R : 0; hdr[WH_RS_NU] = nu; }
+  if (!use) return;
+  float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);
+  int r = 0;
+  for (int di = 0; di < sc.ndyn; di++) {
+    const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[di]; const int n = WSI(C)[sc.W_UCNT + di];
+    for (int j = 0; j < n; j++, r++) {
+      if (r % nt != ln) continue;
+      const float* u = WSH(C, sc.X_UROW) + UR_W * (bp[BP_UROW] + j);
+      int col = float_as_int(u[UR_COL]); float sg = 1.f; if (col < 0) { col = -1 - col; sg = -1.f; }
+      float* Jd = RSV + (size_t)r * 2 * GV; float* Md = Jd + GV;
+      for (int i = 0; i < 2 * GV; i += 4) st4(Jd + i, 0.f, 0.f, 0.f, 0.f);
+      const int go = bp[BP_GVOFF], gs = bp[BP_GS]; const float* Mc = WSH(C, sc.W_MINV) + bp[BP_MINVOFF] + col * gs;
+      Jd[go + col] = sg;
+      for (int i = 0; i < gs; i++) Md[go + i] = sg * Mc[i];
+      float* rc = REC + RR_W * r;
+      st4(rc, u[UR_RHS], u[UR_DINV], u[UR_LO], u[UR_HI]); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float((di << 16) | j));
+    }
+  }
+  for (int rr = 0; rr < ncr; rr++) {
+    const int r2 = nu + rr;
+    if (r2 % nt != ln) continue;
+    const float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr; const float* J = row + CR_HDR; const float* M = J + sc.GP;
+    const int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
+    float* Jd = RSV + (size_t)r2 * 2 * GV; float* Md = Jd + GV;
+    for (int i = 0; i < 2 * GV; i += 4) st4(Jd + i, 0.f, 0.f, 0.f, 0.f);
+    int off = 0;
+    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[i]; Md[go + i] += M[i]; } off = g; }
+    if (dib >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } }
+    float* rc = REC + RR_W * r2;
+    st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], 0.f, int_as_float(RS_CONTACT | rr));
+  }
+}
+// A[r * stride + s] = J_s M^-1 J_r^T for r < R, s < R; zero for the padding s in [R, roundup(R, nt))
+DG_FN void phase_rs_build(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  const int R = WSI(C)[sc.W_HDR + WH_RS_R], Rp = (R + nt - 1) / nt * nt, GV = sc.GV; int cap;
+  const float* RSV = WSG(C, sc.X_RSV); float* A = rs_amat(C, R, Rp, &cap);
+  for (int r = 0; r < R; r++) {
+    const float* Md = RSV + (size_t)r * 2 * GV + GV;
+    for (int s2 = ln; s2 < Rp; s2 += nt) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (s2 < R) {
+        const float* Jd = RSV + (size_t)s2 * 2 * GV;
+        for (int c = 0; c < GV; c += 4) { const F4 jv = ld4(Jd + c), mv = ld4(Md + c); a0 = fmaf(jv.x, mv.x, a0); a1 = fmaf(jv.y, mv.y, a1); a2 = fmaf(jv.z, mv.z, a2); a3 = fmaf(jv.w, mv.w, a3); }
+      }
+      A[r * cap + s2] = (a0 + a1) + (a2 + a3);
+    }
+  }
+}
+// dv of every body from the accumulated impulses:  dv = sum_rows (M^-1 J^T)_row x applied_row ; motor / limit impulses back
+// into their row records (phase_integrate reports them)
+DG_FN void phase_rs_finish(const Env& C, int ln, int nt) {
+  const DevScene& sc = SC;
+  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], GV = sc.GV;
+  const float* RSV = WSG(C, sc.X_RSV); const float* REC = WSG(C, sc.X_RSREC); float* dv = WSH(C, sc.W_DV);
+  for (int i = ln; i < GV; i += nt) {
+    float sum = 0.f;
+    for (int r = 0; r < R; r++) sum = fmaf(RSV[(size_t)r * 2 * GV + GV + i], REC[RR_W * r + RR_APPLIED], sum);
+    dv[i] = sum;
+  }
+  for (int r = ln; r < nu; r += nt) {
+    const int v = float_as_int(REC[RR_W * r + RR_ID]); const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[(v >> 16) & 0x3fff];
+    (WSH(C, sc.X_UROW) + UR_W * (bp[BP_UROW] + (v & 0xffff)))[UR_APPLIED] = REC[RR_W * r + RR_APPLIED];
+  }
+}
+#if defined(__CUDA_ARCH__) && defined(DG_STEP_T)
+// The sweeps.  Called with the REMAPPED thread layout: the NT lanes of a team are consecutive threads of one warp
+// (l = lane in team), every thread of the warp takes part in every shuffle, and every loop bound is warp-uniform
+// (maxima / minima over the teams of the warp); a team is masked off outside its own row ranges.  One update is
+// branch-free: every lane evaluates the clamp of ITS row (k, l), the owner's result is picked by the shuffle.
+template <int K, int NT>
+__device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsigned wmask, const int R, const int nu, const int nc) {
+  const DevScene& sc = SC;
+  const int tbase = (threadIdx.x & 31) & ~(NT - 1); int cap;
+  float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + NT - 1) / NT * NT, &cap) + l; float* capp = WSH(C, sc.W_CAPP);
+  float rhs[K], dinv[K], lo[K], hi[K], ap[K], y[K], mu[K]; int par[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    rhs[k] = 0.f; dinv[k] = 0.f; lo[k] = 0.f; hi[k] = 0.f; ap[k] = 0.f; y[k] = 0.f; mu[k] = 0.f; par[k] = -1;
+    const int r = k * NT + l;
+    if (r < R) { const F4 r0 = ld4(REC + RR_W * r), r1 = ld4(REC + RR_W * r + 4); rhs[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
+  }
+  const int nn = nu + nc, big = 1 << 28, rlast = R > 0 ? R - 1 : 0;
+  const int nu_max = __reduce_max_sync(wmask, nu), nn_max = __reduce_max_sync(wmask, nn), R_max = __reduce_max_sync(wmask, R);
+  const int nu_min = __reduce_min_sync(wmask, R > 0 ? nu : big), nn_min = __reduce_min_sync(wmask, R > 0 ? nn : big);
+  // one Gauss-Seidel update of row r = k NT + j.  Rows outside [first, last) of this team get d = 0; their A row is
+  // read from a clamped (written) row, so the product is an exact zero.  Columns beyond the team's own padding only
+  // feed y slots that belong to no row.
+#define DG_RS_UPDATE(k, j, r, first, last, normal)                                                             \
+  {                                                                                                            \
+    const float* Ar_ = A + min((r), rlast) * cap;                                                              \
+    float a_[K];                                                                                               \
+    _Pragma("unroll") for (int kk = 0; kk < K; kk++) a_[kk] = Ar_[kk * NT];                                    \
+    const float new_ = fminf(fmaxf(ap[k] + fmaf(-y[k], dinv[k], rhs[k]), lo[k]), hi[k]);                       \
+    const bool valid_ = (r) >= (first) && (r) < (last);                                                        \
+    float d_ = __shfl_sync(wmask, new_ - ap[k], tbase + (j));                                                  \
+    d_ = valid_ ? d_ : 0.f;                                                                                    \
+    if (valid_ && l == (j)) { ap[k] = new_; if (normal) capp[(r) - nu] = new_; }                               \
+    _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(a_[kk], d_, y[kk]);                          \
+  }
+  for (int it = 0; it < sc.iters; it++) {
+    if (it & 1) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (k * NT >= nu_max) break;
+        _Pragma("unroll 1") for (int j = 0; j < NT; j++) { const int r = k * NT + j; if (r >= nu_max) break; DG_RS_UPDATE(k, j, r, 0, nu, false) }
+      }
+    } else {
+#pragma unroll
+      for (int k = K - 1; k >= 0; k--) {
+        if (k * NT >= nu_max) continue;
+        _Pragma("unroll 1") for (int j = NT - 1; j >= 0; j--) { const int r = k * NT + j; if (r >= nu_max) continue; DG_RS_UPDATE(k, j, r, 0, nu, false) }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (k * NT >= nn_max) break;
+      if ((k + 1) * NT <= nu_min) continue;
+      _Pragma("unroll 1") for (int j = 0; j < NT; j++) { const int r = k * NT + j; if (r >= nn_max) break; if (r < nu_min) continue; DG_RS_UPDATE(k, j, r, nu, nn, true) }
+    }
+    __syncwarp(wmask);
+#pragma unroll
+    for (int k = 0; k < K; k++) if (par[k] >= 0) { hi[k] = mu[k] * capp[par[k]]; lo[k] = -hi[k]; }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (k * NT >= R_max) break;
+      if ((k + 1) * NT <= nn_min) continue;
+      _Pragma("unroll 1") for (int j = 0; j < NT; j++) { const int r = k * NT + j; if (r >= R_max) break; if (r < nn_min) continue; DG_RS_UPDATE(k, j, r, nn, R, false) }
+    }
+  }
+#undef DG_RS_UPDATE
+#pragma unroll
+  for (int k = 0; k < K; k++) { const int r = k * NT + l; if (r < R) REC[RR_W * r + RR_APPLIED] = ap[k]; }
+}
+// remaps the block's threads (thread t -> lane t % NT of the block's environment t / NT) and runs the sweeps
+template <int NT>
+__device__ __forceinline__ void rs_solve_block(const Env& C) {
+  if constexpr (NT >= 2) {
+  const DevScene& sc = SC;
+  const int E = blockDim.x / NT, ei = threadIdx.x % E, e2 = threadIdx.x / NT, l2 = threadIdx.x % NT;
+  Env C2 = C;
+  C2.ws = C.ws + (long)(e2 - ei) * sc.w_total; C2.wg = C.wg + (long)(e2 - ei) * sc.g_total;
+  const unsigned in_warp = blockDim.x - (threadIdx.x & ~31u);          // threads of this warp that exist
+  const unsigned wmask = in_warp >= 32u ? 0xffffffffu : (1u << in_warp) - 1u;
+  const int* hdr = WSI(C2) + sc.W_HDR;
+  const int R = hdr[WH_RS_R], nu = hdr[WH_RS_NU], nc = (R - nu) / 3;
+  const int R_max = __reduce_max_sync(wmask, R);
+  if (R_max > 0) {
+    const int kneed = (R_max + NT - 1) / NT;
+    if (kneed <= 2) rs_solve_team<2, NT>(C2, l2, wmask, R, nu, nc);
+    else if (kneed <= 4) rs_solve_team<4, NT>(C2, l2, wmask, R, nu, nc);
+    else rs_solve_team<RS_KMAX, NT>(C2, l2, wmask, R, nu, nc);
+  }
+  }
+}
+#elif defined(__CUDA_ARCH__)
+template <int NT> __device__ __forceinline__ void rs_solve_block(const Env&) {}
+#else
+// one-lane form of the same sweeps for the CPU emulation (tests/emul): identical row order and arithmetic
+DG_FN void rs_solve_serial(const Env& C, int nt) {
+  const DevScene& sc = SC;
+  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], nn = nu + (R - nu) / 3; int cap;
+  float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + nt - 1) / nt * nt, &cap); float* capp = WSH(C, sc.W_CAPP);
+  float lo[RS_KMAX * 32], hi[RS_KMAX * 32], ap[RS_KMAX * 32], y[RS_KMAX * 32];
+  for (int r = 0; r < R; r++) { lo[r] = REC[RR_W * r + RR_LO]; hi[r] = REC[RR_W * r + RR_HI]; ap[r] = 0.f; y[r] = 0.f; }
+  auto update = [&](int r, bool normal) {
+    const float* rc = REC + RR_W * r;
+    const float nw = fminf(fmaxf(ap[r] + fmaf(-y[r], rc[RR_DINV], rc[RR_RHS]), lo[r]), hi[r]), d = nw - ap[r];
+    ap[r] = nw;
+    if (normal) capp[r - nu] = nw;
+    for (int s2 = 0; s2 < R; s2++) y[s2] = fmaf(A[r * cap + s2], d, y[s2]);
+  };
+  for (int it = 0; it < sc.iters; it++) {
+    if (it & 1) for (int r = 0; r < nu; r++) update(r, false); else for (int r = nu - 1; r >= 0; r--) update(r, false);
+    for (int r = nu; r < nn; r++) update(r, true);
+    for (int r = nn; r < R; r++) { hi[r] = REC[RR_W * r + RR_MU] * capp[float_as_int(REC[RR_W * r + RR_PAR])]; lo[r] = -hi[r]; }
+    for (int r = nn; r < R; r++) update(r, false);
+  }
+  for (int r = 0; r < R; r++) REC[RR_W * r + RR_APPLIED] = ap[r];
+}
+#endif
+
 // ------------------------------------------------------------------ integration --------------------------------
 DG_FN void integrate_base_quat(float* q, const float* om, float h) {
   float ang = v_len(om), ax[3];
@@ -1438,12 +1645,29 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
       DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
     } else {
       DG_PHASE(phase_contact_rows(C, ln, nt, h));
-      // environments in which no row couples two dynamic bodies: every body solves on its own, all sweeps at once
-      DG_PHASE(if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
-      if (block_any(HDRV(WH_COUPLED) != 0, nt)) {   // the others sweep in lock-step
+#if defined(__CUDA_ARCH__)
+      if (!C.active && ln == 0) WSI(C)[sc.W_HDR + WH_RS_R] = 0;   // slots without an environment never wrote their header
+#endif
+      DG_PHASE(phase_rs_setup(C, ln, nt));
+      // environments with contacts: the whole team solves in row space (A is built here, swept below); contact-free ones
+      // keep the register-resident per-body sweeps.  (WH_RS_R == 0 with contacts: dv-space sweeps, solver == 0 / too many rows)
+      DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_build(C, ln, nt);
+               else if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
+      if (sc.solver == 1 && nt > 1) {
+#if defined(__CUDA_ARCH__)
+#if defined(DG_STEP_T)
+        rs_solve_block<DG_STEP_T>(C);
+#endif
+        __syncthreads();
+#else
+        DG_PHASE(if (ln == 0 && HDRV(WH_RS_R) > 0) rs_solve_serial(C, nt));
+#endif
+        DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_finish(C, ln, nt));
+      }
+      if (block_any(HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0, nt)) {   // dv-space, coupled bodies: lock-step sweeps
         for (int it = 0; it < sc.iters; it++) {
-          DG_PHASE(if (HDRV(WH_COUPLED) != 0) phase_pgs_unit(C, ln, nt, it, it + 1));
-          DG_PHASE(if (HDRV(WH_COUPLED) != 0) phase_pgs_contact(C, ln, nt));
+          DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_unit(C, ln, nt, it, it + 1));
+          DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_contact(C, ln, nt));
         }
       }
     }

@@ -56,6 +56,35 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   }
 }
 
+// Build layout: this file is compiled once per team size with -DDG_STEP_T=<T> (that object holds only dg_step_kernel<T>
+// and its two host wrappers) and once without (everything else); diy_gym_b200/build.py runs the compilations in
+// parallel and links the objects into one library.
+struct StepLaunch { int grid, block; size_t smem; cudaStream_t stream; };
+template <int T> static cudaError_t step_configure_t(int block_threads, size_t smem, size_t smem_cap, int* occ) {
+  // the attribute is per function, not per world: always allow the device maximum so that worlds of different sizes coexist
+  cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
+  if (e != cudaSuccess) return e;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, dg_step_kernel<T>, block_threads, smem);
+}
+template <int T> static cudaError_t step_launch_t(const DevScene& sc, const LaunchArgs& a, const StepLaunch& l) {
+  dg_step_kernel<T><<<l.grid, l.block, l.smem, l.stream>>>(sc, a);
+  return cudaGetLastError();
+}
+#define DG_DECLARE_STEP(T)                                                                              \
+  cudaError_t dg_step_configure_##T(int block_threads, size_t smem, size_t smem_cap, int* occ);          \
+  cudaError_t dg_step_launch_##T(const DevScene& sc, const LaunchArgs& a, const StepLaunch& l);
+#define DG_DEFINE_STEP(T)                                                                               \
+  cudaError_t dg_step_configure_##T(int block_threads, size_t smem, size_t smem_cap, int* occ) { return step_configure_t<T>(block_threads, smem, smem_cap, occ); } \
+  cudaError_t dg_step_launch_##T(const DevScene& sc, const LaunchArgs& a, const StepLaunch& l) { return step_launch_t<T>(sc, a, l); }
+DG_DECLARE_STEP(1) DG_DECLARE_STEP(2) DG_DECLARE_STEP(4) DG_DECLARE_STEP(8) DG_DECLARE_STEP(16) DG_DECLARE_STEP(32)
+#if defined(DG_STEP_T)
+#define DG_DEFINE_STEP_X(T) DG_DEFINE_STEP(T)
+DG_DEFINE_STEP_X(DG_STEP_T)
+#elif !defined(DG_SPLIT_BUILD)
+#error "compile with -DDG_STEP_T=<team size> (one object per team size) or -DDG_SPLIT_BUILD (everything else): see diy_gym_b200/build.py"
+#endif
+
+#if !defined(DG_STEP_T)
 __global__ void dg_init_kernel(const __grid_constant__ DevScene sc, float* state, float* param, int n_envs) {
   size_t total_s = (size_t)n_envs * sc.S, total_p = (size_t)n_envs * sc.P;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -243,31 +272,30 @@ static std::string g_create_err;
 
 #define CK(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (w)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DG_E_CUDA; } } while (0)
 
-template <int T> static cudaError_t configure(DgWorld* w) {
-  // the attribute is per function, not per world: always allow the device maximum so that worlds of different sizes coexist
-  cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap);
-  if (e != cudaSuccess) return e;
-  int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dg_step_kernel<T>, w->block_threads, w->smem);
+static cudaError_t configure_any(DgWorld* w) {
+  int occ = 0; cudaError_t e;
+  switch (w->team) {
+    case 1: e = dg_step_configure_1(w->block_threads, w->smem, w->smem_cap, &occ); break;
+    case 2: e = dg_step_configure_2(w->block_threads, w->smem, w->smem_cap, &occ); break;
+    case 4: e = dg_step_configure_4(w->block_threads, w->smem, w->smem_cap, &occ); break;
+    case 8: e = dg_step_configure_8(w->block_threads, w->smem, w->smem_cap, &occ); break;
+    case 16: e = dg_step_configure_16(w->block_threads, w->smem, w->smem_cap, &occ); break;
+    default: e = dg_step_configure_32(w->block_threads, w->smem, w->smem_cap, &occ); break;
+  }
   if (e != cudaSuccess) return e;
   if (occ < 1) occ = 1;
-  int teams_per_block = w->block_threads / T;
+  int teams_per_block = w->block_threads / w->team;
   int need = (w->n_envs + teams_per_block - 1) / teams_per_block;
   w->grid = std::max(1, std::min(need, w->sm_count * occ));
   return cudaSuccess;
 }
-template <int T> static cudaError_t launch(DgWorld* w, const LaunchArgs& a, cudaStream_t s) {
-  dg_step_kernel<T><<<w->grid, w->block_threads, w->smem, s>>>(w->dev, a);
-  return cudaGetLastError();
-}
-static cudaError_t configure_any(DgWorld* w) {
-  switch (w->team) { case 1: return configure<1>(w); case 2: return configure<2>(w); case 4: return configure<4>(w); case 8: return configure<8>(w);
-                     case 16: return configure<16>(w); default: return configure<32>(w); }
-}
 static cudaError_t launch_any(DgWorld* w, const LaunchArgs& a, cudaStream_t s) {
   w->launches++;
-  switch (w->team) { case 1: return launch<1>(w, a, s); case 2: return launch<2>(w, a, s); case 4: return launch<4>(w, a, s); case 8: return launch<8>(w, a, s);
-                     case 16: return launch<16>(w, a, s); default: return launch<32>(w, a, s); }
+  const StepLaunch l{w->grid, w->block_threads, w->smem, s};
+  switch (w->team) {
+    case 1: return dg_step_launch_1(w->dev, a, l); case 2: return dg_step_launch_2(w->dev, a, l); case 4: return dg_step_launch_4(w->dev, a, l);
+    case 8: return dg_step_launch_8(w->dev, a, l); case 16: return dg_step_launch_16(w->dev, a, l); default: return dg_step_launch_32(w->dev, a, l);
+  }
 }
 
 extern "C" {
@@ -322,7 +350,30 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   const char* env_mode = getenv("DG_WS_MODE");
   int ws_mode = env_mode ? atoi(env_mode) : 3;
   if (ws_mode != 2 && ws_mode != 3) ws_mode = 3;
-  if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+  // Row-space solver matrix A in shared memory: scenes with floating bodies rest on contacts in every environment, so
+  // their environments get the shared memory that the register-bound residency (~256 threads per SM) leaves unused
+  // anyway; other scenes (arms that rarely touch) keep A in the cold workspace.  DG_RS_ASHARED=<floats> overrides.
+  int rs_ashared = 0;
+  for (int pass = 0; pass < 2; pass++) {
+    if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode, rs_ashared)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+    if (pass == 1) break;
+    const DevScene& d0 = w->hs.dev;
+    bool floating = false;
+    for (int b = 0; b < d0.nb; b++) floating |= d0.body_i[DG_BODY_I_W * b] == 2;
+    const char* env_a = getenv("DG_RS_ASHARED");
+    if (env_a) rs_ashared = atoi(env_a);
+    else if (floating && d0.npair > 0 && d0.rs_cap > 0) {
+      const int by_regs = std::max(1, 256 / team), needed = (n_envs + w->sm_count - 1) / w->sm_count;
+      const int resident = std::max(epb, (std::min(by_regs, needed) + epb - 1) / epb * epb), blocks = resident / epb;
+      const long tables0 = (long)(((DG_LINK_I_W * d0.nl + 3) & ~3) + (DG_LINK_F_W + 16) * d0.nl + 4) * 4;
+      const long avail = ((long)prop.sharedMemPerMultiprocessor - blocks * (1024 + tables0)) / resident - (long)d0.w_total * 4;
+      rs_ashared = (int)std::max(0L, avail / 4);
+      if (rs_ashared < 64) rs_ashared = 0;
+    }
+    if (rs_ashared <= 0) break;
+  }
+  // DG_SOLVER=0: contact environments fall back to the per-body dv-space sweeps (kept for A/B measurements)
+  if (const char* env_solver = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(env_solver) != 0;
   {
     size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
     const int nl_ = w->hs.dev.nl;
@@ -368,6 +419,7 @@ int64_t dg_query(const DgWorld* w, int key) {
     case DG_Q_N_REW: return d.n_rew; case DG_Q_N_TERM: return d.n_term; case DG_Q_N_ENVS: return w->n_envs; case DG_Q_TEAM: return w->team;
     case DG_Q_BLOCK_THREADS: return w->block_threads; case DG_Q_GRID_BLOCKS: return w->grid; case DG_Q_SMEM_BYTES: return (int64_t)w->smem;
     case DG_Q_WS_FLOATS: return d.w_total; case DG_Q_N_CAMERAS: return d.ncam; case DG_Q_LAUNCHES: return w->launches;
+    case DG_Q_RS_ASHARED: return d.rs_ashared; case DG_Q_SOLVER: return d.solver;
   }
   return -1;
 }
@@ -483,3 +535,6 @@ extern "C" int dg_measure_fp32_peak(int device, double* tflops_out) {
   *tflops_out = best;
   return DG_OK;
 }
+#else
+}  // namespace dg
+#endif  // !DG_STEP_T

@@ -19,7 +19,11 @@ enum { D_Q = 0, D_QD, D_APPLIED, D_TAU, D_COUNT };
 // body plan columns
 enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_NRS, BP_AOFF, BP_GS, BP_W };
 // workspace header ints
-enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_COUNT = 8 };
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_COUNT = 8 };
+// row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j
+enum { RS_CONTACT = 0x40000000, RS_KMAX = 8, RS_GVMAX = 128 };
+// row record of the row-space solver
+enum { RR_RHS = 0, RR_DINV, RR_LO, RR_HI, RR_MU, RR_PAR, RR_APPLIED, RR_ID, RR_W = 8 };
 // row record strides
 enum { UR_RHS = 0, UR_DINV, UR_LO, UR_HI, UR_APPLIED, UR_COL, UR_MOTOR, UR_W = 8 };
 enum { CR_RHS = 0, CR_DINV, CR_LO, CR_HI, CR_APPLIED, CR_MU, CR_DA, CR_DB, CR_PARENT, CR_HDR = 12 };
@@ -58,7 +62,11 @@ struct DevScene {
   // region X, articulated-body phase
   int X_ABA, X_LNK, X_I0T;
   // region X, constraint phase
-  int X_SHW, X_CON, X_SURV, X_CTMP, X_UROW, X_CROW, X_MSCR, X_AMAT, X_IK;
+  int X_SHW, X_CON, X_SURV, X_CTMP, X_UROW, X_CROW, X_MSCR, X_AMAT, X_IK, X_RSA, X_RSAS, X_RSV, X_RSREC;
+  int GV;           // generalized coordinates of all dynamic bodies, each padded to a multiple of 4 (the layout of W_DV)
+  int rs_ashared;   // floats of shared memory per environment for the row-space matrix A (environments whose A is larger keep it in the cold workspace)
+  int rs_cap;   // row capacity of the row-space team solver (0: unavailable, team of one lane)
+  int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
 };
 
@@ -106,7 +114,7 @@ struct HostScene {
     d.shape_wb = fb + off.shape_wb; d.vis_wb = fb + off.vis_wb; d.link_x = fb + off.link_x;
   }
 
-  bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team, int ws_mode = 0) {
+  bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team, int ws_mode = 0, int rs_ashared = 0) {
     if (ni < 2 + 3 * DG_NSECTIONS || ibuf[0] != (int32_t)DG_SCENE_MAGIC || ibuf[1] != DG_NSECTIONS) { error = "bad scene magic / section count"; return false; }
     auto sec_off = [&](int s) { return (size_t)ibuf[2 + 3 * s + 1]; };
     auto sec_len = [&](int s) { return (size_t)ibuf[2 + 3 * s + 2]; };
@@ -310,6 +318,15 @@ struct HostScene {
     phase_take(&d.X_CROW, RC_CONTACT, 1, d.crow_stride * 3 * d.maxc);
     phase_take(&d.X_CTMP, RC_SCRATCH, 1, d.ctmp_stride * team);
     phase_take(&d.X_MSCR, RC_SCRATCH, 1, d.mscr_stride * team);
+    // row-space team solver: row table + dense A = J M^-1 J^T over all unit and contact rows of the environment
+    d.GV = gv;
+    d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min((2 * d.nd + 3 * d.maxc + team - 1) / team * team, RS_KMAX * team) : 0;
+    d.solver = 1;
+    d.rs_ashared = std::max(0, std::min(rs_ashared, d.rs_cap * d.rs_cap)) & ~3;
+    phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);
+    phase_take(&d.X_RSAS, RC_SOLVE, 1, d.rs_ashared);
+    phase_take(&d.X_RSV, RC_SCRATCH, 1, d.rs_cap * 2 * gv);      // per row: J and M^-1 J^T, dense over all bodies' coordinates
+    phase_take(&d.X_RSREC, RC_SCRATCH, 1, d.rs_cap * RR_W);
     phase_take(&d.X_IK, RC_SCRATCH, 2, n_ik ? d.ik_stride * std::min(team, n_ik) : 0);
     for (auto& pd : pend) *pd.field = enc_rc(pd.rc, pd.cold, fix[pd.cold] + pd.rel);
     d.w_total = fix[0] + std::max(ph[0][0], std::max(ph[0][1], ph[0][2]));

@@ -35,7 +35,9 @@ enum {
   DG_Q_SMEM_BYTES = 10,  /* dynamic shared memory per block of the step kernel      */
   DG_Q_WS_FLOATS = 11,   /* workspace floats per environment                        */
   DG_Q_N_CAMERAS = 12,
-  DG_Q_LAUNCHES = 13     /* kernels launched by this world since creation           */
+  DG_Q_LAUNCHES = 13,    /* kernels launched by this world since creation           */
+  DG_Q_RS_ASHARED = 14,  /* floats of shared memory per environment holding the contact solver's row-space matrix */
+  DG_Q_SOLVER = 15       /* 1: row-space team solver for contact environments, 0: per-body sweeps */
 };
 
 /* Buffers of one world, all DEVICE pointers, row-major with the environment as the leading dimension. */

@@ -3,6 +3,7 @@
 // emulated by running every phase lane after lane (the barrier semantics of the GPU schedule).  Never shipped,
 // never used by the product path: diy_gym_b200 raises when libdiygym_b200.so / a CUDA device is missing.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -22,8 +23,10 @@ struct EmulWorld {
 extern "C" {
 EmulWorld* dge_create(const int32_t* ibuf, int ni, const double* fbuf, int nf, int n_envs, int team, int ws_mode) {
   EmulWorld* w = new EmulWorld();
-  if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode)) { delete w; return nullptr; }
+  const char* ea = getenv("DG_RS_ASHARED");
+  if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode, ea ? atoi(ea) : 0)) { delete w; return nullptr; }
   w->n_envs = n_envs; w->team = team;
+  if (const char* es = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(es) != 0;
   const DevScene& d = w->hs.dev;
   w->state.resize((size_t)n_envs * d.S + 1); w->param.resize((size_t)n_envs * d.P + 1); w->ws.assign((size_t)d.w_total + 16, 0.f); w->wg.assign((size_t)d.g_total + 16, 0.f);
   for (int e = 0; e < n_envs; e++) {
