@@ -37,6 +37,7 @@ CONFIGS = {
     'from_the_readme': ('examples/from_the_readme/from_the_readme.yaml', 4096),
     'drone_pilot': ('examples/drone_pilot/drone_pilot.yaml', 4096),
     'basic_env': ('examples/basic_env/basic_env.yaml', 4096),
+    'ur_admittance': ('examples/ur_admittance/ur_admittance.yaml', 8192),
 }
 METRIC = 'aggregate env-steps/sec'
 UNIT = 'env-steps/s'

@@ -351,12 +351,61 @@ class _Unsupported(Addon):
         raise NotImplementedError('%s: %s' % (config.get('addon'), self.reason))
 
 
-class AdmittanceController(_Unsupported):
-    reason = 'needs Jacobian + inverse-dynamics kernels ("next" row, SURVEY 8f-2)'
+class AdmittanceController(_OpAddon):
+    """`controllers/admittance_controller.py`: joint torques = F . J_lin + T . J_ang (Jacobian of the admittance point on the
+    end effector) + gravity compensation + p_gain (target_pose - q) - d_gain qd; the default joint motors are switched off."""
+    def __init__(self, parent, config):
+        super().__init__(parent, config)
+        b = parent.body
+        self.end_frame = parent.get_frame_id(config.get('end_effector'))
+        self.offset_admittance_point = list(config.get('offset_admittance_point', [0., 0., 0.]))
+        self.kp = config.get('p_gain', 0.001)
+        self.kd = config.get('d_gain', 0.01)
+        self.joint_ids = [i for i in b.movable_joints() if i <= self.end_frame]
+        n = len(self.joint_ids)
+        # p.calculateInverseDynamics(uid, joint_positions, ...) (admittance_controller.py:47) takes one position per DoF of
+        # the body: a joint list that leaves DoF out makes pybullet raise, and so does a floating base
+        if n != b.n_dofs or b.kind != 1:
+            raise ValueError('admittance_controller: the joints up to end_effector must span every DoF of a fixed-base model '
+                             '(%d of %d)' % (n, b.n_dofs))
+        self.rest_position = list(config.get('rest_position', [0] * n))
+        self.target_pose = list(config.get('target_pose', self.rest_position))
+        if len(self.target_pose) != n:
+            raise ValueError('admittance_controller: target_pose needs %d entries' % n)
+        self.action_space = spaces.Dict({'force': spaces.Box(-5, 5, shape=(3, ), dtype='float32'),
+                                         'torque': spaces.Box(-1., 1., shape=(3, ), dtype='float32')})
+
+    def compile(self, sb):
+        b, n = self.parent.body, len(self.joint_ids)
+        dofs = [b.global_dof(i) for i in self.joint_ids]
+        self.op = sb.add_op('ADMITTANCE', [b.index, b.link_start + self.end_frame, n] + dofs,
+                            [self.kp, self.kd] + self.offset_admittance_point + self.target_pose, n_act=6)
+        m = min(n, len(self.rest_position))   # zip() truncation of admittance_controller.py:36-38
+        sb.add_op('JOINT_RESET', [m] + dofs[:m], self.rest_position[:m])
+        sb.motors_off += dofs                  # VELOCITY_CONTROL with forces = 0 (admittance_controller.py:34)
+
+    def update(self, action):
+        self._put(self._act[:, 0:3], action['force'])
+        self._put(self._act[:, 3:6], action['torque'])
 
 
-class ForceTorqueSensor(_Unsupported):
-    reason = 'needs the joint reaction wrench ("next" row, SURVEY 8f-3)'
+class ForceTorqueSensor(_OpAddon):
+    """`sensors/force_torque_sensor.py`: joint reaction force / torque of the joint `frame` (p.getJointState(...)[2] after
+    enableJointForceTorqueSensor), expressed in the child link's COM frame, from the forward-dynamics pass of the last sub-step."""
+    def __init__(self, parent, config):
+        super().__init__(parent, config)
+        self.frame_id = parent.get_frame_id(config.get('frame')) if 'frame' in config else -1
+        if self.frame_id < 0:   # p.getJointState(uid, -1) raises in the reference as well (force_torque_sensor.py:22)
+            raise ValueError('force_torque_sensor: `frame` must name a joint of the model')
+        box = lambda: spaces.Box(-10, 10, shape=(3, ), dtype='float32')
+        self.observation_space = spaces.Dict({'force': box(), 'torque': box()})
+
+    def compile(self, sb):
+        sb.need_jreact = True
+        self.op = sb.add_op('FT_SENSOR', [self.parent.body.link_start + self.frame_id], n_obs=6)
+
+    def observe(self):
+        return {'force': self._obs[:, 0:3], 'torque': self._obs[:, 3:6]}
 
 
 class VisualRandomizer(_Unsupported):

@@ -35,7 +35,7 @@ HDR_I_FIELDS = [
     'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn',
     # state offsets
     'S_BPOS', 'S_BQUAT', 'S_BVEL', 'S_BOMEGA', 'S_Q', 'S_QD', 'S_MKP', 'S_MKD', 'S_MTPOS', 'S_MTVEL', 'S_MMAXF',
-    'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_STEP', 'S_RESETS',
+    'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_JREACT', 'S_STEP', 'S_RESETS',
     'S_ADDON',
     # param offsets
     'P_MASS', 'P_INERTIA', 'P_LINDAMP', 'P_ANGDAMP', 'P_JDAMP', 'P_FRICTION', 'P_INITPOSE', 'P_RESTQ',
@@ -54,7 +54,7 @@ SHAPE_TYPES = {'sphere': 0, 'box': 1, 'capsule': 2, 'cylinder': 3}
 JOINT_TYPES = {'fixed': 0, 'revolute': 1, 'continuous': 1, 'prismatic': 2}
 
 OP = dict(JOINT_CTRL=1, EXT_FORCE=2, IK_CTRL=3, JOINT_SENSOR=4, OBJECT_SENSOR=5, REACH_TARGET=6, ELECTRICITY=7,
-          STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13)
+          STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13, ADMITTANCE=14, FT_SENSOR=15)
 
 DEFAULT_LATERAL_FRICTION = 0.5
 DEFAULT_DAMPING = 0.04  # multibody linear/angular velocity damping (App. A.2)
@@ -126,6 +126,8 @@ class SceneBuilder:
         self.ops = []  # (type, iargs, fargs, n_act, n_obs, n_rew, n_term)
         self.cams = []
         self.addon_state = 0
+        self.need_jreact = False   # a force_torque_sensor asks for the joint reaction wrenches (6 floats per link in the state row)
+        self.motors_off = []   # global dof indices whose default velocity motor is switched off (admittance_controller.py:34)
         self.finalized = None
 
     def add_body(self, name, desc, xyz=(0, 0, 0), quat=(0, 0, 0, 1), scale=1.0, fixed_base=False, mass=None, color=None):
@@ -290,7 +292,8 @@ class SceneBuilder:
         for name, n in [('S_BPOS', 3 * nb), ('S_BQUAT', 4 * nb), ('S_BVEL', 3 * nb), ('S_BOMEGA', 3 * nb), ('S_Q', nd),
                         ('S_QD', nd), ('S_MKP', nd), ('S_MKD', nd), ('S_MTPOS', nd), ('S_MTVEL', nd), ('S_MMAXF', nd),
                         ('S_MAPPLIED', nd), ('S_JTORQUE', nd), ('S_EXTF', 3 * nframes), ('S_EXTT', 3 * nframes),
-                        ('S_LPOS', 3 * nl), ('S_LQUAT', 4 * nl), ('S_LVEL', 3 * nl), ('S_LOMEGA', 3 * nl), ('S_STEP', 1),
+                        ('S_LPOS', 3 * nl), ('S_LQUAT', 4 * nl), ('S_LVEL', 3 * nl), ('S_LOMEGA', 3 * nl),
+                        ('S_JREACT', 6 * nl if self.need_jreact else 0), ('S_STEP', 1),
                         ('S_RESETS', 1), ('S_ADDON', self.addon_state)]:
             lay[name] = off
             off += n
@@ -319,6 +322,8 @@ class SceneBuilder:
         dt = self.timestep
         state[lay['S_MKD']:lay['S_MKD'] + nd] = 1.0
         state[lay['S_MMAXF']:lay['S_MMAXF'] + nd] = 1.0 / dt
+        for d in self.motors_off:
+            state[lay['S_MMAXF'] + d] = 0.0
         state[lay['S_LQUAT'] + 3:lay['S_LQUAT'] + 4 * nl:4] = 1.0
 
         # ---- ops ----------------------------------------------------------------------------------

@@ -319,8 +319,21 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   }
 }
 
+// joint reaction wrench of every link of body b: f = I^A a + p^A in the link's COM frame, [force(3), torque(3)], from the
+// forward-dynamics pass that just ran (what p.getJointState(...)[2] reports, force_torque_sensor.py:21-23)
+DG_FN void joint_reactions(const Env& C, int b) {
+  const DevScene& sc = SC;
+  const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int l0 = bi[1], nlb = bi[2], s0 = gc(sc.body_plan)[BP_W * b + BP_SLOT];
+  for (int k = 0; k < nlb; k++) {
+    float X[48], n[3], f[3];
+    ldn<48>(ABA(s0 + 1 + k), X);
+    ia_mul(X + AB_A, X + AB_B, X + AB_C, X + AB_ACC, X + AB_ACC + 3, n, f);
+    float* o = ST(S_JREACT) + 6 * (l0 + k);
+    for (int i = 0; i < 3; i++) { o[i] = X[AB_PA + 3 + i] + f[i]; o[3 + i] = X[AB_PA + i] + n[i]; }
+  }
+}
 DG_FN void phase_dynamics(const Env& C, int ln, int nt, float h) {
-  for (int di = ln; di < SC.ndyn; di += nt) { int b = gc(SC.dyn_body)[di]; fk_vel_body<true>(C, b); aba_body(C, b, h); }
+  for (int di = ln; di < SC.ndyn; di += nt) { int b = gc(SC.dyn_body)[di]; fk_vel_body<true>(C, b); aba_body(C, b, h); if (SC.need_react) joint_reactions(C, b); }
 }
 
 // One column of M^-1 of body b: response of the generalized velocity to a unit generalized impulse at coordinate col.
@@ -988,7 +1001,7 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   int nu = 0;
   for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
   const int R = nu + ncr;
-  const bool use = sc.solver == 1 && nt >= 2 && ncr > 0 && R <= sc.rs_cap;
+  const bool use = sc.solver == 1 && nt >= 2 && ncr > 0 && R <= sc.rs_cap && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min);
   if (ln == 0) { hdr[WH_RS_R] = use ? R : 0; hdr[WH_RS_NU] = nu; }
   if (!use) return;
   float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);
@@ -1478,6 +1491,7 @@ DG_FN void ik_solve_any(const Env& C, int b, int ee_gl, const float* tpos_w, con
 }
 
 // ------------------------------------------------------------------ add-on ops ---------------------------------
+DG_FN void admittance_update(const Env& C, const int* ia, const float* fa, const float* a);
 // controllers: update() bodies of /root/reference/diy_gym/addons/controllers/
 DG_FN void phase_actions(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
@@ -1501,6 +1515,8 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
       if (ia[1] == 0) { v_cpy(F, a); v_sub(rel, fa, pos); }
       else { float R[9]; q_to_mat(R, quat); m_vec(F, R, a); m_vec(rel, R, fa); }
       v_add(ST(S_EXTF) + 3 * f, ST(S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(ST(S_EXTT) + 3 * f, ST(S_EXTT) + 3 * f, t);
+    } else if (op[0] == OP_ADMITTANCE && ln == 0) {          // admittance_controller.py:36-55
+      admittance_update(C, ia, fa, a);
     } else if (op[0] == OP_IK_CTRL) {                         // ik_controller.py:51-80
       int mine = (ik_seen++ % nt) == ln;
       if (!mine) continue;
@@ -1519,6 +1535,44 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
     }
   }
   if (ln == 0) ST(S_STEP)[0] += 1.f;
+}
+// world-space axis and origin of the joint that carries link gl, from the cached link poses (same construction as point_jacobian)
+DG_FN void joint_axis_world(const Env& C, int gl, float* aw, float* ow) {
+  const float* lf = shc(C.link_f) + DG_LINK_F_W * gl;
+  float R[9], dw[3];
+  q_to_mat(R, ST(S_LQUAT) + 4 * gl); m_vec(aw, R, lf + 10); m_vec(dw, R, lf + 7); v_sub(ow, ST(S_LPOS) + 3 * gl, dw);
+}
+// admittance_controller.py:36-55: tau = F . J_lin + T . J_ang (Jacobian of the admittance point, p.calculateJacobian)
+//   + gravity torques (p.calculateInverseDynamics at zero velocity / acceleration) + kp (target - q) - kd qd, applied as
+// joint torques (TORQUE_CONTROL).  Fixed-base bodies; the joint list spans every DoF of the body (the host layer checks).
+DG_FN void admittance_update(const Env& C, const int* ia, const float* fa, const float* a) {
+  const DevScene& sc = SC;
+  const int b = ia[0], ee = ia[1], n = ia[2]; const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int l0 = bi[1], nlb = bi[2];
+  const float kp = fa[0], kd = fa[1]; const float* target = fa + 5;
+  for (int i = 0; i < n; i++) { const int d = ia[3 + i]; ST(S_JTORQUE)[d] += (target[i] - ST(S_Q)[d]) * kp - kd * ST(S_QD)[d]; }
+  float Re[9], P[3], t[3];
+  q_to_mat(Re, ST(S_LQUAT) + 4 * ee); m_vec(t, Re, fa + 2); v_add(P, ST(S_LPOS) + 3 * ee, t);   // admittance point (offset in the link's COM frame)
+  for (int gl = ee; gl >= 0; gl = shc(C.link_i)[DG_LINK_I_W * gl + 1]) {
+    const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+    if (li[3] < 0) continue;
+    float aw[3], ow[3], rel[3], c[3];
+    joint_axis_world(C, gl, aw, ow);
+    if (li[2] == 1) { v_sub(rel, P, ow); v_cross(c, aw, rel); ST(S_JTORQUE)[li[3]] += v_dot(a, c) + v_dot(a + 3, aw); }
+    else ST(S_JTORQUE)[li[3]] += v_dot(a, aw);
+  }
+  for (int k = 0; k < nlb; k++) {   // G(q): every link's weight through the joints above it
+    const float m = PR(P_MASS)[sc.nb + l0 + k];
+    if (m == 0.f) continue;
+    const float* pk = ST(S_LPOS) + 3 * (l0 + k);
+    for (int gl = l0 + k; gl >= 0; gl = shc(C.link_i)[DG_LINK_I_W * gl + 1]) {
+      const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+      if (li[3] < 0) continue;
+      float aw[3], ow[3], rel[3], c[3];
+      joint_axis_world(C, gl, aw, ow);
+      if (li[2] == 1) { v_sub(rel, pk, ow); v_cross(c, aw, rel); } else v_cpy(c, aw);
+      ST(S_JTORQUE)[li[3]] -= m * v_dot(sc.g, c);
+    }
+  }
 }
 // sensors / rewards / terminals: observe(), reward(), is_terminal() bodies of diy_gym/addons/{sensors,rewards}/
 DG_FN void phase_observe(const Env& C, int ln, int nt) {
@@ -1543,6 +1597,8 @@ DG_FN void phase_observe(const Env& C, int ln, int nt) {
       if (flags & 2) for (int i = 0; i < 3; i++) o[j++] = v[i];
       if (flags & 1) { float e[3]; euler_from_q(e, q); for (int i = 0; i < 3; i++) o[j++] = e[i]; }
       if ((flags & 3) == 3) for (int i = 0; i < 3; i++) o[j++] = w[i];
+    } else if (op[0] == OP_FT_SENSOR) {                 // force_torque_sensor.py:21-23
+      for (int i = 0; i < 6; i++) o[i] = ST(S_JREACT)[6 * ia[0] + i];
     } else if (op[0] == OP_REACH_TARGET) {              // reach_target.py:21-36
       float sp[3], sq[4], tp[3], tq[4], d[3];
       frame_link_pose(C, ia[0], sp, sq); frame_link_pose(C, ia[1], tp, tq); v_sub(d, tp, sp);

@@ -350,30 +350,14 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   const char* env_mode = getenv("DG_WS_MODE");
   int ws_mode = env_mode ? atoi(env_mode) : 3;
   if (ws_mode != 2 && ws_mode != 3) ws_mode = 3;
-  // Row-space solver matrix A in shared memory: scenes with floating bodies rest on contacts in every environment, so
-  // their environments get the shared memory that the register-bound residency (~256 threads per SM) leaves unused
-  // anyway; other scenes (arms that rarely touch) keep A in the cold workspace.  DG_RS_ASHARED=<floats> overrides.
-  int rs_ashared = 0;
-  for (int pass = 0; pass < 2; pass++) {
-    if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode, rs_ashared)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
-    if (pass == 1) break;
-    const DevScene& d0 = w->hs.dev;
-    bool floating = false;
-    for (int b = 0; b < d0.nb; b++) floating |= d0.body_i[DG_BODY_I_W * b] == 2;
-    const char* env_a = getenv("DG_RS_ASHARED");
-    if (env_a) rs_ashared = atoi(env_a);
-    else if (floating && d0.npair > 0 && d0.rs_cap > 0) {
-      const int by_regs = std::max(1, 256 / team), needed = (n_envs + w->sm_count - 1) / w->sm_count;
-      const int resident = std::max(epb, (std::min(by_regs, needed) + epb - 1) / epb * epb), blocks = resident / epb;
-      const long tables0 = (long)(((DG_LINK_I_W * d0.nl + 3) & ~3) + (DG_LINK_F_W + 16) * d0.nl + 4) * 4;
-      const long avail = ((long)prop.sharedMemPerMultiprocessor - blocks * (1024 + tables0)) / resident - (long)d0.w_total * 4;
-      rs_ashared = (int)std::max(0L, avail / 4);
-      if (rs_ashared < 64) rs_ashared = 0;
-    }
-    if (rs_ashared <= 0) break;
-  }
-  // DG_SOLVER=0: contact environments fall back to the per-body dv-space sweeps (kept for A/B measurements)
+  // The row-space solver keeps its matrix A in the cold workspace: giving it shared memory was measured slower on every
+  // example scene (the larger carve-out shrinks L1, profiles/r1_solver_ab.log); DG_RS_ASHARED=<floats per environment> overrides.
+  const char* env_a = getenv("DG_RS_ASHARED");
+  if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode, env_a ? atoi(env_a) : 0)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+  // DG_SOLVER=0: coupled environments fall back to lock-step dv-space sweeps; DG_RS_MIN=<rows>: uncoupled environments with
+  // at least that many contact rows are solved in row space too (both kept for A/B measurements)
   if (const char* env_solver = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(env_solver) != 0;
+  if (const char* env_min = getenv("DG_RS_MIN")) w->hs.dev.rs_min = atoi(env_min);
   {
     size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
     const int nl_ = w->hs.dev.nl;

@@ -66,6 +66,8 @@ struct DevScene {
   int GV;           // generalized coordinates of all dynamic bodies, each padded to a multiple of 4 (the layout of W_DV)
   int rs_ashared;   // floats of shared memory per environment for the row-space matrix A (environments whose A is larger keep it in the cold workspace)
   int rs_cap;   // row capacity of the row-space team solver (0: unavailable, team of one lane)
+  int need_react;   // a force / torque sensor op reads the joint reaction wrenches (state section S_JREACT)
+  int rs_min;   // contact rows an uncoupled environment needs before the team solves it in row space (fewer: per-body sweeps)
   int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
 };
@@ -256,6 +258,8 @@ struct HostScene {
     for (int k = 0; k < d.npair; k++) GP = std::max(GP, gdim_of_shape(pair_i[2 * k]) + gdim_of_shape(pair_i[2 * k + 1]));
     int n_ik = 0;
     for (int k = 0; k < d.nop; k++) n_ik += op_i[DG_OP_I_W * k] == OP_IK_CTRL;
+    d.need_react = 0;
+    for (int k = 0; k < d.nop; k++) d.need_react |= op_i[DG_OP_I_W * k] == OP_FT_SENSOR;
 
     auto put_vi = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); ints.push_back(0); return o; };
     auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };
@@ -321,7 +325,7 @@ struct HostScene {
     // row-space team solver: row table + dense A = J M^-1 J^T over all unit and contact rows of the environment
     d.GV = gv;
     d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min((2 * d.nd + 3 * d.maxc + team - 1) / team * team, RS_KMAX * team) : 0;
-    d.solver = 1;
+    d.solver = 1; d.rs_min = 1 << 20;   // measured (profiles/r1_rs_min_sweep.log): uncoupled environments are faster with the per-body sweeps
     d.rs_ashared = std::max(0, std::min(rs_ashared, d.rs_cap * d.rs_cap)) & ~3;
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);
     phase_take(&d.X_RSAS, RC_SOLVE, 1, d.rs_ashared);

@@ -118,7 +118,7 @@ typedef struct {
 } Row;
 
 typedef struct DgoWorld {
-  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters;
+  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react;
   int32_t* ibuf; double* fbuf;
   const int32_t *hi, *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
   const double *hf, *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *param_def, *state_def, *cam_f;
@@ -159,6 +159,8 @@ DgoWorld* dgo_create(const int32_t* ibuf, int ni, const double* fbuf, int nf) {
   W->ncam = HI(W, ncam); W->nop = HI(W, nop); W->nframes = HI(W, nframes); W->S = HI(W, S); W->P = HI(W, P);
   W->substeps = HI(W, substeps); W->iters = HI(W, iterations); W->maxc = HI(W, max_contacts); W->hot_start = HI(W, hot_start);
   W->ik_iters = HI(W, ik_iters);
+  W->need_react = 0;
+  for (int k = 0; k < W->nop; k++) W->need_react |= W->op_i[DG_OP_I_W * k] == OP_FT_SENSOR;
   int nf_ = W->nframes, nl = W->nl > 0 ? W->nl : 1;
 #define ALLOC(p, n) W->p = (double*)calloc((size_t)(n) > 0 ? (size_t)(n) : 1, sizeof(double))
   ALLOC(state, W->S); ALLOC(param, W->P); ALLOC(Rw, 9 * nf_); ALLOC(pw, 3 * nf_); ALLOC(E, 9 * nl); ALLOC(r, 3 * nl);
@@ -367,6 +369,14 @@ static void aba_body(DgoWorld* W, int b, const double* tau_damp) {
       W->qdd[li[3]] = qdd;
       v_madd(a, W->Sa + 3 * gl, qdd); v_madd(a + 3, W->Sl + 3 * gl, qdd);
     }
+  }
+  /* joint reaction wrenches (force_torque_sensor.py:21-23 reads p.getJointState(...)[2]): Bullet's multibody forward
+   * dynamics reports  I^A a + p^A  of the child link, in that link's frame, as [Fx Fy Fz Mx My Mz], from the last
+   * unconstrained pass - solver impulses are not included  [RECALLED-UNVERIFIED] */
+  if (W->need_react) for (int k = 0; k < nlb; k++) {
+    int gl = l0 + k, f = frame_of_link(W, gl); double n[3], fo[3]; double* o = ST(W, S_JREACT) + 6 * gl;
+    ia_mul(W->IAa + 9 * f, W->IAb + 9 * f, W->IAc + 9 * f, W->acc + 6 * f, W->acc + 6 * f + 3, n, fo);
+    for (int i = 0; i < 3; i++) { o[i] = W->pA[6 * f + 3 + i] + fo[i]; o[3 + i] = W->pA[6 * f + i] + n[i]; }
   }
 }
 /* out = M^-1 gen  for body b using the cached articulated quantities; gen/out are [tau_w(3), f_w(3), joint(nd_b)] */
@@ -869,6 +879,45 @@ static double urand(uint32_t seed, uint32_t env, uint32_t epoch, uint32_t stream
   uint32_t h = hash32(seed ^ hash32(env + 0x9e3779b9U * (epoch + 1)) ^ hash32(stream * 0x85ebca6bU + 0xc2b2ae35U));
   return (double)(h >> 8) * (1.0 / 16777216.0);
 }
+/* world-space axis and origin of the joint carrying link gl, from the cached link COM poses (getLinkState[0,1]) */
+static void joint_axis_world(const DgoWorld* W, int gl, double* aw, double* ow) {
+  const double* lf = W->link_f + DG_LINK_F_W * gl; double R[9], dw[3];
+  q_to_mat(R, ST(W, S_LQUAT) + 4 * gl); m_vec(aw, R, lf + 10); m_vec(dw, R, lf + 7); v_sub(ow, ST(W, S_LPOS) + 3 * gl, dw);
+}
+/* diy_gym/addons/controllers/admittance_controller.py:36-55.  Restates the three pybullet calls it makes:
+ *   p.calculateJacobian(uid, end_frame, offset, q, 0, 0)  -> translational / rotational Jacobian of the point `offset`
+ *       (given in the link's COM frame) in world axes, one column per DoF  [RECALLED-UNVERIFIED frame conventions];
+ *   p.calculateInverseDynamics(uid, q, 0, 0)              -> G(q), the generalized gravity forces of a fixed-base body;
+ *   p.setJointMotorControlArray(..., TORQUE_CONTROL, forces = F.J_lin + T.J_ang + G + kp (target - q) - kd qd). */
+static void admittance_update(DgoWorld* W, const int32_t* ia, const double* fa, const double* a) {
+  int b = ia[0], ee = ia[1], n = ia[2]; const int32_t* bi = W->body_i + DG_BODY_I_W * b; int l0 = bi[1], nlb = bi[2];
+  double kp = fa[0], kd = fa[1]; const double* target = fa + 5;
+  double g[3] = {HF(W, gx), HF(W, gy), HF(W, gz)};
+  for (int i = 0; i < n; i++) { int d = ia[3 + i]; ST(W, S_JTORQUE)[d] += (target[i] - ST(W, S_Q)[d]) * kp - kd * ST(W, S_QD)[d]; }
+  double Re[9], P[3], t[3];
+  q_to_mat(Re, ST(W, S_LQUAT) + 4 * ee); m_vec(t, Re, fa + 2); v_add(P, ST(W, S_LPOS) + 3 * ee, t);
+  for (int gl = ee; gl >= 0; gl = W->link_i[DG_LINK_I_W * gl + 1]) {
+    const int32_t* li = W->link_i + DG_LINK_I_W * gl;
+    if (li[3] < 0) continue;
+    double aw[3], ow[3], rel[3], c[3];
+    joint_axis_world(W, gl, aw, ow);
+    if (li[2] == 1) { v_sub(rel, P, ow); v_cross(c, aw, rel); ST(W, S_JTORQUE)[li[3]] += v_dot(a, c) + v_dot(a + 3, aw); }
+    else ST(W, S_JTORQUE)[li[3]] += v_dot(a, aw);
+  }
+  for (int k = 0; k < nlb; k++) {
+    double m = PR(W, P_MASS)[W->nb + l0 + k];
+    if (m == 0) continue;
+    const double* pk = ST(W, S_LPOS) + 3 * (l0 + k);
+    for (int gl = l0 + k; gl >= 0; gl = W->link_i[DG_LINK_I_W * gl + 1]) {
+      const int32_t* li = W->link_i + DG_LINK_I_W * gl;
+      if (li[3] < 0) continue;
+      double aw[3], ow[3], rel[3], c[3];
+      joint_axis_world(W, gl, aw, ow);
+      if (li[2] == 1) { v_sub(rel, pk, ow); v_cross(c, aw, rel); } else v_cpy(c, aw);
+      ST(W, S_JTORQUE)[li[3]] -= m * v_dot(g, c);
+    }
+  }
+}
 /* controllers: diy_gym/addons/controllers/ update() bodies */
 void dgo_apply_actions(DgoWorld* W, const double* act) {
   for (int k = 0; k < W->nop; k++) {
@@ -889,6 +938,8 @@ void dgo_apply_actions(DgoWorld* W, const double* act) {
       if (ia[1] == 0) { v_cpy(F, a); v_sub(rel, fa, pos); }
       else { double R[9]; q_to_mat(R, quat); m_vec(F, R, a); m_vec(rel, R, fa); }
       v_add(ST(W, S_EXTF) + 3 * f, ST(W, S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(ST(W, S_EXTT) + 3 * f, ST(W, S_EXTT) + 3 * f, t);
+    } else if (op[0] == OP_ADMITTANCE) {                /* admittance_controller.py:36-55 */
+      admittance_update(W, ia, fa, a);
     } else if (op[0] == OP_IK_CTRL) {                   /* ik_controller.py:51-80 */
       int b = ia[0], ee = ia[1], n = ia[2], use_orn = ia[3], ns = ia[4]; int ndb = W->body_i[DG_BODY_I_W * b + 4];
       double pos[3], quat[4], v[3], o[3], tq[4], out[64];
@@ -929,6 +980,8 @@ void dgo_observe(DgoWorld* W, double* obs, double* rew, uint8_t* term) {
       if (flags & 2) for (int i = 0; i < 3; i++) o[j++] = v[i];
       if (flags & 1) { double e[3]; euler_from_q(e, q); for (int i = 0; i < 3; i++) o[j++] = e[i]; }
       if ((flags & 3) == 3) for (int i = 0; i < 3; i++) o[j++] = w[i];
+    } else if (op[0] == OP_FT_SENSOR) {                 /* force_torque_sensor.py:21-23 */
+      for (int i = 0; i < 6; i++) o[i] = ST(W, S_JREACT)[6 * ia[0] + i];
     } else if (op[0] == OP_REACH_TARGET) {              /* reach_target.py:21-36 */
       double sp[3], sq[4], tp[3], tq[4], d[3];
       frame_link_pose(W, ia[0], sp, sq); frame_link_pose(W, ia[1], tp, tq); v_sub(d, tp, sp);

@@ -27,6 +27,7 @@ EmulWorld* dge_create(const int32_t* ibuf, int ni, const double* fbuf, int nf, i
   if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode, ea ? atoi(ea) : 0)) { delete w; return nullptr; }
   w->n_envs = n_envs; w->team = team;
   if (const char* es = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(es) != 0;
+  if (const char* em = getenv("DG_RS_MIN")) w->hs.dev.rs_min = atoi(em);
   const DevScene& d = w->hs.dev;
   w->state.resize((size_t)n_envs * d.S + 1); w->param.resize((size_t)n_envs * d.P + 1); w->ws.assign((size_t)d.w_total + 16, 0.f); w->wg.assign((size_t)d.g_total + 16, 0.f);
   for (int e = 0; e < n_envs; e++) {

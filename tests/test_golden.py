@@ -11,7 +11,7 @@ from diy_gym_b200 import DIYGym
 from oracle.oracle import OracleWorld
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-NAMES = ['ur_high_5', 'ur_high_5_randomised', 'from_the_readme', 'r2d2_maze', 'basic_env']
+NAMES = ['ur_high_5', 'ur_high_5_randomised', 'from_the_readme', 'r2d2_maze', 'basic_env', 'ur_admittance']
 # open-loop rollout of K = 12 steps: fp32 vs fp64 round-off grows a little along the rollout
 TOL = dict(rtol=2e-3, atol=2e-4)
 

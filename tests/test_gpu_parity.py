@@ -162,7 +162,7 @@ def _env(name, n, **kw):
 
 
 @pytest.mark.parametrize('name,scale', [('ur_high_5', 0.01), ('ur_high_5/ur_high_5_randomised', 0.01), ('from_the_readme', 0.01),
-                                        ('r2d2_maze', 10.0), ('basic_env', 10.0)])
+                                        ('r2d2_maze', 10.0), ('basic_env', 10.0), ('ur_admittance', 1.0)])
 def test_example_configs_reset_and_step_match_oracle(name, scale):
     n = 6
     env = _env(name, n, seed=77, env_id_offset=3)

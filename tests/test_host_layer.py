@@ -224,3 +224,46 @@ def test_custom_addon_can_be_defined_inline():
     env = DIYGym(cfg, num_envs=2, world_factory=factory())
     obs, rew, term, _ = env.step({})
     assert torch.equal(obs['ball']['c'], torch.full((2, 2), 0.25)) and torch.equal(rew, torch.ones(2))
+
+
+# ---- admittance_controller, force_torque_sensor ----------------------------------------------
+def test_admittance_controller_and_force_torque_sensor_trees():
+    """Same spaces as admittance_controller.py:26-28 / force_torque_sensor.py:16-19; the controller holds the arm against
+    gravity (zero wrench -> the tool barely moves) and a commanded force pushes the tool along it."""
+    env = make('ur_admittance', n=2)
+    ctl = env.action_space['ur5']['controller']
+    assert list(ctl.spaces) == ['force', 'torque']
+    assert np.allclose(ctl['force'].high, 5) and np.allclose(ctl['torque'].high, 1) and ctl['force'].shape == (3, )
+    ft = env.observation_space['ur5']['wrist_wrench']
+    assert list(ft.spaces) == ['force', 'torque'] and ft['force'].shape == (3, )
+    zero = {'ur5': {'controller': {'force': torch.zeros(2, 3), 'torque': torch.zeros(2, 3)}}}
+    obs0 = env.reset()
+    p0 = obs0['ur5']['tool_state']['position'].clone()
+    for _ in range(20):
+        obs, rew, term, _ = env.step(zero)
+    # (the hot-start step of reset() runs without the controller, as in the reference, so the arm starts with a small sag velocity)
+    assert (obs['ur5']['tool_state']['position'] - p0).abs().max() < 1e-2
+    w = obs['ur5']['wrist_wrench']
+    assert w['force'].shape == (2, 3) and 1.0 < w['force'][0].norm() < 50.0           # carries the wrist-3 link + tool
+    push = {'ur5': {'controller': {'force': torch.tensor([[5.0, 0, 0], [0, 0, 0]]), 'torque': torch.zeros(2, 3)}}}
+    for _ in range(40):
+        obs, rew, term, _ = env.step(push)
+    moved = obs['ur5']['tool_state']['position'] - p0
+    assert moved[0, 0] > 5e-3 and moved[0, 0] > 5 * abs(moved[1, 0]) and moved[1].abs().max() < 2e-2
+
+
+def test_admittance_controller_rejects_partial_chains_like_pybullet():
+    import yaml
+    cfg = {'ur5': {'model': 'ur5/ur5_robot.urdf', 'controller': {'addon': 'admittance_controller', 'end_effector': 'elbow_joint'}}}
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_tmp_admittance.yaml')
+    with open(path, 'w') as f:
+        yaml.safe_dump(cfg, f)
+    try:
+        with pytest.raises(ValueError):
+            make_path(path)
+    finally:
+        os.remove(path)
+
+
+def make_path(path, n=1):
+    return DIYGym(path, num_envs=n, world_factory=factory())

@@ -27,7 +27,7 @@ def action_batch(sc, rng, n, scale):
 
 
 @pytest.mark.parametrize('name,scale,team', [('ur_high_5', 0.01, 1), ('ur_high_5', 0.01, 8), ('ur_high_5/ur_high_5_randomised', 0.01, 4),
-                                             ('from_the_readme', 0.01, 4), ('r2d2_maze', 10.0, 4), ('basic_env', 10.0, 2)])
+                                             ('from_the_readme', 0.01, 4), ('r2d2_maze', 10.0, 4), ('basic_env', 10.0, 2), ('ur_admittance', 1.0, 4)])
 def test_reset_and_single_steps_match_oracle(name, scale, team):
     sc = scene_of(name)
     n = 3

@@ -252,3 +252,92 @@ def test_euler_quaternion_helpers_round_trip():
         Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
         Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
         assert np.allclose(quat_to_mat(q), Rz @ Ry @ Rx, atol=1e-12)
+
+
+def test_admittance_gravity_compensation_matches_independent_gravity_vector():
+    """admittance_controller.py:47 (p.calculateInverseDynamics(q, 0, 0)): with no commanded wrench and zero gains the op
+    writes exactly G(q) into the applied joint torques - checked against the numpy potential-energy gradient of
+    tests/helpers.py - and a motor-less, damping-less arm then stays where it is."""
+    from diy_gym_b200.assets import resolve_model
+    from diy_gym_b200.compiler.scene import SceneBuilder
+    sb = SceneBuilder()
+    b = sb.add_body('m', resolve_model('ur5/ur5_robot.urdf'))
+    nd = b.n_dofs
+    ee = b.joint_names().index('ee_fixed_joint')
+    dofs = [b.global_dof(i) for i in b.movable_joints()]
+    sb.add_op('ADMITTANCE', [b.index, b.link_start + ee, nd] + dofs, [0.0, 0.0, 0.0, 0.0, 0.05] + [0.0] * nd, n_act=6)
+    sb.motors_off += dofs
+    sc = sb.finalize()
+    w = OracleWorld(sc)
+    free_dynamics(w, sc)
+    q = np.array([0.3, -1.1, 1.4, -0.4, 0.7, 0.2])
+    w.s('S_Q', nd)[:] = q
+    w.refresh()
+    _, G, _ = mass_matrix_gravity_energy(sc, w, q)
+    w.apply_actions(np.zeros(6))
+    assert np.allclose(w.s('S_JTORQUE', nd), G, rtol=1e-10, atol=1e-10)
+    # a pure force along +x at the admittance point adds J_lin^T F: compare with a finite difference of the point position
+    w.s('S_JTORQUE', nd)[:] = 0
+    w.apply_actions(np.array([1.0, 0, 0, 0, 0, 0]))
+    tau_f = w.s('S_JTORQUE', nd) - G
+    lpos, lquat = w.s('S_LPOS', 3 * sc['nl']).copy().reshape(-1, 3), w.s('S_LQUAT', 4 * sc['nl']).copy().reshape(-1, 4)
+    from diy_gym_b200.compiler.mathutil import quat_rotate
+    p0 = lpos[ee] + quat_rotate(lquat[ee], np.array([0, 0, 0.05]))
+    for j in range(nd):
+        dq = q.copy(); dq[j] += 1e-6
+        w.s('S_Q', nd)[:] = dq
+        w.refresh()
+        lp, lq = w.s('S_LPOS', 3 * sc['nl']).reshape(-1, 3), w.s('S_LQUAT', 4 * sc['nl']).reshape(-1, 4)
+        p1 = lp[ee] + quat_rotate(lq[ee], np.array([0, 0, 0.05]))
+        assert abs((p1 - p0)[0] / 1e-6 - tau_f[j]) < 1e-5
+    # hold still under gravity compensation
+    w.s('S_Q', nd)[:] = q
+    w.s('S_QD', nd)[:] = 0
+    w.refresh()
+    for _ in range(50):
+        w.s('S_JTORQUE', nd)[:] = 0
+        w.apply_actions(np.zeros(6))
+        w.step_physics()
+    assert np.abs(w.s('S_Q', nd) - q).max() < 1e-6
+
+
+def test_joint_reaction_wrench_of_a_held_arm_carries_the_weight_above_it():
+    """force_torque_sensor.py:21-23: with gravity compensated (zero acceleration) the reaction force of joint j, rotated to the
+    world, is the weight of every link from j outwards, and its torque balances their moment about the link's COM."""
+    sb = SceneBuilder()
+    b = sb.add_body('m', resolve_model('ur5/ur5_robot.urdf'))
+    nd = b.n_dofs
+    names = b.joint_names()
+    ee = names.index('ee_fixed_joint')
+    dofs = [b.global_dof(i) for i in b.movable_joints()]
+    sb.add_op('ADMITTANCE', [b.index, b.link_start + ee, nd] + dofs, [0.0, 0.0, 0.0, 0.0, 0.0] + [0.0] * nd, n_act=6)
+    sb.motors_off += dofs
+    sb.need_jreact = True
+    j = names.index('wrist_1_joint')
+    sb.add_op('FT_SENSOR', [b.link_start + j], n_obs=6)
+    sc = sb.finalize()
+    w = OracleWorld(sc)
+    free_dynamics(w, sc)
+    q = np.array([0.3, -1.1, 1.4, -0.4, 0.7, 0.2])
+    w.s('S_Q', nd)[:] = q
+    w.refresh()
+    w.apply_actions(np.zeros(6))
+    w.step_physics()
+    obs = w.observe()[0]
+    nl = sc['nl']
+    mass = w.p('P_MASS', sc['nframes'])[sc['nb']:]
+    lpos, lquat = w.s('S_LPOS', 3 * nl).reshape(-1, 3), w.s('S_LQUAT', 4 * nl).reshape(-1, 4)
+    parent = [b.links[k + 1]['parent'] - 1 for k in range(nl)]
+    below = [k for k in range(nl) if any(a == j for a in _ancestors(k, parent))]
+    weight = sum(mass[k] for k in below) * 9.81
+    R = quat_to_mat(lquat[j])
+    f_world = R @ obs[0:3]
+    assert np.allclose(f_world, [0, 0, weight], atol=1e-6 * max(weight, 1))
+    moment = sum(np.cross(lpos[k] - lpos[j], [0, 0, -mass[k] * 9.81]) for k in below)
+    assert np.allclose(R @ obs[3:6], -moment, atol=1e-5)
+
+
+def _ancestors(k, parent):
+    while k >= 0:
+        yield k
+        k = parent[k]

@@ -28,7 +28,7 @@ def main():
     register_example_addons()
     out_dir = os.path.join(ROOT, 'tests', 'golden')
     os.makedirs(out_dir, exist_ok=True)
-    for name in ('ur_high_5', 'ur_high_5_randomised', 'from_the_readme', 'r2d2_maze', 'basic_env'):
+    for name in ('ur_high_5', 'ur_high_5_randomised', 'from_the_readme', 'r2d2_maze', 'basic_env', 'ur_admittance'):
         env = DIYGym(os.path.join(ROOT, CONFIGS[name][0]), num_envs=1, compile_only=True)
         sc = env.scene
         lo, hi = action_ranges(env)
