@@ -38,6 +38,7 @@ CONFIGS = {
     'drone_pilot': ('examples/drone_pilot/drone_pilot.yaml', 4096),
     'basic_env': ('examples/basic_env/basic_env.yaml', 4096),
     'ur_admittance': ('examples/ur_admittance/ur_admittance.yaml', 8192),
+    'ur_gripper': ('examples/ur_gripper/ur_gripper.yaml', 4096),
 }
 METRIC = 'aggregate env-steps/sec'
 UNIT = 'env-steps/s'

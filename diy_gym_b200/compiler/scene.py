@@ -25,14 +25,14 @@ from .urdf import inertia_from_rule
 SECTIONS = [
     ('HDR_I', 'i'), ('HDR_F', 'f'), ('BODY_I', 'i'), ('BODY_F', 'f'), ('LINK_I', 'i'), ('LINK_F', 'f'), ('SHAPE_I', 'i'),
     ('SHAPE_F', 'f'), ('PAIR_I', 'i'), ('VIS_I', 'i'), ('VIS_F', 'f'), ('OP_I', 'i'), ('OPARG_I', 'i'), ('OPARG_F', 'f'),
-    ('PARAM_DEFAULT', 'f'), ('STATE_DEFAULT', 'f'), ('CAM_I', 'i'), ('CAM_F', 'f'),
+    ('PARAM_DEFAULT', 'f'), ('STATE_DEFAULT', 'f'), ('CAM_I', 'i'), ('CAM_F', 'f'), ('CONS_I', 'i'), ('CONS_F', 'f'),
 ]
 SECTION_ID = {name: i for i, (name, _) in enumerate(SECTIONS)}
 MAGIC = 0x44594742  # 'DYGB'
 
 HDR_I_FIELDS = [
     'nb', 'nl', 'nd', 'ns', 'nv', 'npair', 'ncam', 'nop', 'n_act', 'n_obs', 'n_rew', 'n_term', 'substeps', 'iterations',
-    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn',
+    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn', 'ncons',
     # state offsets
     'S_BPOS', 'S_BQUAT', 'S_BVEL', 'S_BOMEGA', 'S_Q', 'S_QD', 'S_MKP', 'S_MKD', 'S_MTPOS', 'S_MTVEL', 'S_MMAXF',
     'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_JREACT', 'S_STEP', 'S_RESETS',
@@ -49,6 +49,7 @@ SHAPE_I_W, SHAPE_F_W = 4, 20
 VIS_I_W, VIS_F_W = 4, 24
 OP_I_W = 8
 CAM_I_W, CAM_F_W = 8, 16
+CONS_I_W, CONS_F_W = 4, 16
 
 SHAPE_TYPES = {'sphere': 0, 'box': 1, 'capsule': 2, 'cylinder': 3}
 JOINT_TYPES = {'fixed': 0, 'revolute': 1, 'continuous': 1, 'prismatic': 2}
@@ -113,6 +114,31 @@ class BodyInfo:
     def global_dof(self, joint_index):
         return self.dof_start + self.joint_dof[joint_index]
 
+    def rest_com_pose(self, link_index, joint_angles=None):
+        """World pose (Transform) of the COM frame of link `link_index` (-1 = base) at the joint coordinates
+        `joint_angles` ({joint index: value}, default all zero): what getBasePositionAndOrientation / getLinkState[0:2]
+        report after loadURDF + resetBasePositionAndOrientation + resetJointState."""
+        L, s = self.links, self.scale
+        q = joint_angles or {}
+        LI = [Transform.from_xyz_rpy(np.asarray(l['inertial_xyz']) * s, l['inertial_rpy']) for l in L]
+        Tb = Transform(self.base_pos, self.base_quat)
+        if link_index < 0:
+            return Tb
+        chain, k = [], link_index + 1
+        while k > 0:
+            chain.append(k)
+            k = L[k]['parent']
+        T = Tb * LI[0].inverse()                      # URDF frame of the base link
+        for k in reversed(chain):
+            j = L[k]['joint']
+            T = T * Transform.from_xyz_rpy(np.asarray(j['xyz']) * s, j['rpy'])
+            val = float(q.get(k - 1, 0.0))
+            if JOINT_TYPES[j['type']] != 0 and val != 0.0:
+                ax = np.asarray(j['axis'], float)
+                ax = ax / np.linalg.norm(ax)
+                T = T * (Transform((0, 0, 0), np.r_[ax * np.sin(val / 2), np.cos(val / 2)]) if JOINT_TYPES[j['type']] == 1 else Transform(ax * val))
+        return T * LI[link_index + 1]
+
     def frame(self, link_index):
         """Global frame id: base frames come first (one per body), then every link."""
         return self.frame_base if link_index < 0 else self.frame_link0 + link_index
@@ -125,6 +151,7 @@ class SceneBuilder:
         self.bodies = []
         self.ops = []  # (type, iargs, fargs, n_act, n_obs, n_rew, n_term)
         self.cams = []
+        self.constraints = []   # fixed constraints between a parent frame and a child frame (model.py:69-77)
         self.addon_state = 0
         self.need_jreact = False   # a force_torque_sensor asks for the joint reaction wrenches (6 floats per link in the state row)
         self.motors_off = []   # global dof indices whose default velocity motor is switched off (admittance_controller.py:34)
@@ -158,6 +185,16 @@ class SceneBuilder:
         off = self.addon_state
         self.addon_state += n
         return off
+
+    def add_fixed_constraint(self, body_a, link_a, body_b, link_b, pos_a, quat_a, pos_b=(0, 0, 0), quat_b=(0, 0, 0, 1), max_force=500.0):
+        """p.createConstraint(a, link_a, b, link_b, JOINT_FIXED, ..., pos_a, pos_b, quat_a, quat_b): the two joint frames, given
+        in the COM frames of the two links (-1 = base), are kept coincident (6 solver rows).  Frames are resolved in finalize()."""
+        for b in (body_a, body_b):
+            if b.kind == 0:
+                b.per_env_pose = True   # keeps a workspace slot for the frame (static bodies are otherwise baked into the tables)
+        self.constraints.append(dict(body_a=body_a, link_a=int(link_a), body_b=body_b, link_b=int(link_b), pos_a=list(pos_a),
+                                     quat_a=list(quat_a), pos_b=list(pos_b), quat_b=list(quat_b), max_force=float(max_force)))
+        return len(self.constraints) - 1
 
     def add_camera(self, frame, xyz, quat, width, height, fov, near, far):
         rec = dict(frame=int(frame), xyz=list(xyz), quat=list(quat), width=int(width), height=int(height), fov=float(fov),
@@ -343,6 +380,12 @@ class SceneBuilder:
             n_term += o['n_term']
 
         ncam = len(self.cams)
+        ncons = len(self.constraints)
+        cons_i = np.zeros((ncons, CONS_I_W), np.int32)
+        cons_f = np.zeros((ncons, CONS_F_W))
+        for k, c in enumerate(self.constraints):
+            cons_i[k, 0:2] = [c['body_a'].frame(c['link_a']), c['body_b'].frame(c['link_b'])]
+            cons_f[k, 0:3], cons_f[k, 3:7], cons_f[k, 7:10], cons_f[k, 10:14], cons_f[k, 14] = c['pos_a'], c['quat_a'], c['pos_b'], c['quat_b'], c['max_force']
         cam_i = np.zeros((ncam, CAM_I_W), np.int32)
         cam_f = np.zeros((ncam, CAM_F_W))
         for k, c in enumerate(self.cams):
@@ -358,7 +401,7 @@ class SceneBuilder:
             raise ValueError('max_contacts is limited to 21 (the solver tracks at most 63 contact rows per environment)')
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
-                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn)
+                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn, ncons=ncons)
         hdr.update(lay)
         hdr_i = np.array([hdr[k] for k in HDR_I_FIELDS], np.int32)
         hf = dict(dt=self.timestep, gx=self.gravity[0], gy=self.gravity[1], gz=self.gravity[2], erp=0.2, contact_erp=0.2,
@@ -368,7 +411,7 @@ class SceneBuilder:
 
         sec = dict(HDR_I=hdr_i, HDR_F=hdr_f, BODY_I=body_i, BODY_F=body_f, LINK_I=link_i, LINK_F=link_f, SHAPE_I=shape_i,
                    SHAPE_F=shape_f, PAIR_I=pair_i, VIS_I=vis_i, VIS_F=vis_f, OP_I=op_i, OPARG_I=np.array(oparg_i, np.int32),
-                   OPARG_F=np.array(oparg_f, float), PARAM_DEFAULT=param, STATE_DEFAULT=state, CAM_I=cam_i, CAM_F=cam_f)
+                   OPARG_F=np.array(oparg_f, float), PARAM_DEFAULT=param, STATE_DEFAULT=state, CAM_I=cam_i, CAM_F=cam_f, CONS_I=cons_i, CONS_F=cons_f)
         self.finalized = Scene(sec, hdr, hf, self)
         return self.finalized
 
@@ -415,7 +458,7 @@ def emit_c_header():
         out.append('#define HF_%s %d' % (name, i))
     for k, v in [('BODY_I_W', BODY_I_W), ('BODY_F_W', BODY_F_W), ('LINK_I_W', LINK_I_W), ('LINK_F_W', LINK_F_W),
                  ('SHAPE_I_W', SHAPE_I_W), ('SHAPE_F_W', SHAPE_F_W), ('VIS_I_W', VIS_I_W), ('VIS_F_W', VIS_F_W),
-                 ('OP_I_W', OP_I_W), ('CAM_I_W', CAM_I_W), ('CAM_F_W', CAM_F_W)]:
+                 ('OP_I_W', OP_I_W), ('CAM_I_W', CAM_I_W), ('CAM_F_W', CAM_F_W), ('CONS_I_W', CONS_I_W), ('CONS_F_W', CONS_F_W)]:
         out.append('#define DG_%s %d' % (k, v))
     for k, v in OP.items():
         out.append('#define OP_%s %d' % (k, v))

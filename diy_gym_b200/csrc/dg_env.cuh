@@ -101,7 +101,7 @@ DG_FN void phase_load(const Env& C, int ln, int nt) {
 DG_FN void joint_xform(const Env& C, int gl, float q, float* E, float* r) {
   const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl; const float* R0 = shc(C.link_x) + 16 * gl;
   float Rrel[9], tmp[3];
-  if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
+  if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q, C.sc->ncons > 0); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
   else if (li[2] == 2) { m_cpy(Rrel, R0); float dd[3] = {lf[7] + lf[10] * q, lf[8] + lf[11] * q, lf[9] + lf[12] * q}; m_vec(tmp, R0, dd); }
   else { m_cpy(Rrel, R0); m_vec(tmp, R0, lf + 7); }
   v_add(r, lf + 4, tmp);
@@ -672,6 +672,18 @@ DG_FN void point_jacobian(const Env& C, int f, const float* p, const float* dir,
     gl = li[1];
   }
 }
+// generalized force per unit TORQUE along dir on frame f (compact coordinates of its body)
+DG_FN void angular_jacobian(const Env& C, int f, const float* dir, float* J) {
+  const DevScene& sc = SC;
+  int b = body_of_frame(C, f); const int* bi = gc(sc.body_i) + DG_BODY_I_W * b; const int* bp = gc(sc.body_plan) + BP_W * b;
+  int g = bp[BP_GDIM], d0 = bi[3], s0 = bp[BP_SLOT], l0 = bi[1], jo = 0;
+  for (int i = 0; i < g; i++) J[i] = 0.f;
+  if (bi[0] == 2) { v_cpy(J, dir); jo = 6; }
+  for (int gl = f < sc.nb ? -1 : f - sc.nb; gl >= 0; gl = shc(C.link_i)[DG_LINK_I_W * gl + 1]) {
+    const int* li = shc(C.link_i) + DG_LINK_I_W * gl;
+    if (li[2] == 1) { float aw[3]; m_vec(aw, KIN(s0 + 1 + gl - l0), shc(C.link_f) + DG_LINK_F_W * gl + 10); J[jo + li[3] - d0] = v_dot(dir, aw); }
+  }
+}
 DG_FN void body_genvel(const Env& C, int b, float* gv) {
   const int* bi = gc(SC.body_i) + DG_BODY_I_W * b; int jo = 0;
   if (bi[0] == 2) { const float* bs = BST(gc(SC.body_plan)[BP_W * b + BP_DI]); v_cpy(gv, bs + 10); v_cpy(gv + 3, bs + 7); jo = 6; }
@@ -1000,8 +1012,8 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW], GV = sc.GV;
   int nu = 0;
   for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
-  const int R = nu + ncr;
-  const bool use = sc.solver == 1 && nt >= 2 && ncr > 0 && R <= sc.rs_cap && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min);
+  const int nk = 6 * sc.ncons, R = nu + nk + ncr;
+  const bool use = sc.solver == 1 && nt >= 2 && R <= sc.rs_cap && (nk > 0 || (ncr > 0 && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min)));
   if (ln == 0) { hdr[WH_RS_R] = use ? R : 0; hdr[WH_RS_NU] = nu; }
   if (!use) return;
   float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);
@@ -1021,8 +1033,43 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
       st4(rc, u[UR_RHS], u[UR_DINV], u[UR_LO], u[UR_HI]); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float((di << 16) | j));
     }
   }
+  // fixed constraints between models (model.py:69-77): three point rows along the world axes, three angular rows
+  for (int kr = 0; kr < nk; kr++) {
+    const int r2 = nu + kr;
+    if (r2 % nt != ln) continue;
+    const int kc = kr / 6, i = kr % 6;
+    const int* ci = gc(sc.cons_i) + DG_CONS_I_W * kc; const float* cf = gc(sc.cons_f) + DG_CONS_F_W * kc;
+    const int fa = ci[0], fb = ci[1], ba = body_of_frame(C, fa), bb = body_of_frame(C, fb);
+    const float *Ka = KIN(gc(sc.frame_slot)[fa]), *Kb = KIN(gc(sc.frame_slot)[fb]);
+    float Pa[3], Pb[3], t[3], err;
+    m_vec(t, Ka, cf); v_add(Pa, Ka + 9, t); m_vec(t, Kb, cf + 7); v_add(Pb, Kb + 9, t);
+    if (i < 3) err = Pa[i] - Pb[i];
+    else {
+      float qa[4], qb[4], qaw[4], qbw[4], dq[4];
+      mat_to_q(qa, Ka); mat_to_q(qb, Kb); q_mul(qaw, qa, cf + 3); q_mul(qbw, qb, cf + 10);
+      const float qbi[4] = {-qbw[0], -qbw[1], -qbw[2], qbw[3]};
+      q_mul(dq, qaw, qbi);
+      const float vn = v_len(dq); float ang = 2.f * atan2f(vn, dq[3]); if (ang > kPi) ang -= 2.f * kPi;
+      err = vn < 1e-12f ? 0.f : dq[i - 3] * ang / vn;
+    }
+    float e[3] = {0.f, 0.f, 0.f}, ne[3] = {0.f, 0.f, 0.f}; e[i % 3] = 1.f; ne[i % 3] = -1.f;
+    float* Jd = RSV + (size_t)r2 * 2 * GV; float* Md = Jd + GV;
+    for (int c = 0; c < 2 * GV; c += 4) st4(Jd + c, 0.f, 0.f, 0.f, 0.f);
+    float den = 0.f, rel = 0.f, gvl[RS_GVMAX + 8];
+    for (int side = 0; side < 2; side++) {
+      const int b = side ? bb : ba, f = side ? fb : fa; const int* bp = gc(sc.body_plan) + BP_W * b;
+      if (bp[BP_DI] < 0) continue;
+      const int go = bp[BP_GVOFF], g = bp[BP_GDIM], gs = bp[BP_GS]; const float* Minv = WSH(C, sc.W_MINV) + bp[BP_MINVOFF];
+      if (i < 3) point_jacobian(C, f, side ? Pb : Pa, side ? ne : e, Jd + go); else angular_jacobian(C, f, side ? ne : e, Jd + go);
+      body_genvel(C, b, gvl);
+      for (int c = 0; c < g; c++) { float sm = 0.f; for (int j = 0; j < g; j++) sm += Minv[j * gs + c] * Jd[go + j]; Md[go + c] = sm; den += Jd[go + c] * sm; rel += Jd[go + c] * gvl[c]; }
+    }
+    const float dinv = den > 1e-30f ? 1.0f / den : 0.f, lim = cf[14] * sc.dt, hsub = sc.dt / (float)sc.substeps;
+    float* rc = REC + RR_W * r2;
+    st4(rc, (-rel - err * sc.erp / hsub) * dinv, dinv, -lim, lim); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float(RS_CONTACT | 0xffff));
+  }
   for (int rr = 0; rr < ncr; rr++) {
-    const int r2 = nu + rr;
+    const int r2 = nu + nk + rr;
     if (r2 % nt != ln) continue;
     const float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr; const float* J = row + CR_HDR; const float* M = J + sc.GP;
     const int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
@@ -1085,7 +1132,7 @@ __device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsi
     const int r = k * NT + l;
     if (r < R) { const F4 r0 = ld4(REC + RR_W * r), r1 = ld4(REC + RR_W * r + 4); rhs[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
   }
-  const int nn = nu + nc, big = 1 << 28, rlast = R > 0 ? R - 1 : 0;
+  const int nk = 6 * sc.ncons, nn = nu + nk + nc, big = 1 << 28, rlast = R > 0 ? R - 1 : 0;
   const int nu_max = __reduce_max_sync(wmask, nu), nn_max = __reduce_max_sync(wmask, nn), R_max = __reduce_max_sync(wmask, R);
   const int nu_min = __reduce_min_sync(wmask, R > 0 ? nu : big), nn_min = __reduce_min_sync(wmask, R > 0 ? nn : big);
   // one Gauss-Seidel update of row r = k NT + j.  Rows outside [first, last) of this team get d = 0; their A row is
@@ -1100,7 +1147,7 @@ __device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsi
     const bool valid_ = (r) >= (first) && (r) < (last);                                                        \
     float d_ = __shfl_sync(wmask, new_ - ap[k], tbase + (j));                                                  \
     d_ = valid_ ? d_ : 0.f;                                                                                    \
-    if (valid_ && l == (j)) { ap[k] = new_; if (normal) capp[(r) - nu] = new_; }                               \
+    if (valid_ && l == (j)) { ap[k] = new_; if ((normal) && (r) >= nu + nk) capp[(r) - nu - nk] = new_; }      \
     _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(a_[kk], d_, y[kk]);                          \
   }
   for (int it = 0; it < sc.iters; it++) {
@@ -1148,7 +1195,7 @@ __device__ __forceinline__ void rs_solve_block(const Env& C) {
   const unsigned in_warp = blockDim.x - (threadIdx.x & ~31u);          // threads of this warp that exist
   const unsigned wmask = in_warp >= 32u ? 0xffffffffu : (1u << in_warp) - 1u;
   const int* hdr = WSI(C2) + sc.W_HDR;
-  const int R = hdr[WH_RS_R], nu = hdr[WH_RS_NU], nc = (R - nu) / 3;
+  const int R = hdr[WH_RS_R], nu = R > 0 ? hdr[WH_RS_NU] : 0, nc = R > 0 ? (R - nu - 6 * sc.ncons) / 3 : 0;   // (R == 0: slot without rows, its header may be stale)
   const int R_max = __reduce_max_sync(wmask, R);
   if (R_max > 0) {
     const int kneed = (R_max + NT - 1) / NT;
@@ -1164,7 +1211,7 @@ template <int NT> __device__ __forceinline__ void rs_solve_block(const Env&) {}
 // one-lane form of the same sweeps for the CPU emulation (tests/emul): identical row order and arithmetic
 DG_FN void rs_solve_serial(const Env& C, int nt) {
   const DevScene& sc = SC;
-  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], nn = nu + (R - nu) / 3; int cap;
+  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], nk = 6 * sc.ncons, nn = nu + nk + (R - nu - nk) / 3; int cap;
   float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + nt - 1) / nt * nt, &cap); float* capp = WSH(C, sc.W_CAPP);
   float lo[RS_KMAX * 32], hi[RS_KMAX * 32], ap[RS_KMAX * 32], y[RS_KMAX * 32];
   for (int r = 0; r < R; r++) { lo[r] = REC[RR_W * r + RR_LO]; hi[r] = REC[RR_W * r + RR_HI]; ap[r] = 0.f; y[r] = 0.f; }
@@ -1172,7 +1219,7 @@ DG_FN void rs_solve_serial(const Env& C, int nt) {
     const float* rc = REC + RR_W * r;
     const float nw = fminf(fmaxf(ap[r] + fmaf(-y[r], rc[RR_DINV], rc[RR_RHS]), lo[r]), hi[r]), d = nw - ap[r];
     ap[r] = nw;
-    if (normal) capp[r - nu] = nw;
+    if (normal && r >= nu + nk) capp[r - nu - nk] = nw;
     for (int s2 = 0; s2 < R; s2++) y[s2] = fmaf(A[r * cap + s2], d, y[s2]);
   };
   for (int it = 0; it < sc.iters; it++) {
@@ -1697,7 +1744,7 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
     }
     DG_PHASE(phase_minv(C, ln, nt));
     DG_PHASE(phase_unit_rows(C, ln, nt, h));
-    if (!block_any(HDRV(WH_NCROW) > 0, nt)) {
+    if (sc.ncons == 0 && !block_any(HDRV(WH_NCROW) > 0, nt)) {
       DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
     } else {
       DG_PHASE(phase_contact_rows(C, ln, nt, h));

@@ -326,6 +326,10 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
       int coords = 0;
       for (int b = 0; b < nb_; b++) if (bsec[DG_BODY_I_W * b] != 0) coords += (bsec[DG_BODY_I_W * b] == 2 ? 6 : 0) + bsec[DG_BODY_I_W * b + 4];
       team = coords > 12 ? 8 : 4;
+      // fixed constraints between models ride on the row-space team solver, whose row capacity grows with the team
+      const int32_t* hsec = ibuf + ibuf[2 + 3 * SEC_HDR_I + 1];
+      const int rows_max = 2 * hsec[HI_nd] + 3 * hsec[HI_max_contacts] + 6 * hsec[HI_ncons];
+      while (hsec[HI_ncons] > 0 && team < 32 && RS_KMAX * team < rows_max) team *= 2;
     }
     if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
   }

@@ -90,14 +90,17 @@ DG_HD void mat_to_q(float* q, const float* m) {
   q_norm(q);
 }
 // rotation about unit axis a by angle (Rodrigues), row-major
-DG_HD void axis_angle_mat(float* m, const float* a, float ang) {
+DG_HD void axis_angle_mat(float* m, const float* a, float ang, bool precise = false) {
   float s, c;
 #if defined(__CUDA_ARCH__)
   // SFU sine / cosine after reduction to [-pi, pi] (absolute error ~4e-7 there, the size of a few fp32 ulps of the
-  // rotation entries); the libm-accurate sincosf costs ~10x the instructions in the FK / IK inner loops
-  ang = fmaf(-6.283185307179586f, rintf(ang * 0.15915494309189535f), ang);
-  __sincosf(ang, &s, &c);
+  // rotation entries); the libm-accurate sincosf costs ~10x the instructions in the FK / IK inner loops.  `precise`:
+  // scenes with fixed constraints between models, whose error-reduction term multiplies a link-position error by
+  // erp / h ~ 100 / s - the SFU error then shows up as 1e-3 rad/s on light wrist joints (measured, ur_gripper).
+  if (precise) sincosf(ang, &s, &c);
+  else { ang = fmaf(-6.283185307179586f, rintf(ang * 0.15915494309189535f), ang); __sincosf(ang, &s, &c); }
 #else
+  (void)precise;
   sincosf(ang, &s, &c);
 #endif
   float t = 1 - c, x = a[0], y = a[1], z = a[2];

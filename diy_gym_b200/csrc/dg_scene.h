@@ -66,6 +66,8 @@ struct DevScene {
   int GV;           // generalized coordinates of all dynamic bodies, each padded to a multiple of 4 (the layout of W_DV)
   int rs_ashared;   // floats of shared memory per environment for the row-space matrix A (environments whose A is larger keep it in the cold workspace)
   int rs_cap;   // row capacity of the row-space team solver (0: unavailable, team of one lane)
+  int ncons;        // fixed constraints between bodies (6 solver rows each, row-space solver only)
+  const int* cons_i; const float* cons_f;
   int need_react;   // a force / torque sensor op reads the joint reaction wrenches (state section S_JREACT)
   int rs_min;   // contact rows an uncoupled environment needs before the team solves it in row space (fewer: per-body sweeps)
   int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
@@ -95,7 +97,7 @@ struct HostScene {
 
   // offsets of every table inside ints / floats (so a device copy can be re-pointed)
   struct Off { size_t body_i, link_i, shape_i, pair_i, vis_i, op_i, oparg_i, cam_i, dyn_body, body_plan, frame_slot, link_depth, shape_slot, grp_i, grp_pairs, loose_pairs;
-               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x, body_reach; } off;
+               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x, body_reach, cons_i, cons_f; } off;
 
   static void quat_to_mat(const double* q, double* m) {
     double x = q[0], y = q[1], z = q[2], w = q[3];
@@ -114,6 +116,7 @@ struct HostScene {
     d.body_f = fb + off.body_f; d.link_f = fb + off.link_f; d.shape_f = fb + off.shape_f; d.vis_f = fb + off.vis_f;
     d.oparg_f = fb + off.oparg_f; d.cam_f = fb + off.cam_f; d.param_def = fb + off.param_def; d.state_def = fb + off.state_def;
     d.shape_wb = fb + off.shape_wb; d.vis_wb = fb + off.vis_wb; d.link_x = fb + off.link_x;
+    d.cons_i = ib + off.cons_i; d.cons_f = fb + off.cons_f;
   }
 
   bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team, int ws_mode = 0, int rs_ashared = 0) {
@@ -147,6 +150,8 @@ struct HostScene {
     off.vis_i = put_i(SEC_VIS_I); off.op_i = put_i(SEC_OP_I); off.oparg_i = put_i(SEC_OPARG_I); off.cam_i = put_i(SEC_CAM_I);
     off.body_f = put_f(SEC_BODY_F); off.link_f = put_f(SEC_LINK_F); off.shape_f = put_f(SEC_SHAPE_F); off.vis_f = put_f(SEC_VIS_F);
     off.oparg_f = put_f(SEC_OPARG_F); off.cam_f = put_f(SEC_CAM_F); off.param_def = put_f(SEC_PARAM_DEFAULT); off.state_def = put_f(SEC_STATE_DEFAULT);
+    off.cons_i = put_i(SEC_CONS_I); off.cons_f = put_f(SEC_CONS_F);
+    d.ncons = hi[HI_ncons];
 
     const int32_t* body_i = ibuf + sec_off(SEC_BODY_I);
     const int32_t* link_i = ibuf + sec_off(SEC_LINK_I);
@@ -324,7 +329,13 @@ struct HostScene {
     phase_take(&d.X_MSCR, RC_SCRATCH, 1, d.mscr_stride * team);
     // row-space team solver: row table + dense A = J M^-1 J^T over all unit and contact rows of the environment
     d.GV = gv;
-    d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min((2 * d.nd + 3 * d.maxc + team - 1) / team * team, RS_KMAX * team) : 0;
+    const int rows_max = 2 * d.nd + 3 * d.maxc + 6 * d.ncons;
+    d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min((rows_max + team - 1) / team * team, RS_KMAX * team) : 0;
+    if (d.ncons > 0 && d.rs_cap < rows_max) {
+      error = "scenes with fixed constraints between models are solved by the row-space team solver: " + std::to_string(rows_max) +
+              " rows need a team of at least " + std::to_string((rows_max + RS_KMAX - 1) / RS_KMAX) + " lanes (and at most " + std::to_string((int)RS_GVMAX) + " generalized coordinates)";
+      return false;
+    }
     d.solver = 1; d.rs_min = 1 << 20;   // measured (profiles/r1_rs_min_sweep.log): uncoupled environments are faster with the per-body sweeps
     d.rs_ashared = std::max(0, std::min(rs_ashared, d.rs_cap * d.rs_cap)) & ~3;
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);

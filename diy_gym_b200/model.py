@@ -29,13 +29,24 @@ class Model(Receptor):
         scale = config.get('scale', 1.0)
         urdf = config.get('model')
         desc = resolve_model(urdf)   # raises ValueError('Could not find URDF: ...') like model.py:63
+        spawn_pos, spawn_quat = self.position, self.orientation
         if parent is not None:
-            # The reference welds child models to a parent frame with p.createConstraint(JOINT_FIXED)
-            # (model.py:69-77).  Inter-body fixed constraints are a "next" row, not built yet.
-            raise NotImplementedError('nested models (fixed constraint to a parent frame) are not supported yet: ' + self.name)
-        self.body = self.env.builder.add_body(self.name, desc, xyz=self.position, quat=self.orientation, scale=scale,
+            # model.py:69-77: the child is spawned at the COM pose of the parent frame (getLinkState[:2] / base pose) and welded
+            # to it with p.createConstraint(JOINT_FIXED): joint frame = (xyz, rpy) in the parent frame, identity in the child frame
+            parent_frame_id = parent.get_frame_id(config.get('parent_frame')) if 'parent_frame' in config else -1
+            # (the parent's controllers have already put its joints at their rest_position: add-ons are built before nested models)
+            q_rest = {}
+            for a in parent.addons.values():
+                if hasattr(a, 'joint_ids') and hasattr(a, 'rest_position'):
+                    q_rest.update(dict(zip(a.joint_ids, a.rest_position)))
+            T = parent.body.rest_com_pose(parent_frame_id, q_rest)
+            spawn_pos, spawn_quat = T.p, T.q
+        self.body = self.env.builder.add_body(self.name, desc, xyz=spawn_pos, quat=spawn_quat, scale=scale,
                                               fixed_base=use_fixed_base, mass=config.get('mass') if 'mass' in config else None,
                                               color=config.get('color') if 'color' in config else None)
+        if parent is not None:
+            child_frame_id = self.get_frame_id(config.get('child_frame')) if 'child_frame' in config else -1
+            self.env.builder.add_fixed_constraint(parent.body, parent_frame_id, self.body, child_frame_id, self.position, self.orientation)
         self.uid = self.body.index
         self.addons = OrderedDict(sorted({child.name: AddonFactory.build(child.get('addon'), self, child)
                                           for child in config.find_all('addon')}.items(), key=lambda t: t[0]))

@@ -118,7 +118,8 @@ typedef struct {
 } Row;
 
 typedef struct DgoWorld {
-  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react;
+  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react, ncons;
+  const int32_t* cons_i; const double* cons_f;
   int32_t* ibuf; double* fbuf;
   const int32_t *hi, *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
   const double *hf, *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *param_def, *state_def, *cam_f;
@@ -159,6 +160,7 @@ DgoWorld* dgo_create(const int32_t* ibuf, int ni, const double* fbuf, int nf) {
   W->ncam = HI(W, ncam); W->nop = HI(W, nop); W->nframes = HI(W, nframes); W->S = HI(W, S); W->P = HI(W, P);
   W->substeps = HI(W, substeps); W->iters = HI(W, iterations); W->maxc = HI(W, max_contacts); W->hot_start = HI(W, hot_start);
   W->ik_iters = HI(W, ik_iters);
+  W->ncons = HI(W, ncons); W->cons_i = sec_i(ib, SEC_CONS_I); W->cons_f = sec_f(ib, fb, SEC_CONS_F);
   W->need_react = 0;
   for (int k = 0; k < W->nop; k++) W->need_react |= W->op_i[DG_OP_I_W * k] == OP_FT_SENSOR;
   int nf_ = W->nframes, nl = W->nl > 0 ? W->nl : 1;
@@ -598,6 +600,18 @@ static void point_jacobian(DgoWorld* W, int f, const double* p, const double* di
     gl = li[1];
   }
 }
+/* generalized force per unit TORQUE along `dir` on frame f (same coordinates as point_jacobian) */
+static void angular_jacobian(DgoWorld* W, int f, const double* dir, double* J) {
+  int b = body_of_frame(W, f); const int32_t* bi = W->body_i + DG_BODY_I_W * b;
+  int ndb = bi[4], d0 = bi[3];
+  for (int i = 0; i < 6 + ndb; i++) J[i] = 0;
+  if (bi[0] == 0) return;
+  if (bi[0] == 2) v_cpy(J, dir);
+  for (int gl = f < W->nb ? -1 : f - W->nb; gl >= 0; gl = W->link_i[DG_LINK_I_W * gl + 1]) {
+    const int32_t* li = W->link_i + DG_LINK_I_W * gl; const double* lf = W->link_f + DG_LINK_F_W * gl;
+    if (li[2] == 1) { double aw[3]; m_vec(aw, W->Rw + 9 * frame_of_link(W, gl), lf + 10); J[6 + li[3] - d0] = v_dot(dir, aw); }
+  }
+}
 static void body_genvel(const DgoWorld* W, int b, double* gv) {
   const int32_t* bi = W->body_i + DG_BODY_I_W * b;
   v_cpy(gv, ST(W, S_BOMEGA) + 3 * b); v_cpy(gv + 3, ST(W, S_BVEL) + 3 * b);
@@ -652,6 +666,32 @@ static void build_rows(DgoWorld* W, double h) {
       double kp = ST(W, S_MKP)[d], kd = ST(W, S_MKD)[d], tp = ST(W, S_MTPOS)[d], tv = ST(W, S_MTVEL)[d];
       double desired = kp * (tp - q[d]) / h + qd[d] + kd * (tv - qd[d]);
       r->rhs = (desired - rel) * r->diag_inv; r->lo = -maxf * dt; r->hi = maxf * dt;
+    }
+  }
+  /* fixed constraints between models (diy_gym/model.py:69-77, p.createConstraint(..., JOINT_FIXED, ...)): the joint frame on
+   * the parent link (pos_a, quat_a in its COM frame) and the one on the child link are held together by three point rows
+   * along the world axes and three angular rows, error reduction erp per sub-step, impulse bound max_force x dt.
+   * [RECALLED-UNVERIFIED: Bullet's btMultiBodyFixedConstraint builds its rows in the parent frame; same solution set] */
+  for (int k = 0; k < W->ncons; k++) {
+    const int32_t* ci = W->cons_i + DG_CONS_I_W * k; const double* cf = W->cons_f + DG_CONS_F_W * k;
+    int fa = ci[0], fb = ci[1], ba = body_of_frame(W, fa), bb = body_of_frame(W, fb);
+    double Pa[3], Pb[3], t[3], qa[4], qb[4], qaw[4], qbw[4], qbi[4], dq[4], th[3];
+    m_vec(t, W->Rw + 9 * fa, cf); v_add(Pa, W->pw + 3 * fa, t);
+    m_vec(t, W->Rw + 9 * fb, cf + 7); v_add(Pb, W->pw + 3 * fb, t);
+    mat_to_q(qa, W->Rw + 9 * fa); mat_to_q(qb, W->Rw + 9 * fb);
+    q_mul(qaw, qa, cf + 3); q_mul(qbw, qb, cf + 10);
+    qbi[0] = -qbw[0]; qbi[1] = -qbw[1]; qbi[2] = -qbw[2]; qbi[3] = qbw[3];
+    q_mul(dq, qaw, qbi);                                   /* rotation that takes the child joint frame to the parent one */
+    { double vn = v_len(dq), ang = 2 * atan2(vn, dq[3]); if (ang > M_PI) ang -= 2 * M_PI;
+      if (vn < 1e-12) v_set(th, 0, 0, 0); else v_scale(th, dq, ang / vn); }
+    for (int i = 0; i < 6; i++) {
+      double e[3] = {0, 0, 0}, ne[3] = {0, 0, 0}; e[i % 3] = 1; ne[i % 3] = -1;
+      Row* r = new_row(W);
+      if (W->body_i[DG_BODY_I_W * ba] != 0) { r->bodyA = ba; if (i < 3) point_jacobian(W, fa, Pa, e, r->JA); else angular_jacobian(W, fa, e, r->JA); }
+      if (W->body_i[DG_BODY_I_W * bb] != 0) { r->bodyB = bb; if (i < 3) point_jacobian(W, fb, Pb, ne, r->JB); else angular_jacobian(W, fb, ne, r->JB); }
+      double rel = finish_row(W, r);
+      double err = i < 3 ? Pa[i] - Pb[i] : th[i - 3];
+      r->rhs = (-rel - err * erp / h) * r->diag_inv; r->lo = -cf[14] * dt; r->hi = cf[14] * dt;
     }
   }
   /* contacts: all normals first, then friction rows */

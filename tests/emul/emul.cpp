@@ -3,6 +3,7 @@
 // emulated by running every phase lane after lane (the barrier semantics of the GPU schedule).  Never shipped,
 // never used by the product path: diy_gym_b200 raises when libdiygym_b200.so / a CUDA device is missing.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -24,7 +25,7 @@ extern "C" {
 EmulWorld* dge_create(const int32_t* ibuf, int ni, const double* fbuf, int nf, int n_envs, int team, int ws_mode) {
   EmulWorld* w = new EmulWorld();
   const char* ea = getenv("DG_RS_ASHARED");
-  if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode, ea ? atoi(ea) : 0)) { delete w; return nullptr; }
+  if (!w->hs.build(ibuf, ni, fbuf, nf, team, ws_mode, ea ? atoi(ea) : 0)) { fprintf(stderr, "emul: %s\n", w->hs.error.c_str()); delete w; return nullptr; }
   w->n_envs = n_envs; w->team = team;
   if (const char* es = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(es) != 0;
   if (const char* em = getenv("DG_RS_MIN")) w->hs.dev.rs_min = atoi(em);
@@ -50,11 +51,14 @@ static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* re
   C.active = true; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;
 }
+// DGE_POISON=<value>: fills both workspaces with that value before every environment, so that a read of workspace memory
+// that this step did not write (garbage on the GPU, zeros here otherwise) shows up as a changed result
+static void poison(EmulWorld* w) { if (const char* p = getenv("DGE_POISON")) { float v = (float)atof(p); for (auto& x : w->ws) x = v; for (auto& x : w->wg) x = v; } }
 void dge_step(EmulWorld* w, const float* act, float* obs, float* rew, uint8_t* term) {
-  for (int e = 0; e < w->n_envs; e++) { Env C = make_env(w, e, act, obs, rew, term); run_env_step(C, w->team, 0); }
+  for (int e = 0; e < w->n_envs; e++) { poison(w); Env C = make_env(w, e, act, obs, rew, term); run_env_step(C, w->team, 0); }
 }
 void dge_reset(EmulWorld* w, const uint8_t* mask, float* obs, float* rew, uint8_t* term) {
-  for (int e = 0; e < w->n_envs; e++) { if (mask && !mask[e]) continue; Env C = make_env(w, e, nullptr, obs, rew, term); run_env_reset(C, w->team, 0); }
+  for (int e = 0; e < w->n_envs; e++) { if (mask && !mask[e]) continue; poison(w); Env C = make_env(w, e, nullptr, obs, rew, term); run_env_reset(C, w->team, 0); }
 }
 // physics only (no add-on ops): nsub = 0 refreshes the link cache
 void dge_physics(EmulWorld* w, int nsub) {

@@ -63,7 +63,8 @@ def test_kernel_code_on_cpu_reproduces_golden(name):
     from tests.emul.emul import EmulWorld
     g, sc = load(name)
     # two single-environment worlds so that each gets its own global env id (0 and 5)
-    ws = [EmulWorld(sc, 1, 4, seed=int(g['seed']), env_off=int(e)) for e in g['env_ids']]
+    team = 8 if sc['ncons'] else 4   # (welded models need the row capacity of a team of 8)
+    ws = [EmulWorld(sc, 1, team, seed=int(g['seed']), env_off=int(e)) for e in g['env_ids']]
     cat = lambda outs: tuple(np.concatenate([o[j] for o in outs]) for j in range(3))
     _check_world_against_golden(lambda: np.concatenate([w.state for w in ws]), g, sc,
                                 lambda a: cat([w.step(a[i:i + 1]) for i, w in enumerate(ws)]), lambda: cat([w.reset() for w in ws]))

@@ -267,3 +267,25 @@ def test_admittance_controller_rejects_partial_chains_like_pybullet():
 
 def make_path(path, n=1):
     return DIYGym(path, num_envs=n, world_factory=factory())
+
+
+# ---- nested models welded to a parent frame (model.py:69-77) -----------------------------------------
+def test_nested_model_is_welded_to_the_parent_frame():
+    env = DIYGym(os.path.join(EX, 'ur_gripper', 'ur_gripper.yaml'), num_envs=2, world_factory=factory(team=8))
+    ur5 = env.models['ur5']
+    payload = ur5.models['payload']
+    assert env.scene['ncons'] == 1 and payload.uid == 1
+    # like the reference, only top-level models are receptors: the nested model's add-ons are built but never walked
+    assert list(env.observation_space.spaces) == ['ur5'] and list(env.observation_space['ur5'].spaces) == ['joint_state']
+    env.reset()
+    act = {'ur5': {'controller': {'linear': torch.tensor([[0.01, 0.0, 0.0], [0.0, 0.0, 0.0]])}}}
+    ee = ur5.get_frame_id('ee_fixed_joint')
+    for _ in range(80):
+        env.step(act)
+    pos, quat, _, _ = ur5.link_state(ee)
+    from diy_gym_b200 import torch_math as tm
+    target = pos + tm.quat_rotate(quat, pos.new_tensor([0.0, 0.0, 0.1]).expand_as(pos))
+    gap = (payload.base_pose()[0] - target).norm(dim=1)
+    assert gap.max() < 0.02                      # held by the 6 constraint rows (soft: erp 0.2 per sub-step, under gravity)
+    assert pos[0, 0] - pos[1, 0] > 0.02          # environment 0 was driven along +x, its payload came along
+    assert (payload.base_pose()[0][0, 0] - payload.base_pose()[0][1, 0]) > 0.02
