@@ -263,8 +263,7 @@ struct HostScene {
     for (int k = 0; k < d.npair; k++) GP = std::max(GP, gdim_of_shape(pair_i[2 * k]) + gdim_of_shape(pair_i[2 * k + 1]));
     int n_ik = 0;
     for (int k = 0; k < d.nop; k++) n_ik += op_i[DG_OP_I_W * k] == OP_IK_CTRL;
-    d.need_react = 0;
-    for (int k = 0; k < d.nop; k++) d.need_react |= op_i[DG_OP_I_W * k] == OP_FT_SENSOR;
+    d.need_react = hi[HI_S_STEP] > hi[HI_S_JREACT];   // the state row holds reaction wrenches only when a sensor asked for them
 
     auto put_vi = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); ints.push_back(0); return o; };
     auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };

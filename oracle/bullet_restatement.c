@@ -161,8 +161,7 @@ DgoWorld* dgo_create(const int32_t* ibuf, int ni, const double* fbuf, int nf) {
   W->substeps = HI(W, substeps); W->iters = HI(W, iterations); W->maxc = HI(W, max_contacts); W->hot_start = HI(W, hot_start);
   W->ik_iters = HI(W, ik_iters);
   W->ncons = HI(W, ncons); W->cons_i = sec_i(ib, SEC_CONS_I); W->cons_f = sec_f(ib, fb, SEC_CONS_F);
-  W->need_react = 0;
-  for (int k = 0; k < W->nop; k++) W->need_react |= W->op_i[DG_OP_I_W * k] == OP_FT_SENSOR;
+  W->need_react = HI(W, S_STEP) > HI(W, S_JREACT);   /* the state row holds reaction wrenches only when a sensor asked for them */
   int nf_ = W->nframes, nl = W->nl > 0 ? W->nl : 1;
 #define ALLOC(p, n) W->p = (double*)calloc((size_t)(n) > 0 ? (size_t)(n) : 1, sizeof(double))
   ALLOC(state, W->S); ALLOC(param, W->P); ALLOC(Rw, 9 * nf_); ALLOC(pw, 3 * nf_); ALLOC(E, 9 * nl); ALLOC(r, 3 * nl);

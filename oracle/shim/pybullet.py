@@ -41,6 +41,9 @@ class _Sim:
         self.params = dict(timestep=1 / 240., substeps=1, iterations=50, gravity=(0, 0, 0))
         self.specs = []        # per body: dict(desc, scale, fixed, pos, quat, mass)
         self.pending_q = {}    # (uid, joint) -> (q, qd) set before the world exists
+        self.constraints = []  # createConstraint(JOINT_FIXED) records
+        self.ft_sensors = False
+        self.dirty = False     # a spec changed after the world was built: rebuild (state carried over) at the next query
         self.world = None
         self.scene = None
 
@@ -50,11 +53,16 @@ class _Sim:
         sb = SceneBuilder(timestep=p['timestep'], substeps=max(int(p['substeps']), 1), iterations=int(p['iterations']), gravity=p['gravity'], hot_start=0)
         for i, s in enumerate(self.specs):
             sb.add_body('body%d' % i, s['desc'], xyz=s['pos'], quat=s['quat'], scale=s['scale'], fixed_base=s['fixed'], mass=s['mass'])
+        for c in self.constraints:
+            sb.add_fixed_constraint(sb.bodies[c[0]], c[1], sb.bodies[c[2]], c[3], c[4], c[5], c[6], c[7])
+        sb.need_jreact = self.ft_sensors
         return sb
 
     def ensure(self):
-        if self.world is not None and self.scene['nb'] == len(self.specs):
+        if self.world is not None and self.scene['nb'] == len(self.specs) and self.scene['ncons'] == len(self.constraints) and \
+                bool(self.scene.builder.need_jreact) == self.ft_sensors and not self.dirty:
             return self.world
+        self.dirty = False
         old, old_scene = self.world, self.scene
         sb = self.builder()
         self.scene = sb.finalize()
@@ -139,15 +147,26 @@ def resetBasePositionAndOrientation(uid, pos, quat, **k):
         w.refresh()
 
 
-def createConstraint(*a, **k):
-    raise error('createConstraint (nested models) is not supported by the oracle shim')
+def createConstraint(parentBodyUniqueId, parentLinkIndex, childBodyUniqueId, childLinkIndex, jointType, jointAxis, parentFramePosition,
+                     childFramePosition, parentFrameOrientation=(0, 0, 0, 1), childFrameOrientation=(0, 0, 0, 1), **k):
+    """JOINT_FIXED only (diy_gym/model.py:74-75): the two joint frames, given in the COM frames of the two links."""
+    if jointType != JOINT_FIXED:
+        raise error('the oracle shim implements JOINT_FIXED constraints only')
+    _sim.constraints.append((parentBodyUniqueId, parentLinkIndex, childBodyUniqueId, childLinkIndex, _vec3(parentFramePosition),
+                             np.array(parentFrameOrientation, float), _vec3(childFramePosition), np.array(childFrameOrientation, float)))
+    return len(_sim.constraints) - 1
+
+
+def enableJointForceTorqueSensor(uid, joint, enableSensor=True, **k):
+    _sim.ft_sensors = _sim.ft_sensors or bool(enableSensor)
 
 
 def changeDynamics(uid, link, mass=None, angularDamping=None, **k):
-    if mass is not None and link == -1 and _sim.world is None:
+    if mass is not None and link == -1:
         _sim.specs[uid]['mass'] = float(mass)
+        _sim.dirty = _sim.world is not None   # (the mass is a scene constant of the oracle world: rebuild, state carried over)
         return
-    raise error('changeDynamics after the world was built is not supported by the oracle shim')
+    raise error('changeDynamics: only the base mass is supported by the oracle shim')
 
 
 def changeVisualShape(*a, **k):
@@ -219,7 +238,7 @@ def setJointMotorControlArray(uid, jointIndices, controlMode, targetPositions=No
         else:
             w.state[h['S_MKP'] + d] = 0.0
             w.state[h['S_MTPOS'] + d] = 0.0
-            w.state[h['S_MTVEL'] + d] = targetVelocities[i]
+            w.state[h['S_MTVEL'] + d] = targetVelocities[i] if targetVelocities is not None else 0.0   # pybullet's default target
     assert n >= 0
 
 
@@ -278,7 +297,11 @@ def getJointState(uid, joint, **k):
     w, h = _sim.ensure(), _sim.scene.hdr
     d = _sim.scene.bodies[uid].global_dof(joint)
     dt = _sim.scene.hdr_f['dt']
-    return (w.state[h['S_Q'] + d], w.state[h['S_QD'] + d], (0.0, ) * 6, w.state[h['S_MAPPLIED'] + d] / dt)
+    react = (0.0, ) * 6
+    if _sim.ft_sensors:   # [Fx Fy Fz Mx My Mz] of the joint's child link, from the last forward-dynamics pass
+        gl = _sim.scene.bodies[uid].link_start + joint
+        react = tuple(w.state[h['S_JREACT'] + 6 * gl:h['S_JREACT'] + 6 * gl + 6])
+    return (w.state[h['S_Q'] + d], w.state[h['S_QD'] + d], react, w.state[h['S_MAPPLIED'] + d] / dt)
 
 
 def getJointStates(uid, joints, **k):
@@ -299,6 +322,84 @@ def calculateInverseKinematics(bodyUniqueId, endEffectorLinkIndex, targetPositio
     sol = w.ik(uid, b.link_start + endEffectorLinkIndex, np.array(targetPosition, float),
                None if targetOrientation is None else np.array(targetOrientation, float), null)
     return tuple(sol)
+
+
+def _joint_axes_at(uid, q):
+    """World axis / origin of every joint and world COM of every link of body uid at joint coordinates q (plain product of
+    the scene's link records; numpy, independent of the C code paths it is used to check)."""
+    b, sc = _sim.scene.bodies[uid], _sim.scene
+    w, h = _sim.ensure(), sc.hdr
+    LI, LF = sc.sec['LINK_I'], sc.sec['LINK_F']
+    R = {-1: _q_to_mat(w.state[h['S_BQUAT'] + 4 * uid:h['S_BQUAT'] + 4 * uid + 4])}
+    P = {-1: np.array(w.state[h['S_BPOS'] + 3 * uid:h['S_BPOS'] + 3 * uid + 3])}
+    axes, orgs = {}, {}
+    for k in range(b.n_links):
+        gl = b.link_start + k
+        li, lf = LI[gl], LF[gl]
+        par = -1 if li[1] < 0 else li[1] - b.link_start
+        R0, a, d = _q_to_mat(lf[0:4]), np.array(lf[10:13]), np.array(lf[7:10])
+        qk = q[b.joint_dof[k]] if b.joint_dof[k] >= 0 else 0.0
+        if li[2] == 1:
+            K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+            Rrel = R0 @ (np.eye(3) + np.sin(qk) * K + (1 - np.cos(qk)) * K @ K)
+            r = np.array(lf[4:7]) + Rrel @ d
+        elif li[2] == 2:
+            Rrel = R0
+            r = np.array(lf[4:7]) + R0 @ (d + a * qk)
+        else:
+            Rrel = R0
+            r = np.array(lf[4:7]) + R0 @ d
+        R[k] = R[par] @ Rrel
+        P[k] = P[par] + R[par] @ r
+        axes[k] = R[k] @ a
+        orgs[k] = P[k] - R[k] @ d
+    return b, LI, R, P, axes, orgs
+
+
+def calculateJacobian(bodyUniqueId, linkIndex, localPosition, objPositions, objVelocities, objAccelerations, **k):
+    """Translational / rotational Jacobian (3 x nDoF each, world axes) of the point `localPosition` of link `linkIndex`, given
+    in that link's COM frame (admittance_controller.py:39-45).  Fixed-base bodies."""
+    b, LI, R, P, axes, orgs = _joint_axes_at(bodyUniqueId, list(objPositions))
+    if len(objPositions) != b.n_dofs:
+        raise error('calculateJacobian: %d joint positions for a body with %d degrees of freedom' % (len(objPositions), b.n_dofs))
+    pt = P[linkIndex] + R[linkIndex] @ _vec3(localPosition)
+    Jl, Ja = np.zeros((3, b.n_dofs)), np.zeros((3, b.n_dofs))
+    kk = linkIndex
+    while kk >= 0:
+        d = b.joint_dof[kk]
+        jt = LI[b.link_start + kk][2]
+        if d >= 0:
+            if jt == 1:
+                Jl[:, d], Ja[:, d] = np.cross(axes[kk], pt - orgs[kk]), axes[kk]
+            else:
+                Jl[:, d] = axes[kk]
+        par = LI[b.link_start + kk][1]
+        kk = -1 if par < 0 else par - b.link_start
+    return tuple(map(tuple, Jl)), tuple(map(tuple, Ja))
+
+
+def calculateInverseDynamics(bodyUniqueId, objPositions, objVelocities, objAccelerations, **k):
+    """Generalized forces that hold the body at objPositions; the reference only calls it with zero velocities and
+    accelerations (admittance_controller.py:47), i.e. asks for the gravity torques."""
+    if any(abs(v) > 0 for v in objVelocities) or any(abs(v) > 0 for v in objAccelerations):
+        raise error('the oracle shim implements calculateInverseDynamics at zero velocity / acceleration only')
+    b, LI, R, P, axes, orgs = _joint_axes_at(bodyUniqueId, list(objPositions))
+    if len(objPositions) != b.n_dofs:
+        raise error('calculateInverseDynamics: %d joint positions for a body with %d degrees of freedom' % (len(objPositions), b.n_dofs))
+    w, h = _sim.ensure(), _sim.scene.hdr
+    g = np.array(_sim.params['gravity'], float)
+    tau = np.zeros(b.n_dofs)
+    for k2 in range(b.n_links):
+        m = w.param[h['P_MASS'] + b.frame(k2)]
+        kk = k2
+        while kk >= 0:
+            d = b.joint_dof[kk]
+            if d >= 0:
+                dp = np.cross(axes[kk], P[k2] - orgs[kk]) if LI[b.link_start + kk][2] == 1 else axes[kk]
+                tau[d] -= m * g.dot(dp)
+            par = LI[b.link_start + kk][1]
+            kk = -1 if par < 0 else par - b.link_start
+    return tuple(tau)
 
 
 # ---------------------------------------------------------------- math helpers -----------------------------------

@@ -16,7 +16,11 @@ from bench import CONFIGS, register_example_addons
 from diy_gym_b200 import Configuration, DIYGym
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze']
+NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze', 'ur_admittance', 'ur_gripper']
+# ur_gripper: the welded child's spawn transient is solved with clamped, unconverged sweeps whose result depends on
+# rounding; the x86 build of the kernel code follows the fp64 rollout from reset, the GPU build is
+# compared after the transient in tests/test_gpu_parity.py instead
+GPU_NAMES = [n for n in NAMES if n != 'ur_gripper']
 TOL = dict(rtol=3e-3, atol=3e-4)
 
 
@@ -112,11 +116,11 @@ def check(name, env):
 def test_host_layer_matches_reference_layer_cpu(name):
     from tests.emul.world import factory
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reflayer_' + name + '.npz'))
-    check(name, make_env(name, g, world_factory=factory()))
+    check(name, make_env(name, g, world_factory=factory(team=8 if name == 'ur_gripper' else 4)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('name', NAMES)
+@pytest.mark.parametrize('name', GPU_NAMES)
 def test_host_layer_matches_reference_layer_cuda(name):
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reflayer_' + name + '.npz'))
     env = make_env(name, g, device=0)

@@ -34,6 +34,9 @@ CONFIGS = {
     'drone_pilot': os.path.join(REF, 'examples', 'drone_pilot', 'drone_pilot.yaml'),
     'basic_env': os.path.join(REF, 'diy_gym', 'tests', 'basic_env.yaml'),
     'r2d2_maze': os.path.join(ROOT, 'examples', 'r2d2_maze', 'r2d2_maze.yaml'),   # emitted by the reference's generator
+    # the reference ships no config for these add-ons / nested models; these two use its schema and its own classes
+    'ur_admittance': os.path.join(ROOT, 'examples', 'ur_admittance', 'ur_admittance.yaml'),
+    'ur_gripper': os.path.join(ROOT, 'examples', 'ur_gripper', 'ur_gripper.yaml'),
 }
 
 
