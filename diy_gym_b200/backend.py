@@ -57,6 +57,10 @@ def load_library():
     L.dg_set_action_mask.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int]
     L.dg_step_host.restype = ctypes.c_int
     L.dg_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dg_debug_phase_cycles.restype = ctypes.c_int
+    L.dg_debug_phase_cycles.argtypes = [vp, ctypes.c_int]
+    L.dg_debug_read.restype = ctypes.c_int
+    L.dg_debug_read.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int]
     L.dg_measure_fp32_peak.restype = ctypes.c_int
     L.dg_measure_fp32_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     _lib = L

@@ -35,6 +35,7 @@ struct Env {
   int env_id;
   bool active;        // false: no environment for this slot in this launch (barriers only)
   unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
+  unsigned long long* dbg;        // phase timing (dg_debug_phase_cycles): [block][64] cycle sums keyed by source line & 63, or null
 };
 
 #define SC (*C.sc)
@@ -1000,11 +1001,9 @@ DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_co
 // case: their A entries simply have two body terms.
 // Setup scatters every row's J and M^-1 J^T into DENSE vectors over the generalized coordinates of all dynamic bodies
 // (the layout of W_DV), so that building A and folding the impulses back into dv are plain dense products.
-// home of A: shared memory (compact stride) when it fits the per-environment budget, else the cold workspace
-DG_FN float* rs_amat(const Env& C, int R, int Rp, int* stride) {
-  if (R > 0 && R * Rp + RS_KMAX * SC.team <= SC.rs_ashared) { *stride = Rp; return WSH(C, SC.X_RSAS); }   // (slack: a row is read to a full register block)
-  *stride = SC.rs_cap; return WSG(C, SC.X_RSA);
-}
+// home of A: the cold workspace (L1 / L2 backed).  Shared memory was measured slower on every example scene - the larger
+// carve-out shrinks L1 for all other phases (profiles/r1_solver_ab.log, r1_phase_probe.log) - and is not offered any more.
+DG_FN float* rs_amat(const Env& C, int R, int Rp, int* stride) { (void)R; (void)Rp; *stride = SC.rs_cap; return WSG(C, SC.X_RSA); }
 // row records + dense vectors, lane per row; WH_RS_R = 0 sends the environment to the dv-space sweeps (no contact,
 // one-lane team, too many rows or coordinates)
 DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
@@ -1120,8 +1119,11 @@ DG_FN void phase_rs_finish(const Env& C, int ln, int nt) {
 // (l = lane in team), every thread of the warp takes part in every shuffle, and every loop bound is warp-uniform
 // (maxima / minima over the teams of the warp); a team is masked off outside its own row ranges.  One update is
 // branch-free: every lane evaluates the clamp of ITS row (k, l), the owner's result is picked by the shuffle.
-template <int K, int NT>
-__device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsigned wmask, const int R, const int nu, const int nc) {
+// FULL: every warp of the block has 32 threads, so the shuffles take the literal full mask; a mask held in a register makes
+// nvcc guard every shuffle with MATCH.ANY + REDUX + VOTE + a divergence branch (~250 cycles per row, profiles/r1_phase_probe.log).
+template <int K, int NT, bool FULL>
+__device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsigned wmask_rt, const int R, const int nu, const int nc) {
+  const unsigned wmask = FULL ? 0xffffffffu : wmask_rt;
   const DevScene& sc = SC;
   const int tbase = (threadIdx.x & 31) & ~(NT - 1); int cap;
   float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + NT - 1) / NT * NT, &cap) + l; float* capp = WSH(C, sc.W_CAPP);
@@ -1150,6 +1152,7 @@ __device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsi
     if (valid_ && l == (j)) { ap[k] = new_; if ((normal) && (r) >= nu + nk) capp[(r) - nu - nk] = new_; }      \
     _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(a_[kk], d_, y[kk]);                          \
   }
+  // (fetching row r of A one slot ahead was measured: no change - the loads are not what a slot waits for)
   for (int it = 0; it < sc.iters; it++) {
     if (it & 1) {
 #pragma unroll
@@ -1199,9 +1202,14 @@ __device__ __forceinline__ void rs_solve_block(const Env& C) {
   const int R_max = __reduce_max_sync(wmask, R);
   if (R_max > 0) {
     const int kneed = (R_max + NT - 1) / NT;
-    if (kneed <= 2) rs_solve_team<2, NT>(C2, l2, wmask, R, nu, nc);
-    else if (kneed <= 4) rs_solve_team<4, NT>(C2, l2, wmask, R, nu, nc);
-    else rs_solve_team<RS_KMAX, NT>(C2, l2, wmask, R, nu, nc);
+    if ((blockDim.x & 31u) == 0u) {
+      if (kneed <= 2) rs_solve_team<2, NT, true>(C2, l2, wmask, R, nu, nc);
+      else if (kneed <= 4) rs_solve_team<4, NT, true>(C2, l2, wmask, R, nu, nc);
+      else rs_solve_team<RS_KMAX, NT, true>(C2, l2, wmask, R, nu, nc);
+    } else {
+      if (kneed <= 4) rs_solve_team<4, NT, false>(C2, l2, wmask, R, nu, nc);
+      else rs_solve_team<RS_KMAX, NT, false>(C2, l2, wmask, R, nu, nc);
+    }
   }
   }
 }
@@ -1716,7 +1724,9 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
 // off) have C.active == false: they skip the phase bodies but keep the barriers.  T == 1 needs no barriers at all.
 // The CPU emulation runs one environment at a time, lane after lane - exactly the barrier semantics.
 #if defined(__CUDA_ARCH__)
-#define DG_PHASE(call) do { if (C.active) { call; } if (nt > 1) __syncthreads(); } while (0)
+// (with C.dbg set, thread 0 of every block adds the cycles of each phase, barrier included, to its slot of the debug table)
+#define DG_PHASE(call) do { const long long t0_ = C.dbg ? clock64() : 0; if (C.active) { call; } if (nt > 1) __syncthreads(); \
+                            if (C.dbg && threadIdx.x == 0) C.dbg[(size_t)blockIdx.x * 64 + (__LINE__ & 63)] += (unsigned long long)(clock64() - t0_); } while (0)
 #define DG_LANE_ARGS int ln
 DG_HD bool block_any(bool p, int nt) { return nt > 1 ? (__syncthreads_or(p ? 1 : 0) != 0) : p; }
 #else
@@ -1758,10 +1768,12 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
                else if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
       if (sc.solver == 1 && nt > 1) {
 #if defined(__CUDA_ARCH__)
+        const long long t0_ = C.dbg ? clock64() : 0;
 #if defined(DG_STEP_T)
         rs_solve_block<DG_STEP_T>(C);
 #endif
         __syncthreads();
+        if (C.dbg && threadIdx.x == 0) C.dbg[(size_t)blockIdx.x * 64 + (__LINE__ & 63)] += (unsigned long long)(clock64() - t0_);
 #else
         DG_PHASE(if (ln == 0 && HDRV(WH_RS_R) > 0) rs_solve_serial(C, nt));
 #endif

@@ -23,6 +23,7 @@ struct LaunchArgs {
   const uint8_t* mask; int n_envs; int mode; uint32_t seed; int env_off;
   unsigned long long opmask[2];
   float* gws;   // cold workspace: one slot of sc.g_total floats per resident team
+  unsigned long long* dbg;   // phase-timing table or null (dg_debug_phase_cycles)
 };
 
 template <int T>
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   __syncthreads();
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
   C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * E + ei) * sc.g_total; C.seed = a.seed;
-  C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1];
+  C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg;
   // block-uniform trip count: every thread of the block walks the same number of environment groups
   for (int base = blockIdx.x * E; base < a.n_envs; base += gridDim.x * E) {
     const int e = base + ei;
@@ -158,7 +159,7 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
   const int width = ci[1], height = ci[2];
   unsigned* cand = reinterpret_cast<unsigned*>(vs + VS_W * sc.nv);
   const int ncw = (sc.nv + 31) / 32;
-  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr;
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr;
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
   const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
@@ -265,6 +266,7 @@ struct DgWorld {
   uint32_t seed = 1234u; int env_off = 0;
   unsigned long long opmask[2] = {~0ull, ~0ull};
   float* gws = nullptr;
+  unsigned long long* dbg = nullptr;   // [grid][64] phase-cycle sums while dg_debug_phase_cycles is on
   int64_t launches = 0;
   std::string err;
 };
@@ -354,10 +356,7 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   const char* env_mode = getenv("DG_WS_MODE");
   int ws_mode = env_mode ? atoi(env_mode) : 3;
   if (ws_mode != 2 && ws_mode != 3) ws_mode = 3;
-  // The row-space solver keeps its matrix A in the cold workspace: giving it shared memory was measured slower on every
-  // example scene (the larger carve-out shrinks L1, profiles/r1_solver_ab.log); DG_RS_ASHARED=<floats per environment> overrides.
-  const char* env_a = getenv("DG_RS_ASHARED");
-  if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode, env_a ? atoi(env_a) : 0)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
+  if (!w->hs.build(ibuf, n_ibuf, fbuf, n_fbuf, team, ws_mode)) { g_create_err = "scene: " + w->hs.error; delete w; return DG_E_SCENE; }
   // DG_SOLVER=0: coupled environments fall back to lock-step dv-space sweeps; DG_RS_MIN=<rows>: uncoupled environments with
   // at least that many contact rows are solved in row space too (both kept for A/B measurements)
   if (const char* env_solver = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(env_solver) != 0;
@@ -396,6 +395,7 @@ void dg_world_destroy(DgWorld* w) {
   if (w->d_ints) cudaFree(w->d_ints);
   if (w->d_floats) cudaFree(w->d_floats);
   if (w->gws) cudaFree(w->gws);
+  if (w->dbg) cudaFree(w->dbg);
   delete w;
 }
 
@@ -446,8 +446,26 @@ int dg_init_state(DgWorld* w, void* stream) {
 static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "buffers not bound"; return DG_E_UNBOUND; }
-  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws};
+  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg};
   CK(w, launch_any(w, a, (cudaStream_t)stream));
+  return DG_OK;
+}
+// Measurement aid: with `enable`, thread 0 of every block of the step kernel accumulates the cycles of each phase (barrier
+// included) into a [grid][64] table keyed by (source line of the phase in dg_env.cuh) & 63; dg_debug_read copies it out
+// (out[block * 64 + key], n <= grid * 64 entries) and clears it.  tools/phase_probe.py prints it.
+int dg_debug_phase_cycles(DgWorld* w, int enable) {
+  if (!w) return DG_E_ARG;
+  CK(w, cudaSetDevice(w->device));
+  if (!enable) { if (w->dbg) { cudaDeviceSynchronize(); cudaFree(w->dbg); w->dbg = nullptr; } return DG_OK; }
+  if (!w->dbg) CK(w, cudaMalloc(&w->dbg, (size_t)w->grid * 64 * sizeof(unsigned long long)));
+  CK(w, cudaMemset(w->dbg, 0, (size_t)w->grid * 64 * sizeof(unsigned long long)));
+  return DG_OK;
+}
+int dg_debug_read(DgWorld* w, unsigned long long* out, int n) {
+  if (!w || !out || !w->dbg || n > w->grid * 64) return DG_E_ARG;
+  CK(w, cudaDeviceSynchronize());
+  CK(w, cudaMemcpy(out, w->dbg, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(w, cudaMemset(w->dbg, 0, (size_t)w->grid * 64 * sizeof(unsigned long long)));
   return DG_OK;
 }
 int dg_step(DgWorld* w, void* stream) { return run(w, 0, nullptr, stream); }

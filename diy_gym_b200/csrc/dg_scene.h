@@ -336,9 +336,8 @@ struct HostScene {
       return false;
     }
     d.solver = 1; d.rs_min = 1 << 20;   // measured (profiles/r1_rs_min_sweep.log): uncoupled environments are faster with the per-body sweeps
-    d.rs_ashared = std::max(0, std::min(rs_ashared, d.rs_cap * d.rs_cap)) & ~3;
+    d.rs_ashared = 0; d.X_RSAS = 0; (void)rs_ashared;   // (shared-memory home of A: measured slower, removed)
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);
-    phase_take(&d.X_RSAS, RC_SOLVE, 1, d.rs_ashared);
     phase_take(&d.X_RSV, RC_SCRATCH, 1, d.rs_cap * 2 * gv);      // per row: J and M^-1 J^T, dense over all bodies' coordinates
     phase_take(&d.X_RSREC, RC_SCRATCH, 1, d.rs_cap * RR_W);
     phase_take(&d.X_IK, RC_SCRATCH, 2, n_ik ? d.ik_stride * std::min(team, n_ik) : 0);

@@ -76,6 +76,11 @@ int dg_init_state(DgWorld* w, void* stream);
 /* One DIYGym.step for every environment: add-on update(action) -> stepSimulation -> observe/reward/is_terminal.
  * Replaces /root/reference/diy_gym/diy_gym.py:187-209 (p.stepSimulation at :207 and every add-on hook it fans out to). */
 int dg_step(DgWorld* w, void* stream);
+/* Measurement aid (no reference counterpart): per-block, per-phase cycle sums of the step kernel.  enable != 0 allocates and
+ * clears a [grid][64] table keyed by (source line of the phase in dg_env.cuh) & 63; dg_debug_read copies n <= grid * 64
+ * entries out and clears the table; enable == 0 frees it.  tools/phase_probe.py prints the result. */
+int dg_debug_phase_cycles(DgWorld* w, int enable);
+int dg_debug_read(DgWorld* w, unsigned long long* out, int n);
 /* DIYGym.reset for the environments whose mask byte is non-zero (mask_dev == NULL: all).
  * Replaces /root/reference/diy_gym/diy_gym.py:130-148 (add-on reset hooks, hot-start steps, observe). */
 int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream);
