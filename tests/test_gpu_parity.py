@@ -265,3 +265,14 @@ def test_full_size_properties_ur_high_5_8192():
     assert torch.equal(st[:16], small.world.state)
     env.close()
     small.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('envs_per_block', [3, 6])
+@pytest.mark.parametrize('name,scale', [('r2d2_maze', 10.0), ('basic_env', 10.0), ('ur_gripper', 0.01)])
+def test_row_space_solver_on_partial_warps_and_uncoupled_scenes(monkeypatch, name, scale, envs_per_block):
+    """The row-space team solver with every contact environment routed through it (DG_RS_MIN=0) and with blocks whose
+    last warp is partial (24 / 48 threads: the sweeps then take the run-time shuffle mask instead of the literal one)."""
+    monkeypatch.setenv('DG_RS_MIN', '0')
+    monkeypatch.setenv('DG_ENVS_PER_BLOCK', str(envs_per_block))
+    test_example_configs_reset_and_step_match_oracle(name, scale)
