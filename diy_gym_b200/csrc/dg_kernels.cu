@@ -65,6 +65,11 @@ template <int T> static cudaError_t step_configure_t(int block_threads, size_t s
   // the attribute is per function, not per world: always allow the device maximum so that worlds of different sizes coexist
   cudaError_t e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cap);
   if (e != cudaSuccess) return e;
+  // DG_CARVEOUT=<percent of the SM's shared memory>: preferred carve-out of the step kernel (the rest is L1); measurement aid
+  if (const char* cv = getenv("DG_CARVEOUT")) {
+    e = cudaFuncSetAttribute(dg_step_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv));
+    if (e != cudaSuccess) return e;
+  }
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, dg_step_kernel<T>, block_threads, smem);
 }
 template <int T> static cudaError_t step_launch_t(const DevScene& sc, const LaunchArgs& a, const StepLaunch& l) {
