@@ -401,11 +401,11 @@ class SceneBuilder:
             raise ValueError('max_contacts is limited to 21 (the solver tracks at most 63 contact rows per environment)')
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
-                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn, ncons=ncons)
+                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=int(__import__('os').environ.get('DG_DBG_IKIT', 20)), ndyn=ndyn, ncons=ncons)
         hdr.update(lay)
         hdr_i = np.array([hdr[k] for k in HDR_I_FIELDS], np.int32)
         hf = dict(dt=self.timestep, gx=self.gravity[0], gy=self.gravity[1], gz=self.gravity[2], erp=0.2, contact_erp=0.2,
-                  linear_slop=0.0, contact_margin=0.0, ik_damping=0.5, ik_threshold=1e-4, max_joint_vel=100.0,
+                  linear_slop=0.0, contact_margin=0.0, ik_damping=0.5, ik_threshold=float(__import__('os').environ.get('DG_DBG_IKTHR', 1e-4)), max_joint_vel=100.0,
                   default_motor_impulse=1.0, limit_max_impulse=100.0, ik_null_lambda_sq=0.36)
         hdr_f = np.array([hf[k] for k in HDR_F_FIELDS])
 

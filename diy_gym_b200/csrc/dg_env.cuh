@@ -34,6 +34,7 @@ struct Env {
   uint32_t seed;
   int env_id;
   bool active;        // false: no environment for this slot in this launch (barriers only)
+  int grp0, grp1;     // environments of the block that share a warp in the row-space sweeps, as offsets (in workspaces) from this one: [grp0, grp1)
   unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
   unsigned long long* dbg;        // phase timing (dg_debug_phase_cycles): [block][64] cycle sums keyed by source line & 63, or null
 };
@@ -102,7 +103,7 @@ DG_FN void phase_load(const Env& C, int ln, int nt) {
 DG_FN void joint_xform(const Env& C, int gl, float q, float* E, float* r) {
   const int* li = shc(C.link_i) + DG_LINK_I_W * gl; const float* lf = shc(C.link_f) + DG_LINK_F_W * gl; const float* R0 = shc(C.link_x) + 16 * gl;
   float Rrel[9], tmp[3];
-  if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q, C.sc->ncons > 0); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
+  if (li[2] == 1) { float Ra[9]; axis_angle_mat(Ra, lf + 10, q, C.sc->precise != 0); m_mul(Rrel, R0, Ra); m_vec(tmp, Rrel, lf + 7); }
   else if (li[2] == 2) { m_cpy(Rrel, R0); float dd[3] = {lf[7] + lf[10] * q, lf[8] + lf[11] * q, lf[9] + lf[12] * q}; m_vec(tmp, R0, dd); }
   else { m_cpy(Rrel, R0); m_vec(tmp, R0, lf + 7); }
   v_add(r, lf + 4, tmp);
@@ -992,30 +993,70 @@ DG_FN void phase_pgs_unit(const Env& C, int ln, int nt, int it0, int it1) {
 DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_contact_sweep(C); }
 
 // ------------------------------------------------------------------ row-space team solver ----------------------
-// Environments with contacts are solved by the WHOLE team in row space: y_r = J_r dv is carried for every unit and
-// contact row, A[r][s] = J_s M^-1 J_r^T is built once per sub-step by all lanes, and one Gauss-Seidel update of row r
-// is  d = clamp(rhs_r - y_r dinv_r),  y_s += A[r][s] d  with the rows s dealt round-robin to the lanes (row r lives
-// in lane r % nt, register r / nt).  Row order, clamps and friction bounds are those of the dv-space sweeps
-// (pgs_body_full / pgs_contact_sweep): unit rows (direction alternating with the iteration), normal rows, friction rows
-// bounded by mu x (normal impulse after this sweep's normal rows).  Rows that couple two dynamic bodies need no special
-// case: their A entries simply have two body terms.
+// Environments with contacts (or welded models) are solved by the WHOLE team in row space: y_p = J_p dv is carried for
+// every unit, constraint and contact row, A[p][s] = J_s M^-1 J_p^T is built once per sub-step by all lanes, and one
+// Gauss-Seidel update of row p is  d = clamp(rhs_p - y_p dinv_p),  y_s += A[p][s] d.  Row order, clamps and friction bounds
+// are those of the dv-space sweeps (pgs_body_full / pgs_contact_sweep) and of the oracle: unit rows (direction alternating
+// with the iteration), constraint + normal rows, friction rows bounded by mu x (normal impulse after this sweep's normal
+// rows).  Rows that couple two dynamic bodies need no special case: their A entries simply have two body terms.
+//
+// Layout.  Rows live at POSITIONS of three sections, each padded to a multiple of K (K = 2, 4 or 8 rows per lane):
+//   [0, nu) unit rows | [P1, P1 + nk) constraint rows, [P1 + nk, P1 + nk + nc) normals | [P2, P2 + 2 nc) friction rows,
+//   P1 = pad(nu), P2 = P1 + pad(nk + nc), Rp = P2 + pad(2 nc).
+// A padding position carries rhs = dinv = lo = hi = 0 and a zero row / column of A: its update is d = 0 by arithmetic, no
+// mask needed.  Lane l of the team OWNS positions [l K, (l + 1) K) - a BLOCK of consecutive rows - and keeps their y, rhs,
+// clamps and accumulated impulses in registers; a sweep walks the blocks of a section in order, the K slots of a block
+// unrolled.  Because consecutive rows belong to the same lane, the Gauss-Seidel dependency d_p -> y_{p+1} stays inside one
+// thread (clamp + one FMA, ~25 cycles); the other lanes receive d_p by a shuffle whose latency is hidden - they fold it into
+// their y one slot later - and only at a block boundary (every K rows) does the next owner wait for the broadcast.
+// (Round 1 dealt the rows round-robin: every update then waited for a shuffle, ~270 cycles per row measured.)
 // Setup scatters every row's J and M^-1 J^T into DENSE vectors over the generalized coordinates of all dynamic bodies
 // (the layout of W_DV), so that building A and folding the impulses back into dv are plain dense products.
-// home of A: the cold workspace (L1 / L2 backed).  Shared memory was measured slower on every example scene - the larger
-// carve-out shrinks L1 for all other phases (profiles/r1_solver_ab.log, r1_phase_probe.log) - and is not offered any more.
-DG_FN float* rs_amat(const Env& C, int R, int Rp, int* stride) { (void)R; (void)Rp; *stride = SC.rs_cap; return WSG(C, SC.X_RSA); }
-// row records + dense vectors, lane per row; WH_RS_R = 0 sends the environment to the dv-space sweeps (no contact,
-// one-lane team, too many rows or coordinates)
+// home of A: the cold workspace (L1 / L2 backed).
+struct RsLayout { int K, nu, nk, nc, P1, nrm0, nrm1, P2, fr1, Rp; };
+DG_HD int rs_pad(int n, int K) { return (n + K - 1) / K * K; }
+DG_HD int rs_total(int nu, int nk, int nc, int K) { return rs_pad(nu, K) + rs_pad(nk + nc, K) + rs_pad(2 * nc, K); }
+DG_HD RsLayout rs_layout(int K, int nu, int nk, int nc) {
+  RsLayout L; L.K = K; L.nu = nu; L.nk = nk; L.nc = nc; L.P1 = rs_pad(nu, K); L.nrm0 = L.P1 + nk; L.nrm1 = L.nrm0 + nc;
+  L.P2 = L.P1 + rs_pad(nk + nc, K); L.fr1 = L.P2 + 2 * nc; L.Rp = L.P2 + rs_pad(2 * nc, K);
+  return L;
+}
+DG_HD bool rs_real(const RsLayout& L, int p) { return p < L.nu || (p >= L.P1 && p < L.nrm1) || (p >= L.P2 && p < L.fr1); }
+DG_FN RsLayout rs_layout_of(const Env& C) {
+  const int* hdr = WSI(C) + SC.W_HDR;
+  return rs_layout(hdr[WH_RS_K], hdr[WH_RS_NU], 6 * SC.ncons, hdr[WH_NCROW] / 3);
+}
+// smallest K whose padded layout fits a team of nt lanes (and the row capacity of the workspace); 0: does not fit
+DG_HD int rs_kneed(int nu, int nk, int nc, int nt, int cap) {
+  for (int K = 2; K <= RS_KMAX; K *= 2) { const int t = rs_total(nu, nk, nc, K); if (t <= K * nt && t <= cap) return K; }
+  return 0;
+}
+// lane 0: row counts and the K this environment needs; WH_RS_NEED = 0 sends the environment to the dv-space sweeps
+// (no contact, one-lane team, too many rows or coordinates)
+DG_FN void phase_rs_plan(const Env& C, int ln, int nt) {
+  if (ln != 0) return;
+  const DevScene& sc = SC;
+  int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW];
+  int nu = 0;
+  for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
+  const int nk = 6 * sc.ncons;
+  const bool want = sc.solver == 1 && nt >= 2 && (nk > 0 || (ncr > 0 && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min)));
+  hdr[WH_RS_NU] = nu; hdr[WH_RS_NEED] = want ? rs_kneed(nu, nk, ncr / 3, nt, sc.rs_cap) : 0; hdr[WH_RS_R] = 0;
+}
+// row records + dense vectors, lane per row.  K is the largest need among the environments that share a warp in the sweeps
+// (C.grp0 .. C.grp1: their workspaces sit at multiples of w_total from this one), so that the warp runs one instantiation.
 DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW], GV = sc.GV;
-  int nu = 0;
-  for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
-  const int nk = 6 * sc.ncons, R = nu + nk + ncr;
-  const bool use = sc.solver == 1 && nt >= 2 && R <= sc.rs_cap && (nk > 0 || (ncr > 0 && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min)));
-  if (ln == 0) { hdr[WH_RS_R] = use ? R : 0; hdr[WH_RS_NU] = nu; }
-  if (!use) return;
+  if (hdr[WH_RS_NEED] == 0) return;
+  int K = 0;
+  for (int e2 = C.grp0; e2 < C.grp1; e2++) { const int k2 = ((const int*)(as_shared(C.ws) + (long)e2 * sc.w_total))[sc.W_HDR + WH_RS_NEED]; K = k2 > K ? k2 : K; }
+  const int nu = hdr[WH_RS_NU], nk = 6 * sc.ncons;
+  const RsLayout L = rs_layout(K, nu, nk, ncr / 3);
+  if (L.Rp > sc.rs_cap) return;   // (a neighbour's K pads this environment beyond the capacity: dv-space sweeps, WH_RS_R stays 0)
+  if (ln == 0) { hdr[WH_RS_R] = L.Rp; hdr[WH_RS_K] = K; }
   float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);
+  for (int p = ln; p < L.Rp; p += nt) if (!rs_real(L, p)) { float* rc = REC + RR_W * p; st4(rc, 0.f, 0.f, 0.f, 0.f); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float(-1)); }
   int r = 0;
   for (int di = 0; di < sc.ndyn; di++) {
     const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[di]; const int n = WSI(C)[sc.W_UCNT + di];
@@ -1034,8 +1075,8 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   }
   // fixed constraints between models (model.py:69-77): three point rows along the world axes, three angular rows
   for (int kr = 0; kr < nk; kr++) {
-    const int r2 = nu + kr;
-    if (r2 % nt != ln) continue;
+    const int r2 = L.P1 + kr;
+    if (kr % nt != ln) continue;
     const int kc = kr / 6, i = kr % 6;
     const int* ci = gc(sc.cons_i) + DG_CONS_I_W * kc; const float* cf = gc(sc.cons_f) + DG_CONS_F_W * kc;
     const int fa = ci[0], fb = ci[1], ba = body_of_frame(C, fa), bb = body_of_frame(C, fb);
@@ -1067,9 +1108,10 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     float* rc = REC + RR_W * r2;
     st4(rc, (-rel - err * sc.erp / hsub) * dinv, dinv, -lim, lim); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float(RS_CONTACT | 0xffff));
   }
+  const int nc = ncr / 3;
   for (int rr = 0; rr < ncr; rr++) {
-    const int r2 = nu + nk + rr;
-    if (r2 % nt != ln) continue;
+    const int r2 = rr < nc ? L.nrm0 + rr : L.P2 + (rr - nc);
+    if (rr % nt != ln) continue;
     const float* row = WSP(C, sc.X_CROW) + sc.crow_stride * rr; const float* J = row + CR_HDR; const float* M = J + sc.GP;
     const int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
     float* Jd = RSV + (size_t)r2 * 2 * GV; float* Md = Jd + GV;
@@ -1081,20 +1123,22 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], 0.f, int_as_float(RS_CONTACT | rr));
   }
 }
-// A[r * stride + s] = J_s M^-1 J_r^T for r < R, s < R; zero for the padding s in [R, roundup(R, nt))
+// A[p * cap + s] = J_s M^-1 J_p^T for real positions p, s < Rp; zero rows / columns for the padding positions and for the
+// columns up to K nt that the lanes of the sweeps read
 DG_FN void phase_rs_build(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
-  const int R = WSI(C)[sc.W_HDR + WH_RS_R], Rp = (R + nt - 1) / nt * nt, GV = sc.GV; int cap;
-  const float* RSV = WSG(C, sc.X_RSV); float* A = rs_amat(C, R, Rp, &cap);
-  for (int r = 0; r < R; r++) {
-    const float* Md = RSV + (size_t)r * 2 * GV + GV;
-    for (int s2 = ln; s2 < Rp; s2 += nt) {
+  const RsLayout L = rs_layout_of(C); const int GV = sc.GV, cap = sc.rs_cap;
+  int ncol = L.K * nt; if (ncol > cap) ncol = cap; if (ncol < L.Rp) ncol = L.Rp;
+  const float* RSV = WSG(C, sc.X_RSV); float* A = WSG(C, sc.X_RSA);
+  for (int p = 0; p < L.Rp; p++) {
+    const float* Md = RSV + (size_t)p * 2 * GV + GV; const bool rp = rs_real(L, p);
+    for (int s2 = ln; s2 < ncol; s2 += nt) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      if (s2 < R) {
+      if (rp && s2 < L.Rp && rs_real(L, s2)) {
         const float* Jd = RSV + (size_t)s2 * 2 * GV;
         for (int c = 0; c < GV; c += 4) { const F4 jv = ld4(Jd + c), mv = ld4(Md + c); a0 = fmaf(jv.x, mv.x, a0); a1 = fmaf(jv.y, mv.y, a1); a2 = fmaf(jv.z, mv.z, a2); a3 = fmaf(jv.w, mv.w, a3); }
       }
-      A[r * cap + s2] = (a0 + a1) + (a2 + a3);
+      A[p * cap + s2] = (a0 + a1) + (a2 + a3);
     }
   }
 }
@@ -1102,94 +1146,92 @@ DG_FN void phase_rs_build(const Env& C, int ln, int nt) {
 // into their row records (phase_integrate reports them)
 DG_FN void phase_rs_finish(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
-  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], GV = sc.GV;
+  const RsLayout L = rs_layout_of(C); const int GV = sc.GV;
   const float* RSV = WSG(C, sc.X_RSV); const float* REC = WSG(C, sc.X_RSREC); float* dv = WSH(C, sc.W_DV);
   for (int i = ln; i < GV; i += nt) {
     float sum = 0.f;
-    for (int r = 0; r < R; r++) sum = fmaf(RSV[(size_t)r * 2 * GV + GV + i], REC[RR_W * r + RR_APPLIED], sum);
+    for (int p = 0; p < L.Rp; p++) if (rs_real(L, p)) sum = fmaf(RSV[(size_t)p * 2 * GV + GV + i], REC[RR_W * p + RR_APPLIED], sum);
     dv[i] = sum;
   }
-  for (int r = ln; r < nu; r += nt) {
+  for (int r = ln; r < L.nu; r += nt) {
     const int v = float_as_int(REC[RR_W * r + RR_ID]); const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[(v >> 16) & 0x3fff];
     (WSH(C, sc.X_UROW) + UR_W * (bp[BP_UROW] + (v & 0xffff)))[UR_APPLIED] = REC[RR_W * r + RR_APPLIED];
   }
 }
 #if defined(__CUDA_ARCH__) && defined(DG_STEP_T)
 // The sweeps.  Called with the REMAPPED thread layout: the NT lanes of a team are consecutive threads of one warp
-// (l = lane in team), every thread of the warp takes part in every shuffle, and every loop bound is warp-uniform
-// (maxima / minima over the teams of the warp); a team is masked off outside its own row ranges.  One update is
-// branch-free: every lane evaluates the clamp of ITS row (k, l), the owner's result is picked by the shuffle.
-// FULL: every warp of the block has 32 threads, so the shuffles take the literal full mask; a mask held in a register makes
-// nvcc guard every shuffle with MATCH.ANY + REDUX + VOTE + a divergence branch (~250 cycles per row, profiles/r1_phase_probe.log).
+// (l = lane in team), every thread of the warp takes part in every shuffle and runs the same sequence of (block, slot)
+// steps: the block COUNT of a section is the maximum over the teams of the warp, a team that has fewer blocks idles through
+// the surplus steps (no owner, zero broadcast).  FULL: every warp of the block has 32 threads, so the shuffles take the
+// literal full mask; a mask held in a register makes nvcc guard every shuffle with MATCH.ANY + REDUX + VOTE.
+template <int K> struct RsRow { float v[K]; };
+template <int K> __device__ __forceinline__ RsRow<K> rs_ldrow(const float* p) {
+  RsRow<K> r;
+  if constexpr (K == 2) { const float2 v = *reinterpret_cast<const float2*>(p); r.v[0] = v.x; r.v[1] = v.y; }
+  else {
+#pragma unroll
+    for (int c = 0; c < K / 4; c++) { const float4 v = *reinterpret_cast<const float4*>(p + 4 * c); r.v[4 * c] = v.x; r.v[4 * c + 1] = v.y; r.v[4 * c + 2] = v.z; r.v[4 * c + 3] = v.w; }
+  }
+  return r;
+}
 template <int K, int NT, bool FULL>
-__device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsigned wmask_rt, const int R, const int nu, const int nc) {
+__device__ __noinline__ void rs_solve_team(const Env& C, const int l, const unsigned wmask_rt, const RsLayout L) {
   const unsigned wmask = FULL ? 0xffffffffu : wmask_rt;
   const DevScene& sc = SC;
-  const int tbase = (threadIdx.x & 31) & ~(NT - 1); int cap;
-  float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + NT - 1) / NT * NT, &cap) + l; float* capp = WSH(C, sc.W_CAPP);
+  const int tbase = (threadIdx.x & 31) & ~(NT - 1), cap = sc.rs_cap;
+  float* REC = WSG(C, sc.X_RSREC); const float* Al = WSG(C, sc.X_RSA) + l * K; float* capp = WSH(C, sc.W_CAPP);
   float rhs[K], dinv[K], lo[K], hi[K], ap[K], y[K], mu[K]; int par[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
     rhs[k] = 0.f; dinv[k] = 0.f; lo[k] = 0.f; hi[k] = 0.f; ap[k] = 0.f; y[k] = 0.f; mu[k] = 0.f; par[k] = -1;
-    const int r = k * NT + l;
-    if (r < R) { const F4 r0 = ld4(REC + RR_W * r), r1 = ld4(REC + RR_W * r + 4); rhs[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
+    const int p = l * K + k;
+    if (p < L.Rp) { const F4 r0 = ld4(REC + RR_W * p), r1 = ld4(REC + RR_W * p + 4); rhs[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
   }
-  const int nk = 6 * sc.ncons, nn = nu + nk + nc, big = 1 << 28, rlast = R > 0 ? R - 1 : 0;
-  const int nu_max = __reduce_max_sync(wmask, nu), nn_max = __reduce_max_sync(wmask, nn), R_max = __reduce_max_sync(wmask, R);
-  const int nu_min = __reduce_min_sync(wmask, R > 0 ? nu : big), nn_min = __reduce_min_sync(wmask, R > 0 ? nn : big);
-  // one Gauss-Seidel update of row r = k NT + j.  Rows outside [first, last) of this team get d = 0; their A row is
-  // read from a clamped (written) row, so the product is an exact zero.  Columns beyond the team's own padding only
-  // feed y slots that belong to no row.
-#define DG_RS_UPDATE(k, j, r, first, last, normal)                                                             \
-  {                                                                                                            \
-    const float* Ar_ = A + min((r), rlast) * cap;                                                              \
-    float a_[K];                                                                                               \
-    _Pragma("unroll") for (int kk = 0; kk < K; kk++) a_[kk] = Ar_[kk * NT];                                    \
-    const float new_ = fminf(fmaxf(ap[k] + fmaf(-y[k], dinv[k], rhs[k]), lo[k]), hi[k]);                       \
-    const bool valid_ = (r) >= (first) && (r) < (last);                                                        \
-    float d_ = __shfl_sync(wmask, new_ - ap[k], tbase + (j));                                                  \
-    d_ = valid_ ? d_ : 0.f;                                                                                    \
-    if (valid_ && l == (j)) { ap[k] = new_; if ((normal) && (r) >= nu + nk) capp[(r) - nu - nk] = new_; }      \
-    _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(a_[kk], d_, y[kk]);                          \
+  // blocks per section of this team, and the step counts of the warp
+  const int nb1 = L.P1 / K, nb2 = (L.P2 - L.P1) / K, nb3 = (L.Rp - L.P2) / K, plast = L.Rp > 0 ? L.Rp - 1 : 0;
+  const int nb1m = __reduce_max_sync(wmask, nb1), nb2m = __reduce_max_sync(wmask, nb2), nb3m = __reduce_max_sync(wmask, nb3);
+  float bprev = 0.f; int pprev = 0;   // broadcast received one step ago and not yet folded into y, and its row
+  // one Gauss-Seidel update of position p = jt K + k (jt: block of this team, act: the team has this block).  HAND: first
+  // step of a block - the pending broadcast is folded in first, the new owner needs it.  Then every lane evaluates the clamp
+  // of ITS slot k; the owner keeps the result, folds its own d into its y at once (the next row's y is its own register) and
+  // broadcasts d; the other lanes fold the PREVIOUS broadcast (issued a step ago: no wait).
+#define DG_RS_STEP(jt_, act_, k, HAND, NORMAL)                                                                   \
+  {                                                                                                              \
+    const int jc_ = (jt_) < NT ? (jt_) : NT - 1;                                                                 \
+    const int p_ = min(jc_ * K + (k), plast);                                                                    \
+    const bool own_ = (act_) && l == (jt_);                                                                      \
+    if (HAND) {                                                                                                  \
+      const RsRow<K> h_ = rs_ldrow<K>(Al + pprev * cap);                                                         \
+      _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(h_.v[kk], bprev, y[kk]);                     \
+      bprev = 0.f;                                                                                               \
+    }                                                                                                            \
+    const RsRow<K> a_ = rs_ldrow<K>(Al + (own_ ? p_ : pprev) * cap);                                             \
+    const float new_ = fminf(fmaxf(ap[k] + fmaf(-y[k], dinv[k], rhs[k]), lo[k]), hi[k]);                         \
+    const float dl_ = own_ ? new_ - ap[k] : 0.f;                                                                 \
+    if (own_) { ap[k] = new_; if ((NORMAL) && p_ >= L.nrm0 && p_ < L.nrm1) capp[p_ - L.nrm0] = new_; }           \
+    const float b_ = __shfl_sync(wmask, dl_, tbase + jc_);                                                       \
+    const float cf_ = own_ ? dl_ : bprev;                                                                        \
+    _Pragma("unroll") for (int kk = 0; kk < K; kk++) y[kk] = fmaf(a_.v[kk], cf_, y[kk]);                         \
+    bprev = own_ ? 0.f : b_; pprev = p_;                                                                         \
   }
-  // The slots of a block of NT rows are unrolled and branch-free (a block is skipped as a whole when no team of the warp
-  // has a row of the pass in it; inside, rows outside a team's range are masked): the per-slot loop branches cost more
-  // than the masked slots (ur_gripper 0.59 -> 0.48 ms, basic_env 0.106 -> 0.084 ms of sweeps per launch).  Teams of 16 / 32 lanes
-  // keep the slot loop rolled: unrolling them costs minutes of compile time for team sizes no example scene selects.
-  // (Fetching row r of A one slot ahead was measured: no change.)
+#define DG_RS_BLOCK_FWD(jt_, act_, NORMAL)                                                                       \
+  { _Pragma("unroll") for (int k = 0; k < K; k++) { if (k == 0) DG_RS_STEP(jt_, act_, k, true, NORMAL) else DG_RS_STEP(jt_, act_, k, false, NORMAL) } }
+#define DG_RS_BLOCK_REV(jt_, act_)                                                                               \
+  { _Pragma("unroll") for (int k = K - 1; k >= 0; k--) { if (k == K - 1) DG_RS_STEP(jt_, act_, k, true, false) else DG_RS_STEP(jt_, act_, k, false, false) } }
   for (int it = 0; it < sc.iters; it++) {
-    if (it & 1) {
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        if (k * NT >= nu_max) break;
-        _Pragma("unroll (NT <= 8 ? NT : 1)") for (int j = 0; j < NT; j++) { const int r = k * NT + j; DG_RS_UPDATE(k, j, r, 0, nu, false) }
-      }
-    } else {
-#pragma unroll
-      for (int k = K - 1; k >= 0; k--) {
-        if (k * NT >= nu_max) continue;
-        _Pragma("unroll (NT <= 8 ? NT : 1)") for (int j = NT - 1; j >= 0; j--) { const int r = k * NT + j; DG_RS_UPDATE(k, j, r, 0, nu, false) }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if (k * NT >= nn_max) break;
-      if ((k + 1) * NT <= nu_min) continue;
-      _Pragma("unroll (NT <= 8 ? NT : 1)") for (int j = 0; j < NT; j++) { const int r = k * NT + j; DG_RS_UPDATE(k, j, r, nu, nn, true) }
-    }
+    if (it & 1) { for (int jj = 0; jj < nb1m; jj++) DG_RS_BLOCK_FWD(jj, jj < nb1, false) }
+    else { for (int jj = nb1m - 1; jj >= 0; jj--) DG_RS_BLOCK_REV(jj, jj < nb1) }
+    for (int jj = 0; jj < nb2m; jj++) DG_RS_BLOCK_FWD(nb1 + jj, jj < nb2, true)
     __syncwarp(wmask);
 #pragma unroll
     for (int k = 0; k < K; k++) if (par[k] >= 0) { hi[k] = mu[k] * capp[par[k]]; lo[k] = -hi[k]; }
-#pragma unroll
-    for (int k = 0; k < K; k++) {
-      if (k * NT >= R_max) break;
-      if ((k + 1) * NT <= nn_min) continue;
-      _Pragma("unroll (NT <= 8 ? NT : 1)") for (int j = 0; j < NT; j++) { const int r = k * NT + j; DG_RS_UPDATE(k, j, r, nn, R, false) }
-    }
+    for (int jj = 0; jj < nb3m; jj++) DG_RS_BLOCK_FWD(nb1 + nb2 + jj, jj < nb3, false)
   }
-#undef DG_RS_UPDATE
+#undef DG_RS_BLOCK_FWD
+#undef DG_RS_BLOCK_REV
+#undef DG_RS_STEP
 #pragma unroll
-  for (int k = 0; k < K; k++) { const int r = k * NT + l; if (r < R) REC[RR_W * r + RR_APPLIED] = ap[k]; }
+  for (int k = 0; k < K; k++) { const int p = l * K + k; if (p < L.Rp) REC[RR_W * p + RR_APPLIED] = ap[k]; }
 }
 // remaps the block's threads (thread t -> lane t % NT of the block's environment t / NT) and runs the sweeps
 template <int NT>
@@ -1202,17 +1244,18 @@ __device__ __forceinline__ void rs_solve_block(const Env& C) {
   const unsigned in_warp = blockDim.x - (threadIdx.x & ~31u);          // threads of this warp that exist
   const unsigned wmask = in_warp >= 32u ? 0xffffffffu : (1u << in_warp) - 1u;
   const int* hdr = WSI(C2) + sc.W_HDR;
-  const int R = hdr[WH_RS_R], nu = R > 0 ? hdr[WH_RS_NU] : 0, nc = R > 0 ? (R - nu - 6 * sc.ncons) / 3 : 0;   // (R == 0: slot without rows, its header may be stale)
-  const int R_max = __reduce_max_sync(wmask, R);
-  if (R_max > 0) {
-    const int kneed = (R_max + NT - 1) / NT;
+  const int R = hdr[WH_RS_R];
+  // (R == 0: slot without rows - its other header fields may be stale)
+  const RsLayout L = R > 0 ? rs_layout(hdr[WH_RS_K], hdr[WH_RS_NU], 6 * sc.ncons, hdr[WH_NCROW] / 3) : rs_layout(2, 0, 0, 0);
+  const int Kw = __reduce_max_sync(wmask, R > 0 ? L.K : 0);   // the same for every environment of the warp that has rows (phase_rs_setup)
+  if (Kw > 0) {
     if ((blockDim.x & 31u) == 0u) {
-      if (kneed <= 2) rs_solve_team<2, NT, true>(C2, l2, wmask, R, nu, nc);
-      else if (kneed <= 4) rs_solve_team<4, NT, true>(C2, l2, wmask, R, nu, nc);
-      else rs_solve_team<RS_KMAX, NT, true>(C2, l2, wmask, R, nu, nc);
+      if (Kw <= 2) rs_solve_team<2, NT, true>(C2, l2, wmask, L);
+      else if (Kw <= 4) rs_solve_team<4, NT, true>(C2, l2, wmask, L);
+      else rs_solve_team<RS_KMAX, NT, true>(C2, l2, wmask, L);
     } else {
-      if (kneed <= 4) rs_solve_team<4, NT, false>(C2, l2, wmask, R, nu, nc);
-      else rs_solve_team<RS_KMAX, NT, false>(C2, l2, wmask, R, nu, nc);
+      if (Kw <= 4) rs_solve_team<4, NT, false>(C2, l2, wmask, L);
+      else rs_solve_team<RS_KMAX, NT, false>(C2, l2, wmask, L);
     }
   }
   }
@@ -1222,25 +1265,26 @@ template <int NT> __device__ __forceinline__ void rs_solve_block(const Env&) {}
 #else
 // one-lane form of the same sweeps for the CPU emulation (tests/emul): identical row order and arithmetic
 DG_FN void rs_solve_serial(const Env& C, int nt) {
+  (void)nt;
   const DevScene& sc = SC;
-  const int R = WSI(C)[sc.W_HDR + WH_RS_R], nu = WSI(C)[sc.W_HDR + WH_RS_NU], nk = 6 * sc.ncons, nn = nu + nk + (R - nu - nk) / 3; int cap;
-  float* REC = WSG(C, sc.X_RSREC); const float* A = rs_amat(C, R, (R + nt - 1) / nt * nt, &cap); float* capp = WSH(C, sc.W_CAPP);
+  const RsLayout L = rs_layout_of(C); const int cap = sc.rs_cap;
+  float* REC = WSG(C, sc.X_RSREC); const float* A = WSG(C, sc.X_RSA); float* capp = WSH(C, sc.W_CAPP);
   float lo[RS_KMAX * 32], hi[RS_KMAX * 32], ap[RS_KMAX * 32], y[RS_KMAX * 32];
-  for (int r = 0; r < R; r++) { lo[r] = REC[RR_W * r + RR_LO]; hi[r] = REC[RR_W * r + RR_HI]; ap[r] = 0.f; y[r] = 0.f; }
-  auto update = [&](int r, bool normal) {
-    const float* rc = REC + RR_W * r;
-    const float nw = fminf(fmaxf(ap[r] + fmaf(-y[r], rc[RR_DINV], rc[RR_RHS]), lo[r]), hi[r]), d = nw - ap[r];
-    ap[r] = nw;
-    if (normal && r >= nu + nk) capp[r - nu - nk] = nw;
-    for (int s2 = 0; s2 < R; s2++) y[s2] = fmaf(A[r * cap + s2], d, y[s2]);
+  for (int p = 0; p < L.Rp; p++) { lo[p] = REC[RR_W * p + RR_LO]; hi[p] = REC[RR_W * p + RR_HI]; ap[p] = 0.f; y[p] = 0.f; }
+  auto update = [&](int p, bool normal) {
+    const float* rc = REC + RR_W * p;
+    const float nw = fminf(fmaxf(ap[p] + fmaf(-y[p], rc[RR_DINV], rc[RR_RHS]), lo[p]), hi[p]), d = nw - ap[p];
+    ap[p] = nw;
+    if (normal && p >= L.nrm0 && p < L.nrm1) capp[p - L.nrm0] = nw;
+    for (int s2 = 0; s2 < L.Rp; s2++) y[s2] = fmaf(A[p * cap + s2], d, y[s2]);
   };
   for (int it = 0; it < sc.iters; it++) {
-    if (it & 1) for (int r = 0; r < nu; r++) update(r, false); else for (int r = nu - 1; r >= 0; r--) update(r, false);
-    for (int r = nu; r < nn; r++) update(r, true);
-    for (int r = nn; r < R; r++) { hi[r] = REC[RR_W * r + RR_MU] * capp[float_as_int(REC[RR_W * r + RR_PAR])]; lo[r] = -hi[r]; }
-    for (int r = nn; r < R; r++) update(r, false);
+    if (it & 1) for (int p = 0; p < L.P1; p++) update(p, false); else for (int p = L.P1 - 1; p >= 0; p--) update(p, false);
+    for (int p = L.P1; p < L.P2; p++) update(p, true);
+    for (int p = L.P2; p < L.fr1; p++) { hi[p] = REC[RR_W * p + RR_MU] * capp[float_as_int(REC[RR_W * p + RR_PAR])]; lo[p] = -hi[p]; }
+    for (int p = L.P2; p < L.Rp; p++) update(p, false);
   }
-  for (int r = 0; r < R; r++) REC[RR_W * r + RR_APPLIED] = ap[r];
+  for (int p = 0; p < L.Rp; p++) REC[RR_W * p + RR_APPLIED] = ap[p];
 }
 #endif
 
@@ -1763,8 +1807,9 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
     } else {
       DG_PHASE(phase_contact_rows(C, ln, nt, h));
 #if defined(__CUDA_ARCH__)
-      if (!C.active && ln == 0) WSI(C)[sc.W_HDR + WH_RS_R] = 0;   // slots without an environment never wrote their header
+      if (!C.active && ln == 0) { WSI(C)[sc.W_HDR + WH_RS_R] = 0; WSI(C)[sc.W_HDR + WH_RS_NEED] = 0; }   // slots without an environment never wrote their header
 #endif
+      DG_PHASE(phase_rs_plan(C, ln, nt));
       DG_PHASE(phase_rs_setup(C, ln, nt));
       // environments with contacts: the whole team solves in row space (A is built here, swept below); contact-free ones
       // keep the register-resident per-body sweeps.  (WH_RS_R == 0 with contacts: dv-space sweeps, solver == 0 / too many rows)

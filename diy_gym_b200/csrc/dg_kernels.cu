@@ -44,6 +44,10 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
   C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * E + ei) * sc.g_total; C.seed = a.seed;
   C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg;
+  { // environments that share a warp once the row-space sweeps remap the threads (thread t -> lane t % T of environment t / T)
+    const int G = T >= 32 ? 1 : 32 / T, g0 = ei / G * G;
+    C.grp0 = g0 - ei; C.grp1 = (g0 + G < E ? g0 + G : E) - ei;
+  }
   // block-uniform trip count: every thread of the block walks the same number of environment groups
   for (int base = blockIdx.x * E; base < a.n_envs; base += gridDim.x * E) {
     const int e = base + ei;
@@ -335,8 +339,9 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
       team = coords > 12 ? 8 : 4;
       // fixed constraints between models ride on the row-space team solver, whose row capacity grows with the team
       const int32_t* hsec = ibuf + ibuf[2 + 3 * SEC_HDR_I + 1];
-      const int rows_max = 2 * hsec[HI_nd] + 3 * hsec[HI_max_contacts] + 6 * hsec[HI_ncons];
-      while (hsec[HI_ncons] > 0 && team < 32 && RS_KMAX * team < rows_max) team *= 2;
+      auto pad8 = [](int n) { return (n + RS_KMAX - 1) / RS_KMAX * RS_KMAX; };
+      const int rows_pad = pad8(2 * hsec[HI_nd]) + pad8(hsec[HI_max_contacts] + 6 * hsec[HI_ncons]) + pad8(2 * hsec[HI_max_contacts]);
+      while (hsec[HI_ncons] > 0 && team < 32 && RS_KMAX * team < rows_pad) team *= 2;
     }
     if (team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) team = 4;
   }
@@ -366,6 +371,7 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   // at least that many contact rows are solved in row space too (both kept for A/B measurements)
   if (const char* env_solver = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(env_solver) != 0;
   if (const char* env_min = getenv("DG_RS_MIN")) w->hs.dev.rs_min = atoi(env_min);
+  if (const char* env_pr = getenv("DG_PRECISE")) w->hs.dev.precise = atoi(env_pr) != 0;   // A/B of the SFU sincos in FK / IK (tools/qd_probe.py)
   {
     size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
     const int nl_ = w->hs.dev.nl;

@@ -19,7 +19,7 @@ enum { D_Q = 0, D_QD, D_APPLIED, D_TAU, D_COUNT };
 // body plan columns
 enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_NRS, BP_AOFF, BP_GS, BP_W };
 // workspace header ints
-enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_COUNT = 8 };
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_COUNT = 8 };
 // row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j
 enum { RS_CONTACT = 0x40000000, RS_KMAX = 8, RS_GVMAX = 128 };
 // row record of the row-space solver
@@ -72,6 +72,7 @@ struct DevScene {
   int rs_min;   // contact rows an uncoupled environment needs before the team solves it in row space (fewer: per-body sweeps)
   int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
+  int precise;  // 1: libm sincosf in FK / IK instead of the SFU approximation (scenes with fixed constraints; DG_PRECISE=0/1 overrides)
 };
 
 #define DG_SO(sc, name) ((sc)->so[HI_##name - HI_S_BPOS])
@@ -263,7 +264,8 @@ struct HostScene {
     for (int k = 0; k < d.npair; k++) GP = std::max(GP, gdim_of_shape(pair_i[2 * k]) + gdim_of_shape(pair_i[2 * k + 1]));
     int n_ik = 0;
     for (int k = 0; k < d.nop; k++) n_ik += op_i[DG_OP_I_W * k] == OP_IK_CTRL;
-    d.need_react = hi[HI_S_STEP] > hi[HI_S_JREACT];   // the state row holds reaction wrenches only when a sensor asked for them
+    d.need_react = hi[HI_S_STEP] > hi[HI_S_JREACT];
+    d.precise = d.ncons > 0;   // the state row holds reaction wrenches only when a sensor asked for them
 
     auto put_vi = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); ints.push_back(0); return o; };
     auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };
@@ -328,11 +330,15 @@ struct HostScene {
     phase_take(&d.X_MSCR, RC_SCRATCH, 1, d.mscr_stride * team);
     // row-space team solver: row table + dense A = J M^-1 J^T over all unit and contact rows of the environment
     d.GV = gv;
+    // (rows sit at positions of three sections - unit | constraint + normal | friction - each padded to the K rows a lane
+    // owns, K <= RS_KMAX: dg_env.cuh "row-space team solver")
     const int rows_max = 2 * d.nd + 3 * d.maxc + 6 * d.ncons;
-    d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min((rows_max + team - 1) / team * team, RS_KMAX * team) : 0;
-    if (d.ncons > 0 && d.rs_cap < rows_max) {
+    auto pad8 = [](int n) { return (n + RS_KMAX - 1) / RS_KMAX * RS_KMAX; };
+    const int rows_pad = pad8(2 * d.nd) + pad8(d.maxc + 6 * d.ncons) + pad8(2 * d.maxc);
+    d.rs_cap = (team > 1 && gv <= RS_GVMAX) ? std::min(rows_pad, RS_KMAX * team) : 0;
+    if (d.ncons > 0 && d.rs_cap < rows_pad) {
       error = "scenes with fixed constraints between models are solved by the row-space team solver: " + std::to_string(rows_max) +
-              " rows need a team of at least " + std::to_string((rows_max + RS_KMAX - 1) / RS_KMAX) + " lanes (and at most " + std::to_string((int)RS_GVMAX) + " generalized coordinates)";
+              " rows need a team of at least " + std::to_string((rows_pad + RS_KMAX - 1) / RS_KMAX) + " lanes (and at most " + std::to_string((int)RS_GVMAX) + " generalized coordinates)";
       return false;
     }
     d.solver = 1; d.rs_min = 1 << 20;   // measured (profiles/r1_rs_min_sweep.log): uncoupled environments are faster with the per-body sweeps

@@ -883,6 +883,12 @@ void dgo_ik(DgoWorld* W, int b, int ee_gl, const double* tpos_w, const double* t
       memcpy(J + 3 * ndb, Ja, sizeof(double) * 3 * (size_t)ndb);
       double qc[4], qci[4], dq[4]; mat_to_q(qc, R); qci[0] = -qc[0]; qci[1] = -qc[1]; qci[2] = -qc[2]; qci[3] = qc[3];
       q_mul(dq, tq, qci);
+      /* dq is normalised before the acos: for unit inputs (what the reference hands to pybullet: fp64 quaternions from
+         getLinkState x getQuaternionFromEuler) this changes nothing, but the parity protocol hands the oracle state rows
+         ROUNDED TO FP32, whose quaternions are off unit norm by ~6e-8, and d(acos w)/dw = 1/sin(angle/2) ~ 300 for the
+         0.4 deg rotations this controller asks for turns that into a 0.2 % error of the rotation vector (measured:
+         7e-4 rad on the wrist targets after 20 iterations, 5e-3 rad/s on qdot - profiles/r2_qd_probe_*.json) */
+      { double nq = sqrt(dq[0] * dq[0] + dq[1] * dq[1] + dq[2] * dq[2] + dq[3] * dq[3]); if (nq > 0) for (int i = 0; i < 4; i++) dq[i] /= nq; }
       double wq = dq[3] > 1 ? 1 : (dq[3] < -1 ? -1 : dq[3]);
       double ang = 2 * acos(wq), s2 = 1 - wq * wq, ax[3];
       if (s2 < 10 * 2.220446049250313e-16) v_set(ax, 1, 0, 0); else v_scale(ax, dq, 1.0 / sqrt(s2));

@@ -81,3 +81,62 @@ def mass_matrix_gravity_energy(sc, w, q, qd=None, g=(0, 0, -9.81), body=0):
         pot += -m * np.dot(g, coms[k].p)
     energy = pot + (0.5 * qd @ M @ qd if qd is not None else 0.0)
     return M, G, energy
+
+
+# ---------------------------------------------------------------- strict single-step parity protocol -----------------
+def strict_single_step_parity(env, n_envs, steps, seed=4321, presteps=3, action_scale=None):
+    """BASELINE.json north_star bar, exactly: every step BOTH arms start from the same fp32-rounded state row, take the same
+    action, and the states after ONE DIYGym.step are compared environment by environment:
+        |dq|  <= 1e-4 * max|q|            |dqd| <= 1e-4 * max(max|qd|, 1e-2)
+        base position / quaternion / linear / angular velocity of every body: 1e-4 relative to the largest entry of the
+        section (floors: 1e-2 for the twists, as for qd)
+    `env` is a DIYGym on either world (CUDA through the C ABI, or the CPU build of the kernel source in tests/emul).
+    Returns the per-step records (worst errors, bars, contact counts of the oracle) - the caller asserts."""
+    import torch
+    from oracle.oracle import OracleWorld
+    w, sc, h = env.world, env.scene, env.scene.hdr
+    nd, nb = sc['nd'], sc['nb']
+    cuda = w.state.is_cuda
+    if action_scale is None:
+        from bench import action_ranges
+        lo, hi = action_ranges(env)
+    else:
+        lo, hi = -action_scale * np.ones(max(sc['n_act'], 1))[:sc['n_act']], action_scale * np.ones(max(sc['n_act'], 1))[:sc['n_act']]
+    oracles = [OracleWorld(sc, seed=seed, env_id=i) for i in range(n_envs)]
+    rng = np.random.default_rng(seed)
+    for i, o in enumerate(oracles):
+        o.env_reset()
+        for _ in range(presteps + i % 4):      # decorrelate the environments
+            o.env_step(rng.uniform(lo, hi))
+    recs = []
+    for k in range(steps):
+        st = np.stack([o.state for o in oracles]).astype(np.float32)
+        w.state.copy_(torch.from_numpy(st))
+        w.param.copy_(torch.from_numpy(np.stack([o.param for o in oracles]).astype(np.float32)))
+        for i, o in enumerate(oracles):
+            o.state[:] = st[i]
+        a = rng.uniform(lo, hi, (n_envs, max(w.n_act, 1))).astype(np.float32)[:, :w.n_act]
+        if w.n_act:
+            w.action.copy_(torch.from_numpy(a))
+        w.step()
+        if cuda:
+            torch.cuda.synchronize()
+        outs = [o.env_step(a[i].astype(np.float64)) for i, o in enumerate(oracles)]
+        ncon = np.array([len(o.contacts()) for o in oracles])
+        sg = w.state.cpu().numpy().astype(np.float64)
+        so = np.stack([o.state for o in oracles])
+        rec = {'step': k, 'contacts': ncon, 'err': {}, 'bar': {}, 'err_free': {}}
+        free = ncon == 0
+        for key, nm, n, floor in (('q', 'S_Q', nd, 0.0), ('qd', 'S_QD', nd, 1e-2), ('base_pos', 'S_BPOS', 3 * nb, 0.0), ('base_quat', 'S_BQUAT', 4 * nb, 0.0),
+                                  ('base_vel', 'S_BVEL', 3 * nb, 1e-2), ('base_omega', 'S_BOMEGA', 3 * nb, 1e-2)):
+            if n == 0:
+                continue
+            g, o_ = sg[:, h[nm]:h[nm] + n], so[:, h[nm]:h[nm] + n]
+            rec['err'][key] = float(np.abs(g - o_).max())
+            rec['err_free'][key] = float(np.abs(g - o_)[free].max()) if free.any() else 0.0
+            rec['bar'][key] = 1e-4 * max(float(np.abs(o_).max()), floor)
+        rec['obs'] = (w.obs.cpu().numpy().astype(np.float64), np.stack([x[0] for x in outs]))
+        rec['rew'] = (w.reward.cpu().numpy().astype(np.float64), np.stack([x[1] for x in outs]))
+        rec['term'] = (w.term.cpu().numpy(), np.stack([x[2] for x in outs]))
+        recs.append(rec)
+    return recs

@@ -193,9 +193,15 @@ def test_example_configs_reset_and_step_match_oracle(name, scale):
         torch.cuda.synchronize()
         if nd:
             q_o, qd_o = np.stack([o.s('S_Q', nd) for o in oracles]), np.stack([o.s('S_QD', nd) for o in oracles])
-            assert np.abs(w.s('S_Q', nd).cpu().numpy() - q_o).max() <= 1e-4 * max(np.abs(q_o).max(), 1.0)
-            assert np.abs(w.s('S_QD', nd).cpu().numpy() - qd_o).max() <= 2e-4 * max(np.abs(qd_o).max(), 1.0)
-        assert np.allclose(w.s('S_BPOS', 3 * nb).cpu().numpy(), np.stack([o.s('S_BPOS', 3 * nb) for o in oracles]), rtol=1e-4, atol=1e-5)
+            # north_star bar (1e-4 relative, contact-free); scenes in contact: 150 clamped sweeps in fp32 vs fp64.  The strict
+            # protocol on >= 64 environments x 10 steps, base pose / twist included, is tests/test_strict_parity.py
+            free = not sc['ncons'] and all(len(o.contacts()) == 0 for o in oracles)
+            assert np.abs(w.s('S_Q', nd).cpu().numpy() - q_o).max() <= 1e-4 * (np.abs(q_o).max() if free else max(np.abs(q_o).max(), 1.0))
+            assert np.abs(w.s('S_QD', nd).cpu().numpy() - qd_o).max() <= (1e-4 * max(np.abs(qd_o).max(), 1e-2) if free else 2e-4 * max(np.abs(qd_o).max(), 1.0))
+        for nm, nn in (('S_BPOS', 3 * nb), ('S_BQUAT', 4 * nb)):
+            assert np.allclose(w.s(nm, nn).cpu().numpy(), np.stack([o.s(nm, nn) for o in oracles]), rtol=1e-4, atol=1e-5), nm
+        for nm, nn in (('S_BVEL', 3 * nb), ('S_BOMEGA', 3 * nb)):
+            assert np.allclose(w.s(nm, nn).cpu().numpy(), np.stack([o.s(nm, nn) for o in oracles]), rtol=1e-3, atol=2e-4), nm
         assert np.allclose(w.obs.cpu().numpy(), np.stack([x[0] for x in outs]), rtol=1e-4, atol=1e-4)
         assert np.allclose(w.reward.cpu().numpy(), np.stack([x[1] for x in outs]), rtol=1e-3, atol=1e-4)
         assert np.array_equal(w.term.cpu().numpy(), np.stack([x[2] for x in outs]))

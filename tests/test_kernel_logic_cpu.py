@@ -57,8 +57,10 @@ def test_reset_and_single_steps_match_oracle(name, scale, team):
         outs = [o.env_step(a[i]) for i, o in enumerate(oracles)]
         for i, o in enumerate(oracles):
             if nd:
-                assert np.abs(e.s('S_Q', nd, i) - o.s('S_Q', nd)).max() <= 1e-4 * max(np.abs(o.s('S_Q', nd)).max(), 1.0)
-                assert np.abs(e.s('S_QD', nd, i) - o.s('S_QD', nd)).max() <= 2e-4 * max(np.abs(o.s('S_QD', nd)).max(), 1.0)
+                # north_star bar (1e-4 relative, contact-free); environments in contact: 150 clamped sweeps in fp32 vs fp64
+                free = len(o.contacts()) == 0 and not sc['ncons']
+                assert np.abs(e.s('S_Q', nd, i) - o.s('S_Q', nd)).max() <= 1e-4 * (np.abs(o.s('S_Q', nd)).max() if free else max(np.abs(o.s('S_Q', nd)).max(), 1.0))
+                assert np.abs(e.s('S_QD', nd, i) - o.s('S_QD', nd)).max() <= (1e-4 * max(np.abs(o.s('S_QD', nd)).max(), 1e-2) if free else 2e-4 * max(np.abs(o.s('S_QD', nd)).max(), 1.0))
             assert np.allclose(e.s('S_BPOS', 3 * nb, i), o.s('S_BPOS', 3 * nb), rtol=1e-4, atol=1e-5)
             assert np.allclose(e.s('S_BQUAT', 4 * nb, i), o.s('S_BQUAT', 4 * nb), rtol=1e-4, atol=1e-5)
         assert np.allclose(obs_e, np.stack([x[0] for x in outs]), rtol=1e-4, atol=1e-4)

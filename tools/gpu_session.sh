@@ -1,0 +1,47 @@
+#!/bin/bash
+# One documented GPU session script (replaces the round-1 gpu_session_[a-k].sh scratch files).  Runs on the B200 box through
+#   gpurun --timeout <s> -- 'bash tools/gpu_session.sh <stage> [...]'
+# and writes everything under gpurun_out/<tag>/ (merged back into the build container).  Stages:
+#   tests            pytest -m gpu (log only)
+#   qd               tools/qd_probe.py, SFU and libm sincos
+#   bench <cfg...>   bench.py --config <cfg> (no CPU baseline), default solver and DG_RS_MIN A/B when RS_AB=1
+#   phase <cfg...>   tools/phase_probe.py
+#   ncu_step <cfg>   launch list + one --set full capture of dg_step_kernel
+#   ncu_render       launch list + one --set full capture of dg_render_kernel (from_the_readme)
+TAG=${TAG:-r2}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+stage=$1; shift
+case $stage in
+  tests)
+    python -m pytest tests -m gpu -q -x --timeout 1200 "$@" > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log; tail -5 $OUT/pytest_gpu.log ;;
+  qd)
+    python tools/qd_probe.py --envs 64 --steps 10 > $OUT/qd_probe_sfu.json 2> $OUT/qd_probe_sfu.err
+    DG_PRECISE=1 python tools/qd_probe.py --envs 64 --steps 10 > $OUT/qd_probe_libm.json 2> $OUT/qd_probe_libm.err
+    grep -A10 worst_over_steps $OUT/qd_probe_sfu.json | head -24; grep -A10 worst_over_steps $OUT/qd_probe_libm.json | head -24 ;;
+  bench)
+    for cfg in "$@"; do
+      python bench.py --config $cfg --steps ${STEPS:-20} --warmup 5 --no-cpu-baseline > $OUT/bench_${cfg}${SUFFIX}.json 2> $OUT/bench_${cfg}${SUFFIX}.err
+      python - <<PY
+import json
+try:
+    d = json.loads(open('$OUT/bench_${cfg}${SUFFIX}.json').read().strip().splitlines()[-1])
+    print('$cfg$SUFFIX', 'value %.4g' % d['value'], 'e2e %.4g' % d['e2e']['value'], 'kernel_ms %.4g' % d['roofline']['kernel_ms'], 'ms/step %.4g' % d['ms_per_step'], d['config'].get('team'), d['config'].get('block_threads'))
+except Exception as e:
+    print('$cfg$SUFFIX', 'FAILED', e); print(open('$OUT/bench_${cfg}${SUFFIX}.err').read()[-2000:])
+PY
+    done ;;
+  phase)
+    for cfg in "$@"; do python tools/phase_probe.py $cfg ${ENVS:-} > $OUT/phase_${cfg}${SUFFIX}.log 2>&1; head -14 $OUT/phase_${cfg}${SUFFIX}.log; done ;;
+  ncu_step)
+    cfg=$1
+    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/ncu_launches_${cfg}.csv python bench.py --config $cfg --steps 5 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_${cfg}.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:dg_step_kernel -s 40 -c 1 -o $OUT/ncu_full_${cfg} -f python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 60 > $OUT/ncu_full_${cfg}.log 2>&1
+    ncu -i $OUT/ncu_full_${cfg}.ncu-rep --page details > $OUT/ncu_details_${cfg}.txt 2>&1
+    ncu -i $OUT/ncu_full_${cfg}.ncu-rep --page raw --csv > $OUT/ncu_raw_${cfg}.csv 2>&1 ;;
+  ncu_render)
+    ncu --set full --clock-control none --import-source on -k regex:dg_render_kernel -s 2 -c 1 -o $OUT/ncu_full_render -f python tools/render_probe.py from_the_readme ${ENVS:-4096} > $OUT/ncu_full_render.log 2>&1
+    ncu -i $OUT/ncu_full_render.ncu-rep --page details > $OUT/ncu_details_render.txt 2>&1
+    ncu -i $OUT/ncu_full_render.ncu-rep --page raw --csv > $OUT/ncu_raw_render.csv 2>&1 ;;
+  *) echo "unknown stage $stage"; exit 2 ;;
+esac
