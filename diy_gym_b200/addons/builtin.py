@@ -81,6 +81,7 @@ class ExternalForce(_OpAddon):
 
 
 class InverseKinematicsController(_OpAddon):
+    resets_in_constructor = True   # ik_controller.py:45 calls self.reset(): a nested model is welded to the arm at its rest pose
     """`controllers/ik_controller.py`: end-effector pose delta -> damped-least-squares IK -> position motors."""
     def __init__(self, parent, config):
         super().__init__(parent, config)
@@ -352,6 +353,7 @@ class _Unsupported(Addon):
 
 
 class AdmittanceController(_OpAddon):
+    resets_in_constructor = True   # admittance_controller.py:34
     """`controllers/admittance_controller.py`: joint torques = F . J_lin + T . J_ang (Jacobian of the admittance point on the
     end effector) + gravity compensation + p_gain (target_pose - q) - d_gain qd; the default joint motors are switched off."""
     def __init__(self, parent, config):

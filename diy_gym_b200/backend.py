@@ -20,7 +20,7 @@ class DgBufferTable(ctypes.Structure):
 
 
 Q = dict(STATE_SIZE=0, PARAM_SIZE=1, N_ACT=2, N_OBS=3, N_REW=4, N_TERM=5, N_ENVS=6, TEAM=7, BLOCK_THREADS=8, GRID_BLOCKS=9,
-         SMEM_BYTES=10, WS_FLOATS=11, N_CAMERAS=12, LAUNCHES=13)
+         SMEM_BYTES=10, WS_FLOATS=11, N_CAMERAS=12, LAUNCHES=13, RS_ASHARED=14, SOLVER=15, MAX_CONTACTS=16, CONTACTS_DROPPED=17, SPLIT=18)
 
 
 def load_library():
@@ -44,7 +44,7 @@ def load_library():
     L.dg_bind_buffers.argtypes = [vp, ctypes.POINTER(DgBufferTable)]
     L.dg_set_seed.restype = ctypes.c_int
     L.dg_set_seed.argtypes = [vp, ctypes.c_uint32, ctypes.c_int]
-    for f in ('dg_init_state', 'dg_step'):
+    for f in ('dg_init_state', 'dg_step', 'dg_observe'):
         getattr(L, f).restype = ctypes.c_int
         getattr(L, f).argtypes = [vp, vp]
     L.dg_reset.restype = ctypes.c_int
@@ -95,6 +95,7 @@ class World:
         q = lambda k: int(L.dg_query(h, Q[k]))
         self.S, self.P, self.n_act, self.n_obs, self.n_rew, self.n_term = q('STATE_SIZE'), q('PARAM_SIZE'), q('N_ACT'), q('N_OBS'), q('N_REW'), q('N_TERM')
         self.team, self.block_threads, self.grid_blocks, self.smem_bytes, self.ws_floats = q('TEAM'), q('BLOCK_THREADS'), q('GRID_BLOCKS'), q('SMEM_BYTES'), q('WS_FLOATS')
+        self.split = bool(q('SPLIT'))
         N, dev = self.n_envs, self.device
         self.state = torch.zeros((N, self.S), dtype=torch.float32, device=dev)
         self.param = torch.zeros((N, self.P), dtype=torch.float32, device=dev)
@@ -136,6 +137,17 @@ class World:
 
     def step(self):
         self._check(self.L.dg_step(self._h, self._stream()))
+
+    def set_seed(self, seed, env_id_offset=0):
+        self._check(self.L.dg_set_seed(self._h, int(seed) & 0xffffffff, int(env_id_offset)))
+
+    def observe(self):
+        """Outputs (obs / reward / term) from the state rows as they are: link cache refresh + every sensor op, no physics."""
+        self._check(self.L.dg_observe(self._h, self._stream()))
+
+    def contacts_dropped(self):
+        """Contacts lost to the `max_contacts` capacity since creation (synchronises)."""
+        return int(self.L.dg_query(self._h, Q['CONTACTS_DROPPED']))
 
     def reset(self, mask=None):
         if mask is not None:

@@ -365,6 +365,11 @@ class SceneBuilder:
 
         # ---- ops ----------------------------------------------------------------------------------
         nop = len(self.ops)
+        # the per-step action mask (dg_set_action_mask: add-ons absent from the action dict are not updated, diy_gym.py:202-204)
+        # has 128 bits: an action-bearing op beyond them could not be switched off
+        for k, op in enumerate(self.ops):
+            if k >= 128 and op['n_act']:
+                raise ValueError('more than 128 add-on ops before an action-bearing one (op %d): the action mask has 128 bits' % k)
         op_i = np.zeros((nop, OP_I_W), np.int32)
         oparg_i, oparg_f = [], []
         n_act = n_obs = n_rew = n_term = 0

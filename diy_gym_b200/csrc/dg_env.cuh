@@ -37,6 +37,12 @@ struct Env {
   int grp0, grp1;     // environments of the block that share a warp in the row-space sweeps, as offsets (in workspaces) from this one: [grp0, grp1)
   unsigned long long opmask[2];   // bit k clear = action op k absent from this step's action dict (not updated)
   unsigned long long* dbg;        // phase timing (dg_debug_phase_cycles): [block][64] cycle sums keyed by source line & 63, or null
+  unsigned* dropped;              // contacts lost to the max_contacts cap since the world was created (one counter per world), or null
+  // split schedule (GPU only): the contact sweeps of this environment may be left to the sweep kernel (dg_solve_kernel)
+  int split;                      // 1: environments whose rows fit a warp are deferred to the sweep kernel
+  int* rs_list[2];                // deferred environments: <= 32 row positions | <= 64 (local indices), or null
+  int* rs_count;                  // [2] their counts (atomically incremented)
+  int e_local;                    // index of this environment in the launch
 };
 
 #define SC (*C.sc)
@@ -427,7 +433,7 @@ DG_FN void phase_shape_world(const Env& C, int ln, int nt) {
   }
   int nw = (sc.npair + 31) / 32;
   for (int i = ln; i < nw; i += nt) WSIP(C, sc.X_SURV)[i] = 0;
-  if (ln == 0) { WSI(C)[sc.W_HDR + WH_NCONTACT] = 0; }
+  if (ln == 0) { int* hdr = WSI(C) + sc.W_HDR; hdr[WH_NCONTACT] = 0; hdr[WH_RS_R] = 0; hdr[WH_RS_DEFER] = 0; }
 }
 DG_HD void ct_add(Ct* list, int* n, int cap, int fa, int fb, const float* pa, const float* pb, const float* nrm, float dist, float mu, float margin) {
   if (dist > margin || *n >= cap) return;
@@ -642,15 +648,36 @@ DG_FN void phase_narrow(const Env& C, int ln, int nt, int rnd) {
   }
   tmp[0] = int_as_float(n);
 }
+// Capacity max_contacts (YAML extension key; default 16 with a floating body, else 8, at most 21): when the list is full a
+// new contact replaces the SHALLOWEST stored one if it is deeper - what gets lost is a grazing contact, never the wall the
+// robot is pushing into - and every loss is counted (dg_query DG_Q_CONTACTS_DROPPED).  Same rule as the oracle.
 DG_FN void phase_append(const Env& C, int ln, int nt) {
   if (ln != 0) return;
   const DevScene& sc = SC;
-  int nc = WSI(C)[sc.W_HDR + WH_NCONTACT];
+  int nc = WSI(C)[sc.W_HDR + WH_NCONTACT], lost = 0;
   for (int l = 0; l < nt; l++) {
     const float* tmp = WSG(C, sc.X_CTMP) + sc.ctmp_stride * l; int n = float_as_int(tmp[0]);
-    for (int i = 0; i < n && nc < sc.maxc; i++, nc++) { float* dst = WSP(C, sc.X_CON) + CT_W * nc; const float* src = tmp + 1 + CT_W * i; for (int j = 0; j < CT_W; j++) dst[j] = src[j]; }
+    for (int i = 0; i < n; i++) {
+      const float* src = tmp + 1 + CT_W * i; float* dst;
+      if (nc < sc.maxc) dst = WSP(C, sc.X_CON) + CT_W * nc++;
+      else {
+        lost++;
+        int worst = 0; float wd = (WSP(C, sc.X_CON))[CT_DIST];
+        for (int j = 1; j < nc; j++) { const float dj = (WSP(C, sc.X_CON) + CT_W * j)[CT_DIST]; if (dj > wd) { wd = dj; worst = j; } }
+        if (nc == 0 || !(src[CT_DIST] < wd)) continue;
+        dst = WSP(C, sc.X_CON) + CT_W * worst;
+      }
+      for (int j = 0; j < CT_W; j++) dst[j] = src[j];
+    }
   }
   WSI(C)[sc.W_HDR + WH_NCONTACT] = nc;
+  if (lost && C.dropped) {
+#if defined(__CUDA_ARCH__)
+    atomicAdd(C.dropped, (unsigned)lost);
+#else
+    *C.dropped += (unsigned)lost;
+#endif
+  }
 }
 
 // ------------------------------------------------------------------ constraint rows ----------------------------
@@ -1039,9 +1066,18 @@ DG_FN void phase_rs_plan(const Env& C, int ln, int nt) {
   int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW];
   int nu = 0;
   for (int di = 0; di < sc.ndyn; di++) nu += WSI(C)[sc.W_UCNT + di];
-  const int nk = 6 * sc.ncons;
+  const int nk = 6 * sc.ncons, nc = ncr / 3;
   const bool want = sc.solver == 1 && nt >= 2 && (nk > 0 || (ncr > 0 && (hdr[WH_COUPLED] != 0 || ncr >= sc.rs_min)));
-  hdr[WH_RS_NU] = nu; hdr[WH_RS_NEED] = want ? rs_kneed(nu, nk, ncr / 3, nt, sc.rs_cap) : 0; hdr[WH_RS_R] = 0;
+  hdr[WH_RS_NU] = nu; hdr[WH_RS_R] = 0; hdr[WH_RS_DEFER] = 0;
+  int need = want ? rs_kneed(nu, nk, nc, nt, sc.rs_cap) : 0;
+  if (want && C.split) {
+    // the sweep kernel gives an environment a half warp (<= 32 row positions) or a whole one (<= 64), two rows per lane: its
+    // layout is the K = 2 one; WH_RS_DEFER = 1 / 2 names the list (dg_kernels.cu, dg_solve_kernel)
+    const int t2 = rs_total(nu, nk, nc, 2);
+    const int cls = t2 > sc.rs_cap ? 0 : (t2 <= RS_WARP_R1 ? 1 : (t2 <= RS_WARP_R2 ? 2 : 0));
+    if (cls) { need = 2; hdr[WH_RS_DEFER] = cls; }
+  }
+  hdr[WH_RS_NEED] = need;
 }
 // row records + dense vectors, lane per row.  K is the largest need among the environments that share a warp in the sweeps
 // (C.grp0 .. C.grp1: their workspaces sit at multiples of w_total from this one), so that the warp runs one instantiation.
@@ -1050,11 +1086,21 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   int* hdr = WSI(C) + sc.W_HDR; const int ncr = hdr[WH_NCROW], GV = sc.GV;
   if (hdr[WH_RS_NEED] == 0) return;
   int K = 0;
-  for (int e2 = C.grp0; e2 < C.grp1; e2++) { const int k2 = ((const int*)(as_shared(C.ws) + (long)e2 * sc.w_total))[sc.W_HDR + WH_RS_NEED]; K = k2 > K ? k2 : K; }
+  const bool defer = hdr[WH_RS_DEFER] != 0;   // swept by its own warp in the sweep kernel: its own K
+  if (defer) K = hdr[WH_RS_NEED];
+  else for (int e2 = C.grp0; e2 < C.grp1; e2++) {
+    const int* h2 = (const int*)(as_shared(C.ws) + (long)e2 * sc.w_total) + sc.W_HDR;
+    const int k2 = h2[WH_RS_DEFER] ? 0 : h2[WH_RS_NEED]; K = k2 > K ? k2 : K;
+  }
   const int nu = hdr[WH_RS_NU], nk = 6 * sc.ncons;
   const RsLayout L = rs_layout(K, nu, nk, ncr / 3);
   if (L.Rp > sc.rs_cap) return;   // (a neighbour's K pads this environment beyond the capacity: dv-space sweeps, WH_RS_R stays 0)
-  if (ln == 0) { hdr[WH_RS_R] = L.Rp; hdr[WH_RS_K] = K; }
+  if (ln == 0) {
+    hdr[WH_RS_R] = L.Rp; hdr[WH_RS_K] = K;
+#if defined(__CUDA_ARCH__)
+    if (defer) { const int cls = hdr[WH_RS_DEFER] - 1; const int slot = atomicAdd(C.rs_count + cls, 1); C.rs_list[cls][slot] = C.e_local; }
+#endif
+  }
   float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);
   for (int p = ln; p < L.Rp; p += nt) if (!rs_real(L, p)) { float* rc = REC + RR_W * p; st4(rc, 0.f, 0.f, 0.f, 0.f); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float(-1)); }
   int r = 0;
@@ -1244,7 +1290,7 @@ __device__ __forceinline__ void rs_solve_block(const Env& C) {
   const unsigned in_warp = blockDim.x - (threadIdx.x & ~31u);          // threads of this warp that exist
   const unsigned wmask = in_warp >= 32u ? 0xffffffffu : (1u << in_warp) - 1u;
   const int* hdr = WSI(C2) + sc.W_HDR;
-  const int R = hdr[WH_RS_R];
+  const int R = hdr[WH_RS_DEFER] ? 0 : hdr[WH_RS_R];   // deferred environments are swept by the sweep kernel
   // (R == 0: slot without rows - its other header fields may be stale)
   const RsLayout L = R > 0 ? rs_layout(hdr[WH_RS_K], hdr[WH_RS_NU], 6 * sc.ncons, hdr[WH_NCROW] / 3) : rs_layout(2, 0, 0, 0);
   const int Kw = __reduce_max_sync(wmask, R > 0 ? L.K : 0);   // the same for every environment of the warp that has rows (phase_rs_setup)
@@ -1784,62 +1830,91 @@ DG_HD bool block_any(bool p, int) { return p; }
 #endif
 #define HDRV(k) (C.active ? WSI(C)[SC.W_HDR + (k)] : 0)
 
+// One sub-step up to and including the contact solve of every environment that is not deferred to the sweep kernel
+DG_NOINLINE DG_FN void physics_pre(const Env& C, int nt, float h, DG_LANE_ARGS) {
+  const DevScene& sc = SC;
+  DG_PHASE(phase_dynamics(C, ln, nt, h));
+  DG_PHASE(phase_shape_world(C, ln, nt));
+  if (sc.npair > 0) {
+    DG_PHASE(phase_broad(C, ln, nt));
+    DG_PHASE(phase_count_survivors(C, ln, nt));
+    for (int rnd = 0; block_any(rnd * nt < HDRV(WH_NSURV), nt); rnd++) {
+      DG_PHASE(phase_narrow(C, ln, nt, rnd));
+      DG_PHASE(phase_append(C, ln, nt));
+    }
+  }
+  DG_PHASE(phase_minv(C, ln, nt));
+  DG_PHASE(phase_unit_rows(C, ln, nt, h));
+  if (sc.ncons == 0 && !block_any(HDRV(WH_NCROW) > 0, nt)) {
+    DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
+  } else {
+    DG_PHASE(phase_contact_rows(C, ln, nt, h));
+#if defined(__CUDA_ARCH__)
+    if (!C.active && ln == 0) { WSI(C)[sc.W_HDR + WH_RS_R] = 0; WSI(C)[sc.W_HDR + WH_RS_NEED] = 0; WSI(C)[sc.W_HDR + WH_RS_DEFER] = 0; }   // slots without an environment never wrote their header
+#endif
+    DG_PHASE(phase_rs_plan(C, ln, nt));
+    DG_PHASE(phase_rs_setup(C, ln, nt));
+    // environments with contacts: solved in row space (A is built here; swept below by the team, or - deferred - by a warp of the
+    // sweep kernel); contact-free ones keep the register-resident per-body sweeps.  (WH_RS_R == 0 with contacts: dv-space sweeps,
+    // solver == 0 / too many rows)
+    DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_build(C, ln, nt);
+             else if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
+    if (sc.solver == 1 && nt > 1 && block_any(HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) == 0, nt)) {
+#if defined(__CUDA_ARCH__)
+      const long long t0_ = C.dbg ? clock64() : 0;
+#if defined(DG_STEP_T)
+      rs_solve_block<DG_STEP_T>(C);
+#endif
+      __syncthreads();
+      if (C.dbg && threadIdx.x == 0) C.dbg[(size_t)blockIdx.x * 64 + (__LINE__ & 63)] += (unsigned long long)(clock64() - t0_);
+#else
+      DG_PHASE(if (ln == 0 && HDRV(WH_RS_R) > 0) rs_solve_serial(C, nt));
+#endif
+      DG_PHASE(if (HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) == 0) phase_rs_finish(C, ln, nt));
+    }
+    if (block_any(HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0, nt)) {   // dv-space, coupled bodies: lock-step sweeps
+      for (int it = 0; it < sc.iters; it++) {
+        DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_unit(C, ln, nt, it, it + 1));
+        DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_contact(C, ln, nt));
+      }
+    }
+  }
+}
+// ... and the rest of it: impulses of the deferred environments (swept by the sweep kernel in between) folded into dv, integration
+DG_NOINLINE DG_FN void physics_post(const Env& C, int nt, float h, DG_LANE_ARGS) {
+  if (SC.solver == 1 && nt > 1 && C.split) DG_PHASE(if (HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) != 0) phase_rs_finish(C, ln, nt));
+  DG_PHASE(phase_integrate(C, ln, nt, h));
+}
 // p.stepSimulation() (diy_gym.py:146,207); nsub = 0 only refreshes the link cache
 DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {
   const DevScene& sc = SC;
   float h = sc.dt / (float)sc.substeps;
   DG_PHASE(phase_load(C, ln, nt));
   for (int sub = 0; sub < nsub; sub++) {
-    DG_PHASE(phase_dynamics(C, ln, nt, h));
-    DG_PHASE(phase_shape_world(C, ln, nt));
-    if (sc.npair > 0) {
-      DG_PHASE(phase_broad(C, ln, nt));
-      DG_PHASE(phase_count_survivors(C, ln, nt));
-      for (int rnd = 0; block_any(rnd * nt < HDRV(WH_NSURV), nt); rnd++) {
-        DG_PHASE(phase_narrow(C, ln, nt, rnd));
-        DG_PHASE(phase_append(C, ln, nt));
-      }
-    }
-    DG_PHASE(phase_minv(C, ln, nt));
-    DG_PHASE(phase_unit_rows(C, ln, nt, h));
-    if (sc.ncons == 0 && !block_any(HDRV(WH_NCROW) > 0, nt)) {
-      DG_PHASE(phase_pgs_unit(C, ln, nt, 0, sc.iters));
-    } else {
-      DG_PHASE(phase_contact_rows(C, ln, nt, h));
 #if defined(__CUDA_ARCH__)
-      if (!C.active && ln == 0) { WSI(C)[sc.W_HDR + WH_RS_R] = 0; WSI(C)[sc.W_HDR + WH_RS_NEED] = 0; }   // slots without an environment never wrote their header
-#endif
-      DG_PHASE(phase_rs_plan(C, ln, nt));
-      DG_PHASE(phase_rs_setup(C, ln, nt));
-      // environments with contacts: the whole team solves in row space (A is built here, swept below); contact-free ones
-      // keep the register-resident per-body sweeps.  (WH_RS_R == 0 with contacts: dv-space sweeps, solver == 0 / too many rows)
-      DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_build(C, ln, nt);
-               else if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
-      if (sc.solver == 1 && nt > 1) {
-#if defined(__CUDA_ARCH__)
-        const long long t0_ = C.dbg ? clock64() : 0;
-#if defined(DG_STEP_T)
-        rs_solve_block<DG_STEP_T>(C);
-#endif
-        __syncthreads();
-        if (C.dbg && threadIdx.x == 0) C.dbg[(size_t)blockIdx.x * 64 + (__LINE__ & 63)] += (unsigned long long)(clock64() - t0_);
+    physics_pre(C, nt, h, ln); physics_post(C, nt, h, ln);
 #else
-        DG_PHASE(if (ln == 0 && HDRV(WH_RS_R) > 0) rs_solve_serial(C, nt));
+    physics_pre(C, nt, h, 0); physics_post(C, nt, h, 0);
 #endif
-        DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_finish(C, ln, nt));
-      }
-      if (block_any(HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0, nt)) {   // dv-space, coupled bodies: lock-step sweeps
-        for (int it = 0; it < sc.iters; it++) {
-          DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_unit(C, ln, nt, it, it + 1));
-          DG_PHASE(if (HDRV(WH_COUPLED) != 0 && HDRV(WH_RS_R) == 0) phase_pgs_contact(C, ln, nt));
-        }
-      }
-    }
-    DG_PHASE(phase_integrate(C, ln, nt, h));
   }
   DG_PHASE(phase_final_kin(C, ln, nt));
   DG_PHASE(phase_store(C, ln, nt, clear_forces));
 }
+#if defined(__CUDA_ARCH__)
+// One DIYGym.step cut into kernel launches around the sweep kernel (dg_kernels.cu, "split schedule"):
+//   ST_ACT  add-on update + state row -> workspace      ST_PRE  physics_pre of one sub-step
+//   ST_POST physics_post of one sub-step                ST_END  link cache + state row back, sensors / rewards / terminals
+// The hot workspace travels between launches through the per-environment carry buffer (ST_SAVEC / ST_LOADC, done by the
+// kernel around this call); the cold workspace is per environment anyway.
+DG_FN void run_env_step_stages(const Env& C, int nt, int stages, int ln) {
+  const DevScene& sc = SC;
+  const float h = sc.dt / (float)sc.substeps;
+  if (stages & ST_ACT) { DG_PHASE(phase_actions(C, ln, nt)); DG_PHASE(phase_load(C, ln, nt)); }
+  if (stages & ST_POST) physics_post(C, nt, h, ln);
+  if (stages & ST_PRE) physics_pre(C, nt, h, ln);
+  if (stages & ST_END) { DG_PHASE(phase_final_kin(C, ln, nt)); DG_PHASE(phase_store(C, ln, nt, 1)); DG_PHASE(phase_observe(C, ln, nt)); }
+}
+#endif
 
 // DIYGym.step for one environment
 DG_FN void run_env_step(const Env& C, int nt, DG_LANE_ARGS) {
@@ -1852,6 +1927,16 @@ DG_FN void run_env_step(const Env& C, int nt, DG_LANE_ARGS) {
   run_physics(C, nt, SC.substeps, 1, 0);
   DG_PHASE(phase_observe(C, ln, nt));
 #endif
+}
+// DIYGym.observe / reward / is_terminal from the state rows as they are (diy_gym.py:211-222): refreshes the link cache the
+// sensors read (no physics), then evaluates every sensor / reward / terminal op
+DG_FN void run_env_observe(const Env& C, int nt, DG_LANE_ARGS) {
+#if defined(__CUDA_ARCH__)
+  run_physics(C, nt, 0, 0, ln);
+#else
+  run_physics(C, nt, 0, 0, 0);
+#endif
+  DG_PHASE(phase_observe(C, ln, nt));
 }
 // DIYGym.reset for one environment
 DG_FN void run_env_reset(const Env& C, int nt, DG_LANE_ARGS) {

@@ -24,6 +24,10 @@ struct LaunchArgs {
   unsigned long long opmask[2];
   float* gws;   // cold workspace: one slot of sc.g_total floats per resident team
   unsigned long long* dbg;   // phase-timing table or null (dg_debug_phase_cycles)
+  unsigned* dropped;         // contacts lost to the max_contacts cap (one counter per world)
+  // split schedule (mode 0 only): which stages of the step this launch runs (ST_*), the per-environment carry of the hot
+  // workspace between launches, and the lists of environments left to the sweep kernel
+  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count;
 };
 
 template <int T>
@@ -42,8 +46,9 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   for (int i = threadIdx.x; i < 16 * sc.nl; i += blockDim.x) s_link_x[i] = sc.link_x[i];
   __syncthreads();
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
-  C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.wg = a.gws + ((size_t)blockIdx.x * E + ei) * sc.g_total; C.seed = a.seed;
-  C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg;
+  C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.seed = a.seed;
+  C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg; C.dropped = a.dropped;
+  C.split = (a.mode == 0 && a.stages != ST_ALL) ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count;
   { // environments that share a warp once the row-space sweeps remap the threads (thread t -> lane t % T of environment t / T)
     const int G = T >= 32 ? 1 : 32 / T, g0 = ei / G * G;
     C.grp0 = g0 - ei; C.grp1 = (g0 + G < E ? g0 + G : E) - ei;
@@ -55,9 +60,27 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
     const int ec = e < a.n_envs ? e : a.n_envs - 1;
     C.st = a.state + (size_t)ec * sc.S; C.pr = a.param + (size_t)ec * sc.P;
     C.act = a.act + (size_t)ec * sc.n_act; C.obs = a.obs + (size_t)ec * sc.n_obs; C.rew = a.rew + (size_t)ec * sc.n_rew;
-    C.term = a.term + (size_t)ec * sc.n_term; C.env_id = a.env_off + ec;
-    if (a.mode == 0) run_env_step(C, T, ln); else run_env_reset(C, T, ln);
-    if (T > 1) __syncthreads();
+    C.term = a.term + (size_t)ec * sc.n_term; C.env_id = a.env_off + ec; C.e_local = ec;
+    C.wg = a.gws + (size_t)e * sc.g_total;   // the cold workspace is per environment (the allocation has slack for the tail slots)
+    // masked launches (reset of finished episodes, issued every step without a host round trip): nothing to do for a block
+    // whose environments are all unmasked
+    if (a.mask != nullptr && !__syncthreads_or(C.active ? 1 : 0)) continue;
+    // the hot workspaces of the block's environments are one contiguous piece of shared memory, their carry rows one
+    // contiguous piece of global memory: copied by the whole block, 128 bits per thread
+    const int ncarry = (a.n_envs - base < E ? a.n_envs - base : E) * sc.w_total;
+    if (a.stages & ST_LOADC) {
+      const float4* src = reinterpret_cast<const float4*>(a.carry + (size_t)base * sc.w_total); float4* dst = reinterpret_cast<float4*>(smem);
+      for (int i = threadIdx.x; i < ncarry / 4; i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+    }
+    if (a.mode == 0) { if (a.stages == ST_ALL) run_env_step(C, T, ln); else run_env_step_stages(C, T, a.stages, ln); }
+    else if (a.mode == 1) run_env_reset(C, T, ln); else run_env_observe(C, T, ln);
+    if (T > 1 || (a.stages & ST_SAVEC)) __syncthreads();
+    if (a.stages & ST_SAVEC) {
+      float4* dst = reinterpret_cast<float4*>(a.carry + (size_t)base * sc.w_total); const float4* src = reinterpret_cast<const float4*>(smem);
+      for (int i = threadIdx.x; i < ncarry / 4; i += blockDim.x) dst[i] = src[i];
+      __syncthreads();
+    }
   }
 }
 
@@ -92,6 +115,131 @@ DG_DECLARE_STEP(1) DG_DECLARE_STEP(2) DG_DECLARE_STEP(4) DG_DECLARE_STEP(8) DG_D
 DG_DEFINE_STEP_X(DG_STEP_T)
 #elif !defined(DG_SPLIT_BUILD)
 #error "compile with -DDG_STEP_T=<team size> (one object per team size) or -DDG_SPLIT_BUILD (everything else): see diy_gym_b200/build.py"
+#endif
+
+#if !defined(DG_STEP_T)
+// The contact sweeps of the environments a stage launch deferred.  An environment gets W = 16 lanes (two environments per
+// warp, <= 32 row positions each) or W = 32 (<= 64 positions); one warp per block.  Lane l of the environment owns the TWO
+// consecutive positions 2 l, 2 l + 1 of the padded layout (dg_env.cuh "row-space team solver") and holds, in registers, their
+// right-hand sides, clamps, accumulated impulses, y = J dv and its two columns of A for EVERY row - the 150 sweeps of a
+// sub-step touch no memory.  One pair of updates: every lane evaluates the clamp of its first slot, the owner's change d0 is
+// broadcast by a shuffle; the owner folds d0 into its second row at once (its own register), evaluates that clamp and
+// broadcasts d1; then every lane folds both broadcasts into its two y.  Only every other update waits for a shuffle.
+// Row order, clamps and friction bounds are those of the in-kernel team sweeps and of the oracle.  The two environments of a
+// warp run one instruction stream: their sections are laid out at common offsets (the larger of the two section sizes; the
+// surplus positions of the smaller one are inert padding); if that common layout does not fit, the warp sweeps its two
+// environments one after the other.  Everything that steers the loops is read through block-uniform addresses, so the loop
+// branches stay uniform (no divergence bookkeeping around the shuffles).
+struct SolveArgs { const float* carry; float* gws; const int* list; const int* count; };
+template <int W>
+__global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
+  constexpr int K = 2, G = 32 / W, RMAX = W * K;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int count = *a.count, first = (int)blockIdx.x * G;
+  if (first >= count) return;
+  const int lane = threadIdx.x, half = lane / W, l = lane % W;
+  // layouts of the environments of this warp (every lane reads all of them: uniform)
+  RsLayout Ls[G]; int es[G];
+  int P1w = 0, N2w = 0, N3w = 0;   // common section sizes
+#pragma unroll
+  for (int g = 0; g < G; g++) {
+    es[g] = a.list[first + g < count ? first + g : first];
+    const int* hdr = reinterpret_cast<const int*>(a.carry + (size_t)es[g] * sc.w_total) + sc.W_HDR;
+    Ls[g] = rs_layout(K, hdr[WH_RS_NU], 6 * sc.ncons, hdr[WH_NCROW] / 3);
+    if (first + g >= count) Ls[g] = rs_layout(K, 0, 0, 0);
+    P1w = max(P1w, Ls[g].P1); N2w = max(N2w, Ls[g].P2 - Ls[g].P1); N3w = max(N3w, Ls[g].Rp - Ls[g].P2);
+  }
+  const bool together = P1w + N2w + N3w <= RMAX;   // else: one environment at a time, both halves of the warp on the same one
+  const int npass = (G > 1 && !together) ? G : 1;
+  for (int pass = 0; pass < npass; pass++) {
+    const int mine = npass > 1 ? pass : half;                       // which environment this lane works on
+    const bool writer = npass > 1 ? half == 0 : true;               // (duplicated work: one half writes back)
+    const RsLayout L = Ls[G > 1 ? mine : 0];
+    // loop bounds from block-uniform values only (Ls[pass], not Ls[mine]: the compiler must see that they are uniform)
+    const RsLayout Lu = Ls[G > 1 ? pass : 0];
+    const int P1 = npass > 1 ? Lu.P1 : P1w, P2 = P1 + (npass > 1 ? Lu.P2 - Lu.P1 : N2w), Rp = P2 + (npass > 1 ? Lu.Rp - Lu.P2 : N3w);
+    const bool live = first + mine < count;
+    float* wg = a.gws + (size_t)es[G > 1 ? mine : 0] * sc.g_total;
+    float* REC = wg + sc.X_RSREC; const float* A = wg + sc.X_RSA; const int cap = sc.rs_cap;
+    // warp position g -> position q in the environment's own layout (-1: padding)
+    auto own_pos = [&](int g) {
+      int q;
+      if (g < P1) q = g < L.P1 ? g : -1;
+      else if (g < P2) { q = L.P1 + (g - P1); q = q < L.P2 ? q : -1; }
+      else { q = L.P2 + (g - P2); q = q < L.Rp ? q : -1; }
+      return live ? q : -1;
+    };
+    // Per owned row the lane carries  v = rhs - dinv y  (the unclamped change of the impulse),  lo' = lo - ap, hi' = hi - ap, so that
+    // one update is  d = min(max(v, lo'), hi')  - two dependent instructions - and folding a broadcast change d_p of row p is
+    // v += g[p] d_p  with  g[p][r] = -dinv_r A[p][r]  (for r = p that is -1 up to rounding: the row's own change leaves v - d).
+    // Mathematically the update of the team sweeps / the oracle  (ap' = clamp(ap + rhs - dinv y), d = ap' - ap);  only the
+    // rounding differs.  lo', hi' are re-derived from the exact bounds after every update of the row (no drift).
+    float dinv[K], lo[K], hi[K], ap[K], v[K], lop[K], hip[K], mu[K]; int par[K], qown[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      v[k] = 0.f; dinv[k] = 0.f; lo[k] = 0.f; hi[k] = 0.f; ap[k] = 0.f; mu[k] = 0.f; par[k] = -1;
+      const int q = own_pos(l * K + k); qown[k] = q;
+      if (q >= 0) { const F4 r0 = ld4(REC + RR_W * q), r1 = ld4(REC + RR_W * q + 4); v[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
+      lop[k] = lo[k]; hip[k] = hi[k];   // ap = 0, y = 0 at the start
+    }
+    float g_[RMAX][K];   // g_[p][k] = -dinv[k] A[row at warp position p][this lane's slot k]
+#pragma unroll
+    for (int p = 0; p < RMAX; p++) {
+      const int q = p < Rp ? own_pos(p) : -1;
+#pragma unroll
+      for (int k = 0; k < K; k++) g_[p][k] = (q >= 0 && qown[k] >= 0) ? -dinv[k] * A[q * cap + qown[k]] : 0.f;
+    }
+    const int nrm0 = P1 + 6 * sc.ncons;   // warp position of the normal row of contact 0
+    // rows 2 j and 2 j + 1 (lane j of each environment), ascending (FWD) or descending.  The owner folds its first change into
+    // its second row at once (vf_); the broadcast values are bit-identical to its own changes, so the folds below give it the same v.
+#define DG_STEP2(j, FWD)                                                                         \
+    {                                                                                              \
+      constexpr int k0_ = (FWD) ? 0 : 1, k1_ = (FWD) ? 1 : 0;                                      \
+      const float d0_ = fminf(fmaxf(v[k0_], lop[k0_]), hip[k0_]);                                  \
+      const float b0_ = __shfl_sync(FULL, d0_, (j), W);                                            \
+      const float vf_ = fmaf(g_[K * (j) + k0_][k1_], d0_, v[k1_]);                                   \
+      const float d1_ = fminf(fmaxf(vf_, lop[k1_]), hip[k1_]);                                     \
+      const float b1_ = __shfl_sync(FULL, d1_, (j), W);                                            \
+      if (l == (j)) {                                                                              \
+        ap[k0_] += d0_; lop[k0_] = lo[k0_] - ap[k0_]; hip[k0_] = hi[k0_] - ap[k0_];                \
+        ap[k1_] += d1_; lop[k1_] = lo[k1_] - ap[k1_]; hip[k1_] = hi[k1_] - ap[k1_];                \
+      }                                                                                            \
+      v[0] = fmaf(g_[K * (j) + k0_][0], b0_, v[0]); v[1] = fmaf(g_[K * (j) + k0_][1], b0_, v[1]);       \
+      v[0] = fmaf(g_[K * (j) + k1_][0], b1_, v[0]); v[1] = fmaf(g_[K * (j) + k1_][1], b1_, v[1]);       \
+    }
+    for (int it = 0; it < sc.iters; it++) {
+      if (it & 1) {
+#pragma unroll
+        for (int j = 0; j < W; j++) { if (K * j >= P1) break; DG_STEP2(j, true) }
+      } else {
+#pragma unroll
+        for (int j = W - 1; j >= 0; j--) { if (K * j < P1) DG_STEP2(j, false) }
+      }
+#pragma unroll
+      for (int j = 0; j < W; j++) { if (K * j >= P2) break; if (K * j >= P1) DG_STEP2(j, true) }
+      // friction bounds from the normal impulses this sweep left (the normal of contact c sits at warp position nrm0 + c)
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        const int pn = par[k] >= 0 ? nrm0 + par[k] : 0;
+        const float v0 = __shfl_sync(FULL, ap[0], pn / K, W), v1 = __shfl_sync(FULL, ap[1], pn / K, W);
+        const float vn = (pn % K) ? v1 : v0;
+        if (par[k] >= 0) { hi[k] = mu[k] * vn; lo[k] = -hi[k]; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; }
+      }
+#pragma unroll
+      for (int j = 0; j < W; j++) { if (K * j >= Rp) break; if (K * j >= P2) DG_STEP2(j, true) }
+    }
+#undef DG_STEP2
+    if (writer) {
+#pragma unroll
+      for (int k = 0; k < K; k++) if (qown[k] >= 0) REC[RR_W * qown[k] + RR_APPLIED] = ap[k];
+    }
+  }
+}
+// cls 0: environments with <= 32 row positions (two per warp), cls 1: <= 64 (one per warp)
+static cudaError_t solve_launch(int cls, const DevScene& sc, const SolveArgs& a, int n_envs, cudaStream_t s) {
+  if (cls == 0) dg_solve_kernel<16><<<(n_envs + 1) / 2, 32, 0, s>>>(sc, a); else dg_solve_kernel<32><<<n_envs, 32, 0, s>>>(sc, a);
+  return cudaGetLastError();
+}
 #endif
 
 #if !defined(DG_STEP_T)
@@ -168,7 +316,7 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
   const int width = ci[1], height = ci[2];
   unsigned* cand = reinterpret_cast<unsigned*>(vs + VS_W * sc.nv);
   const int ncw = (sc.nv + 31) / 32;
-  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr;
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr;
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
   const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
@@ -276,11 +424,25 @@ struct DgWorld {
   unsigned long long opmask[2] = {~0ull, ~0ull};
   float* gws = nullptr;
   unsigned long long* dbg = nullptr;   // [grid][64] phase-cycle sums while dg_debug_phase_cycles is on
+  unsigned* dropped = nullptr;         // device counter of contacts lost to the max_contacts cap
+  // split schedule: stage launches of the step kernel around the sweep kernel (see run_step_split)
+  bool split = false;
+  float* carry = nullptr;              // [n_envs + slack][w_total] hot workspaces between stage launches
+  int* rs_lists = nullptr;             // [2][n_envs] environments deferred to the sweep kernel (K = 1 | K = 2)
+  int* rs_counts = nullptr;            // [substeps][2]
+  cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the K = 2 sweeps run beside the K = 1 sweeps
   int64_t launches = 0;
   std::string err;
 };
 static std::string g_create_err;
 
+// Every entry point runs on the world's own device, whatever the caller's current device is (two worlds on two GPUs in one
+// process, or a torch current device different from the world's), and leaves the caller's device as it found it.
+struct DeviceGuard {
+  int prev = -1; bool ok = true;
+  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess; else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 #define CK(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (w)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return DG_E_CUDA; } } while (0)
 
 static cudaError_t configure_any(DgWorld* w) {
@@ -318,8 +480,9 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   if (team != 0 && team != 1 && team != 2 && team != 4 && team != 8 && team != 16 && team != 32) { g_create_err = "dg_world_create: team must be 0,1,2,4,8,16,32"; return DG_E_ARG; }
   DgWorld* w = new DgWorld();
   w->n_envs = n_envs; w->device = device;
-  cudaError_t e = cudaSetDevice(device);
-  if (e != cudaSuccess) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
+  DeviceGuard guard(device);
+  cudaError_t e = guard.ok ? cudaSuccess : cudaGetLastError();
+  if (e != cudaSuccess || !guard.ok) { g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { g_create_err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e); delete w; return DG_E_CUDA; }
@@ -392,21 +555,49 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   e = configure_any(w);
   if (e != cudaSuccess) { g_create_err = std::string("kernel configuration: ") + cudaGetErrorString(e); dg_world_destroy(w); return DG_E_CUDA; }
   {
-    size_t slots = (size_t)w->grid * (w->block_threads / w->team);
+    // cold workspace: one slot per ENVIRONMENT (it travels between the stage launches of the split schedule), with slack for the
+    // environment-less tail slots of the last block
+    size_t slots = (size_t)w->n_envs + 256;
     size_t bytes = std::max<size_t>(slots * (size_t)w->hs.dev.g_total * sizeof(float), 16);
-    if (cudaMalloc(&w->gws, bytes) != cudaSuccess) { g_create_err = "cudaMalloc of the cold workspace failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
+    if (cudaMalloc(&w->gws, bytes) != cudaSuccess) { g_create_err = "cudaMalloc of the cold workspace (" + std::to_string(bytes >> 20) + " MiB) failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_NOMEM; }
     w->dev.g_total = w->hs.dev.g_total;
   }
+  {
+    // split schedule: scenes in which a floating body rests on contacts (contacts are the norm, not the exception) leave the
+    // contact sweeps to the sweep kernel; DG_SPLIT=0/1 overrides.  Needs the row-space solver (team of >= 2 lanes).
+    bool floating = false;
+    const int32_t* bsec = ibuf + ibuf[2 + 3 * SEC_BODY_I + 1];
+    for (int b = 0; b < w->hs.dev.nb; b++) floating = floating || bsec[DG_BODY_I_W * b] == 2;
+    w->split = w->hs.dev.rs_cap > 0 && w->hs.dev.solver == 1 && ((floating && w->hs.dev.npair > 0) || w->hs.dev.ncons > 0);
+    if (const char* env_split = getenv("DG_SPLIT")) w->split = atoi(env_split) != 0 && w->hs.dev.rs_cap > 0 && w->hs.dev.solver == 1;
+    if (w->split) {
+      const size_t nc = ((size_t)w->n_envs + 256) * (size_t)w->hs.dev.w_total * sizeof(float);
+      bool ok = cudaMalloc(&w->carry, nc) == cudaSuccess && cudaMalloc(&w->rs_lists, 2 * (size_t)w->n_envs * sizeof(int)) == cudaSuccess &&
+                cudaMalloc(&w->rs_counts, 2 * (size_t)std::max(w->hs.dev.substeps, 1) * sizeof(int)) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&w->aux, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) { g_create_err = "allocation of the split-schedule buffers failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
+    }
+  }
+  if (cudaMalloc(&w->dropped, sizeof(unsigned)) != cudaSuccess || cudaMemset(w->dropped, 0, sizeof(unsigned)) != cudaSuccess) { g_create_err = "cudaMalloc of the contact-drop counter failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
   *out = w;
   return DG_OK;
 }
 
 void dg_world_destroy(DgWorld* w) {
   if (!w) return;
+  DeviceGuard guard(w->device);
   if (w->d_ints) cudaFree(w->d_ints);
   if (w->d_floats) cudaFree(w->d_floats);
   if (w->gws) cudaFree(w->gws);
   if (w->dbg) cudaFree(w->dbg);
+  if (w->dropped) cudaFree(w->dropped);
+  if (w->carry) cudaFree(w->carry);
+  if (w->rs_lists) cudaFree(w->rs_lists);
+  if (w->rs_counts) cudaFree(w->rs_counts);
+  if (w->aux) cudaStreamDestroy(w->aux);
+  if (w->ev_fork) cudaEventDestroy(w->ev_fork);
+  if (w->ev_join) cudaEventDestroy(w->ev_join);
   delete w;
 }
 
@@ -418,7 +609,12 @@ int64_t dg_query(const DgWorld* w, int key) {
     case DG_Q_N_REW: return d.n_rew; case DG_Q_N_TERM: return d.n_term; case DG_Q_N_ENVS: return w->n_envs; case DG_Q_TEAM: return w->team;
     case DG_Q_BLOCK_THREADS: return w->block_threads; case DG_Q_GRID_BLOCKS: return w->grid; case DG_Q_SMEM_BYTES: return (int64_t)w->smem;
     case DG_Q_WS_FLOATS: return d.w_total; case DG_Q_N_CAMERAS: return d.ncam; case DG_Q_LAUNCHES: return w->launches;
-    case DG_Q_RS_ASHARED: return d.rs_ashared; case DG_Q_SOLVER: return d.solver;
+    case DG_Q_RS_ASHARED: return d.rs_ashared; case DG_Q_SOLVER: return d.solver; case DG_Q_MAX_CONTACTS: return d.maxc; case DG_Q_SPLIT: return w->split ? 1 : 0;
+    case DG_Q_CONTACTS_DROPPED: {   // synchronises the device
+      DeviceGuard guard(w->device); unsigned v = 0;
+      if (!w->dropped || cudaMemcpy(&v, w->dropped, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      return (int64_t)v;
+    }
   }
   return -1;
 }
@@ -440,14 +636,18 @@ int dg_set_seed(DgWorld* w, uint32_t seed, int env_id_offset) {
 int dg_set_action_mask(DgWorld* w, const uint8_t* op_enabled, int n_ops) {
   if (!w || (n_ops > 0 && !op_enabled)) return DG_E_ARG;
   w->opmask[0] = w->opmask[1] = ~0ull;
-  for (int k = 0; k < n_ops && k < 128; k++) if (!op_enabled[k]) w->opmask[k >> 6] &= ~(1ull << (k & 63));
+  for (int k = 0; k < n_ops; k++) if (!op_enabled[k]) {
+    // the mask has 128 bits; an action op beyond them cannot be switched off (compiler/scene.py refuses such scenes)
+    if (k >= 128) { w->err = "dg_set_action_mask: ops at index >= 128 cannot be masked"; return DG_E_ARG; }
+    w->opmask[k >> 6] &= ~(1ull << (k & 63));
+  }
   return DG_OK;
 }
 
 int dg_init_state(DgWorld* w, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_init_state: buffers not bound"; return DG_E_UNBOUND; }
-  CK(w, cudaSetDevice(w->device));
+  DeviceGuard guard(w->device);
   w->launches++;
   dg_init_kernel<<<w->sm_count * 4, 256, 0, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, w->n_envs);
   CK(w, cudaGetLastError());
@@ -457,8 +657,36 @@ int dg_init_state(DgWorld* w, void* stream) {
 static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "buffers not bound"; return DG_E_UNBOUND; }
-  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg};
-  CK(w, launch_any(w, a, (cudaStream_t)stream));
+  DeviceGuard guard(w->device);
+  if (!guard.ok) { w->err = "cudaSetDevice failed"; cudaGetLastError(); return DG_E_CUDA; }
+  LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg, w->dropped,
+               ST_ALL, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode != 0 || !w->split) { CK(w, launch_any(w, a, s)); return DG_OK; }
+  // Split schedule of one step with n sub-steps (2 for the reference's settings, diy_gym.py:76-79):
+  //   stage launch [add-on update, load | sub-step 0 up to the row-space system] -> sweeps ->
+  //   stage launch [impulses + integration of sub-step k-1 | sub-step k up to its system] -> sweeps -> ... ->
+  //   stage launch [impulses + integration of the last sub-step | link cache, state rows, sensors / rewards / terminals]
+  // The sweeps of one sub-step are two launches of the sweep kernel: environments with <= 32 row positions (two per warp) on this
+  // stream, those with <= 64 (one per warp) beside them on the world's auxiliary stream (they take longest, so they should not
+  // queue behind the others).
+  const int nsub = std::max(w->dev.substeps, 1);
+  a.carry = w->carry; a.rs_list0 = w->rs_lists; a.rs_list1 = w->rs_lists + w->n_envs;
+  CK(w, cudaMemsetAsync(w->rs_counts, 0, 2 * (size_t)nsub * sizeof(int), s));
+  for (int sub = 0; sub <= nsub; sub++) {
+    a.stages = (sub == 0 ? ST_ACT : (ST_LOADC | ST_POST)) | (sub < nsub ? (ST_PRE | ST_SAVEC) : ST_END);
+    a.rs_count = w->rs_counts + 2 * std::min(sub, nsub - 1);
+    CK(w, launch_any(w, a, s));
+    if (sub == nsub) break;
+    CK(w, cudaEventRecord(w->ev_fork, s));
+    CK(w, cudaStreamWaitEvent(w->aux, w->ev_fork, 0));
+    const SolveArgs s2{w->carry, w->gws, a.rs_list1, a.rs_count + 1}, s1{w->carry, w->gws, a.rs_list0, a.rs_count};
+    CK(w, solve_launch(1, w->dev, s2, w->n_envs, w->aux));
+    CK(w, cudaEventRecord(w->ev_join, w->aux));
+    CK(w, solve_launch(0, w->dev, s1, w->n_envs, s));
+    CK(w, cudaStreamWaitEvent(s, w->ev_join, 0));
+    w->launches += 2;
+  }
   return DG_OK;
 }
 // Measurement aid: with `enable`, thread 0 of every block of the step kernel accumulates the cycles of each phase (barrier
@@ -466,7 +694,7 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
 // (out[block * 64 + key], n <= grid * 64 entries) and clears it.  tools/phase_probe.py prints it.
 int dg_debug_phase_cycles(DgWorld* w, int enable) {
   if (!w) return DG_E_ARG;
-  CK(w, cudaSetDevice(w->device));
+  DeviceGuard guard(w->device);
   if (!enable) { if (w->dbg) { cudaDeviceSynchronize(); cudaFree(w->dbg); w->dbg = nullptr; } return DG_OK; }
   if (!w->dbg) CK(w, cudaMalloc(&w->dbg, (size_t)w->grid * 64 * sizeof(unsigned long long)));
   CK(w, cudaMemset(w->dbg, 0, (size_t)w->grid * 64 * sizeof(unsigned long long)));
@@ -474,6 +702,7 @@ int dg_debug_phase_cycles(DgWorld* w, int enable) {
 }
 int dg_debug_read(DgWorld* w, unsigned long long* out, int n) {
   if (!w || !out || !w->dbg || n > w->grid * 64) return DG_E_ARG;
+  DeviceGuard guard(w->device);
   CK(w, cudaDeviceSynchronize());
   CK(w, cudaMemcpy(out, w->dbg, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   CK(w, cudaMemset(w->dbg, 0, (size_t)w->grid * 64 * sizeof(unsigned long long)));
@@ -481,12 +710,14 @@ int dg_debug_read(DgWorld* w, unsigned long long* out, int n) {
 }
 int dg_step(DgWorld* w, void* stream) { return run(w, 0, nullptr, stream); }
 int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream) { return run(w, 1, mask_dev, stream); }
+int dg_observe(DgWorld* w, void* stream) { return run(w, 2, nullptr, stream); }
 
 int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream) {
   if (!w || !rgb_dev || !depth_dev) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_render: buffers not bound"; return DG_E_UNBOUND; }
   const DevScene& d = w->dev;
   if (cam < 0 || cam >= d.ncam) { w->err = "dg_render: no such camera"; return DG_E_ARG; }
+  DeviceGuard guard(w->device);
   const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
   int tiles_x = (ci[1] + DG_TILE - 1) / DG_TILE, tiles_y = (ci[2] + DG_TILE - 1) / DG_TILE;
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)(d.nv + 31) / 32 + 4) * sizeof(float);
@@ -503,6 +734,7 @@ int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* strea
 int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* reward_host, uint8_t* term_host, void* stream) {
   if (!w) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_step_host: buffers not bound"; return DG_E_UNBOUND; }
+  DeviceGuard guard(w->device);
   const DevScene& d = w->dev; cudaStream_t s = (cudaStream_t)stream; size_t n = (size_t)w->n_envs;
   if (d.n_act && action_host) CK(w, cudaMemcpyAsync(w->buf.action, action_host, n * d.n_act * sizeof(float), cudaMemcpyHostToDevice, s));
   int rc = dg_step(w, stream);

@@ -19,7 +19,11 @@ enum { D_Q = 0, D_QD, D_APPLIED, D_TAU, D_COUNT };
 // body plan columns
 enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_NRS, BP_AOFF, BP_GS, BP_W };
 // workspace header ints
-enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_COUNT = 8 };
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_RS_DEFER, WH_COUNT = 12 };
+// stages of one DIYGym.step when the contact sweeps run in their own kernel (dg_kernels.cu): see dg_env.cuh "the phase schedule"
+enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC = 32, ST_ALL = 15 };
+// row capacity of the sweep kernel: a warp per environment, K = 1 (<= 32 rows) or 2 (<= 64 rows) rows per lane, A in registers
+enum { RS_WARP_R1 = 32, RS_WARP_R2 = 64 };
 // row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j
 enum { RS_CONTACT = 0x40000000, RS_KMAX = 8, RS_GVMAX = 128 };
 // row record of the row-space solver
@@ -341,7 +345,7 @@ struct HostScene {
               " rows need a team of at least " + std::to_string((rows_pad + RS_KMAX - 1) / RS_KMAX) + " lanes (and at most " + std::to_string((int)RS_GVMAX) + " generalized coordinates)";
       return false;
     }
-    d.solver = 1; d.rs_min = 1 << 20;   // measured (profiles/r1_rs_min_sweep.log): uncoupled environments are faster with the per-body sweeps
+    d.solver = 1; d.rs_min = 0;   // every environment with contacts is solved in row space (round 1 kept uncoupled ones on the per-body sweeps: its row-space sweeps were slower, profiles/r1_rs_min_sweep.log; DG_RS_MIN restores that for A/B runs)
     d.rs_ashared = 0; d.X_RSAS = 0; (void)rs_ashared;   // (shared-memory home of A: measured slower, removed)
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);
     phase_take(&d.X_RSV, RC_SCRATCH, 1, d.rs_cap * 2 * gv);      // per row: J and M^-1 J^T, dense over all bodies' coordinates

@@ -33,11 +33,12 @@ class EpisodeStats:
         """reward: [N] tensor (already summed over add-ons), done: [N] bool tensor."""
         self.ret += reward
         self.length += 1
-        if bool(done.any()):
-            r, l = self.ret[done].double(), self.length[done].double()
-            self.sums += torch.stack([torch.tensor(float(r.numel()), dtype=torch.float64, device=r.device), r.sum(), (r * r).sum(), l.sum()])
-            self.ret[done] = 0
-            self.length[done] = 0
+        # no host synchronisation on the step path: finished episodes are folded in by masked arithmetic
+        d = done.to(self.ret.dtype)
+        r, l = (self.ret * d).double(), (self.length * d).double()
+        self.sums += torch.stack([d.double().sum(), r.sum(), (r * r).sum(), l.sum()])
+        self.ret *= 1 - d
+        self.length *= 1 - d
 
     def reduce(self):
         total = self.sums.clone()

@@ -38,6 +38,7 @@ class DIYGym(Receptor):
         self.name = config.name
         self.env = self
         self.num_envs = int(num_envs)
+        self._env_id_offset = int(env_id_offset)
         self.auto_reset = bool(auto_reset)
         self._max_episode_steps = config.get('max_episode_steps') if 'max_episode_steps' in config else None
         self.hot_start = int(config.get('hot_start', 1))
@@ -107,20 +108,42 @@ class DIYGym(Receptor):
 
     # --------------------------------------------------------------------------------------------
     def seed(self, seed=None):
+        """Seeds the per-environment random streams of respawn / dynamics_randomizer (keyed by seed, global environment id and
+        reset count).  Unlike the reference (diy_gym.py:124-128, which seeds an np_random nothing reads - SURVEY App. D.7) it
+        takes effect: from the next reset on."""
         self._seed = seed
+        if seed is not None and self.world is not None and hasattr(self.world, 'set_seed'):
+            self.world.set_seed(int(seed), self._env_id_offset)
         return [seed]
 
     def reset(self, mask=None):
         """Reset every environment (mask=None) or the masked ones ([num_envs] bool tensor).  Add-on reset hooks
         run first (built-ins inside the kernel, user add-ons in Python), then `hot_start` physics steps."""
-        for receptor in self.receptors.values():
-            for addon in receptor.addons.values():
-                try:
-                    addon.reset(mask)
-                except TypeError:
-                    addon.reset()
+        for addon, takes_mask in self._reset_hooks():
+            if takes_mask:
+                addon.reset(mask)
+            else:
+                addon.reset()
         self.world.reset(mask)
         return self.observe()
+
+    def _reset_hooks(self):
+        """(add-on, accepts a mask argument) for every add-on that overrides reset(); a user add-on written for the reference
+        has `def reset(self)` - it is then reset for every environment.  Decided from the signature, once: a TypeError raised
+        INSIDE a user hook is the user's to see."""
+        if not hasattr(self, '_reset_hook_list'):
+            import inspect
+            from .addons.addon import Addon
+            hooks = []
+            for receptor in self.receptors.values():
+                for addon in receptor.addons.values():
+                    if type(addon).reset is Addon.reset:
+                        continue
+                    params = [p for p in inspect.signature(addon.reset).parameters.values()
+                              if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD, p.VAR_POSITIONAL)]
+                    hooks.append((addon, len(params) > 0))
+            self._reset_hook_list = hooks
+        return self._reset_hook_list
 
     def observe(self):
         ret = self.walk_addons(lambda addon: addon.observe())
@@ -156,11 +179,21 @@ class DIYGym(Receptor):
         self._apply_action_mask(present)
         self.world.step()
         obs, rew, term = self.observe(), self.reward(), self.is_terminal()
+        info = {}
         if self.auto_reset:
             done = term if isinstance(term, torch.Tensor) else walk_dict(term, any)
-            if isinstance(done, torch.Tensor) and bool(done.any()):
-                self.reset(done)
-        return obs, rew, term, {}
+            if isinstance(done, torch.Tensor):
+                # The returned leaves are VIEWS of the world's output buffers and the masked reset rewrites the rows of the
+                # finished environments: the terminal step's reward and observation are copied out first (the reward a learner
+                # gets for the last transition must be that transition's).  No host synchronisation: the masked reset is launched
+                # unconditionally, a block whose mask bytes are all zero returns at once.
+                def clone(t):
+                    if isinstance(t, dict):
+                        return OrderedDict((k, clone(v)) for k, v in t.items())
+                    return t.clone() if isinstance(t, torch.Tensor) else t
+                rew, info = clone(rew), {'terminal_observation': clone(obs), 'done': done}
+                obs = self.reset(done)
+        return obs, rew, term, info
 
     def _apply_action_mask(self, present):
         """Only add-ons present in the action dict are updated (diy_gym.py:202-204): switch the others' ops off."""

@@ -35,9 +35,11 @@ class Model(Receptor):
             # to it with p.createConstraint(JOINT_FIXED): joint frame = (xyz, rpy) in the parent frame, identity in the child frame
             parent_frame_id = parent.get_frame_id(config.get('parent_frame')) if 'parent_frame' in config else -1
             # (the parent's controllers have already put its joints at their rest_position: add-ons are built before nested models)
+            # - but only the controllers whose constructor calls reset() in the reference do that (ik_controller.py:45,
+            # admittance_controller.py:34); under a joint_controller the parent is still at q = 0 when the child is welded
             q_rest = {}
             for a in parent.addons.values():
-                if hasattr(a, 'joint_ids') and hasattr(a, 'rest_position'):
+                if getattr(a, 'resets_in_constructor', False) and hasattr(a, 'joint_ids') and hasattr(a, 'rest_position'):
                     q_rest.update(dict(zip(a.joint_ids, a.rest_position)))
             T = parent.body.rest_com_pose(parent_frame_id, q_rest)
             spawn_pos, spawn_quat = T.p, T.q

@@ -37,7 +37,10 @@ enum {
   DG_Q_N_CAMERAS = 12,
   DG_Q_LAUNCHES = 13,    /* kernels launched by this world since creation           */
   DG_Q_RS_ASHARED = 14,  /* floats of shared memory per environment holding the contact solver's row-space matrix */
-  DG_Q_SOLVER = 15       /* 1: row-space team solver for contact environments, 0: per-body sweeps */
+  DG_Q_SOLVER = 15,      /* 1: row-space team solver for contact environments, 0: per-body sweeps */
+  DG_Q_MAX_CONTACTS = 16,     /* contact-point capacity per environment (YAML extension key `max_contacts`) */
+  DG_Q_CONTACTS_DROPPED = 17, /* contacts lost to that capacity since the world was created (synchronises the device) */
+  DG_Q_SPLIT = 18             /* 1: a step is several stage launches around the contact-sweep kernel, 0: one fused launch */
 };
 
 /* Buffers of one world, all DEVICE pointers, row-major with the environment as the leading dimension. */
@@ -84,6 +87,10 @@ int dg_debug_read(DgWorld* w, unsigned long long* out, int n);
 /* DIYGym.reset for the environments whose mask byte is non-zero (mask_dev == NULL: all).
  * Replaces /root/reference/diy_gym/diy_gym.py:130-148 (add-on reset hooks, hot-start steps, observe). */
 int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream);
+/* DIYGym.observe / reward / is_terminal on the state rows as they are (no physics): refreshes the link-pose cache the sensors
+ * read and evaluates every sensor / reward / terminal op into obs / reward / term.
+ * Replaces /root/reference/diy_gym/diy_gym.py:211-222 (observe, reward, is_terminal -> walk_addons). */
+int dg_observe(DgWorld* w, void* stream);
 /* Camera add-on number `cam`: rgb [n_envs][H][W][3] float in [0,1], depth [n_envs][H][W] eye-space z (negative).
  * Replaces p.getCameraImage + post-processing (/root/reference/diy_gym/addons/sensors/camera.py:58-92). */
 int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream);

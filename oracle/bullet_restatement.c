@@ -132,6 +132,7 @@ typedef struct DgoWorld {
   Row* rows; int nrows;
   double* dv;                  /* per body, MAXROWDOF each */
   uint32_t seed; int env_id;
+  long dropped;   /* contacts lost to the max_contacts cap since creation */
 } DgoWorld;
 
 #define HI(W, k) ((W)->hi[HI_##k])
@@ -189,6 +190,7 @@ int dgo_param_size(DgoWorld* W) { return W->P; }
 void dgo_set_seed(DgoWorld* W, uint32_t seed, int env_id) { W->seed = seed; W->env_id = env_id; }
 double dgo_flops(int reset) { double f = g_flops; if (reset) g_flops = 0; return f; }
 int dgo_num_contacts(DgoWorld* W) { return W->ncontacts; }
+long dgo_contacts_dropped(DgoWorld* W) { return W->dropped; }
 void dgo_get_contact(DgoWorld* W, int i, double* out) {  /* fa, fb, pa3, pb3, n3, dist, mu */
   const Contact* c = &W->contacts[i]; out[0] = c->fa; out[1] = c->fb; memcpy(out + 2, c->pa, 24); memcpy(out + 5, c->pb, 24); memcpy(out + 8, c->n, 24); out[11] = c->dist; out[12] = c->mu;
 }
@@ -571,7 +573,16 @@ static void collide_pair(DgoWorld* W, int sa, int sb, double margin) {
       tmp[nt++] = c;
     }
   }
-  for (int i = 0; i < nt && W->ncontacts < W->maxc; i++) W->contacts[W->ncontacts++] = tmp[i];
+  /* capacity max_contacts (an extension key of the YAML, default 16 with a floating body, else 8): when the list is full a new
+     contact replaces the SHALLOWEST stored one if it is deeper, so that what gets lost is a grazing contact, never the wall the
+     robot is pushing into; every loss is counted (dgo_contacts_dropped).  pybullet has no such cap. */
+  for (int i = 0; i < nt; i++) {
+    if (W->ncontacts < W->maxc) { W->contacts[W->ncontacts++] = tmp[i]; continue; }
+    W->dropped++;
+    int worst = 0;
+    for (int j = 1; j < W->ncontacts; j++) if (W->contacts[j].dist > W->contacts[worst].dist) worst = j;
+    if (W->ncontacts > 0 && tmp[i].dist < W->contacts[worst].dist) W->contacts[worst] = tmp[i];
+  }
 }
 static void collide(DgoWorld* W) {
   W->ncontacts = 0;

@@ -39,6 +39,8 @@ def lib():
             getattr(L, f).restype = ctypes.c_int
             getattr(L, f).argtypes = [vp]
         L.dgo_set_seed.argtypes = [vp, ctypes.c_uint32, ctypes.c_int]
+        L.dgo_contacts_dropped.restype = ctypes.c_long
+        L.dgo_contacts_dropped.argtypes = [vp]
         L.dgo_flops.restype = ctypes.c_double
         L.dgo_flops.argtypes = [ctypes.c_int]
         L.dgo_get_contact.argtypes = [vp, ctypes.c_int, dp]
@@ -133,6 +135,9 @@ class OracleWorld:
         lib().dgo_ik(self._w, body, ee_link_global, _dp(tpos), _dp(tq), int(torn is not None), int(nullspace is not None), _dp(lo),
                      _dp(hi), _dp(rng), _dp(rest), _dp(out))
         return out[:nd]
+
+    def contacts_dropped(self):
+        return int(lib().dgo_contacts_dropped(self._w))
 
     def contacts(self):
         n = lib().dgo_num_contacts(self._w)

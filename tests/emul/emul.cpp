@@ -19,6 +19,7 @@ struct EmulWorld {
   std::vector<float> state, param, ws, wg;
   uint32_t seed = 1234u; int env_off = 0;
   unsigned long long opmask[2] = {~0ull, ~0ull};
+  unsigned dropped = 0;
 };
 
 extern "C" {
@@ -48,7 +49,7 @@ static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* re
   const DevScene& d = w->hs.dev; Env C;
   C.sc = &d; C.ws = w->ws.data(); C.wg = w->wg.data(); C.link_i = d.link_i; C.link_f = d.link_f; C.link_x = d.link_x; C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
   C.act = act ? act + (size_t)e * d.n_act : nullptr; C.obs = obs + (size_t)e * d.n_obs; C.rew = rew + (size_t)e * d.n_rew;
-  C.dbg = nullptr; C.active = true; C.grp0 = 0; C.grp1 = 1; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
+  C.dbg = nullptr; C.active = true; C.grp0 = 0; C.grp1 = 1; C.dropped = &w->dropped; C.split = 0; C.rs_list[0] = C.rs_list[1] = nullptr; C.rs_count = nullptr; C.e_local = e; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;
 }
 // DGE_POISON=<value>: fills both workspaces with that value before every environment, so that a read of workspace memory
@@ -60,6 +61,10 @@ void dge_step(EmulWorld* w, const float* act, float* obs, float* rew, uint8_t* t
 void dge_reset(EmulWorld* w, const uint8_t* mask, float* obs, float* rew, uint8_t* term) {
   for (int e = 0; e < w->n_envs; e++) { if (mask && !mask[e]) continue; poison(w); Env C = make_env(w, e, nullptr, obs, rew, term); run_env_reset(C, w->team, 0); }
 }
+void dge_observe(EmulWorld* w, float* obs, float* rew, uint8_t* term) {
+  for (int e = 0; e < w->n_envs; e++) { poison(w); Env C = make_env(w, e, nullptr, obs, rew, term); run_env_observe(C, w->team, 0); }
+}
+unsigned dge_contacts_dropped(EmulWorld* w) { return w->dropped; }
 // physics only (no add-on ops): nsub = 0 refreshes the link cache
 void dge_physics(EmulWorld* w, int nsub) {
   std::vector<float> o(w->hs.dev.n_obs + 1), r(w->hs.dev.n_rew + 1); std::vector<uint8_t> t(w->hs.dev.n_term + 1);

@@ -41,6 +41,9 @@ def lib():
         L.dge_step.argtypes = [vp, fp, fp, fp, u8]
         L.dge_reset.argtypes = [vp, u8, fp, fp, u8]
         L.dge_physics.argtypes = [vp, ctypes.c_int]
+        L.dge_observe.argtypes = [vp, fp, fp, u8]
+        L.dge_contacts_dropped.restype = ctypes.c_uint
+        L.dge_contacts_dropped.argtypes = [vp]
         _LIB = L
     return _LIB
 
@@ -95,6 +98,14 @@ class EmulWorld:
         o, r, t = self._outptrs()
         lib().dge_step(self._w, _fp(act), o, r, t)
         return self._outs()
+
+    def observe(self):
+        o, r, t = self._outptrs()
+        lib().dge_observe(self._w, o, r, t)
+        return self._outs()
+
+    def contacts_dropped(self):
+        return int(lib().dge_contacts_dropped(self._w))
 
     def reset(self, mask=None):
         o, r, t = self._outptrs()

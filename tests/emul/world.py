@@ -39,6 +39,16 @@ class EmulTorchWorld:
         self.launches += 1
         lib().dge_step(self.e._w, _fp(self._a), *self._ptrs())
 
+    def set_seed(self, seed, env_id_offset=0):
+        lib().dge_set_seed(self.e._w, int(seed) & 0xffffffff, int(env_id_offset))
+
+    def observe(self):
+        self.launches += 1
+        lib().dge_observe(self.e._w, *self._ptrs())
+
+    def contacts_dropped(self):
+        return self.e.contacts_dropped()
+
     def reset(self, mask=None):
         self.launches += 1
         m = None

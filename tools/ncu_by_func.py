@@ -12,8 +12,13 @@ rep, lib, kname = sys.argv[1], sys.argv[2], sys.argv[3]
 srcdir = os.environ.get('NCU_SRC') or os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'diy_gym_b200', 'csrc')
 tmp = tempfile.mkdtemp()
 subprocess.check_call(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-dis = subprocess.run(['nvdisasm', '--print-line-info', '-c', cubin], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for f in sorted(os.listdir(tmp)):   # one cubin per compiled object (diy_gym_b200/build.py): take the one that holds the kernel
+    if f.endswith('.cubin'):
+        out_ = subprocess.run(['nvdisasm', '--print-line-info', '-c', os.path.join(tmp, f)], capture_output=True, text=True).stdout
+        if ('.text.' in out_) and any(kname in l for l in out_.splitlines() if l.startswith('\t.section\t.text.')):
+            dis = out_.splitlines()
+            break
 # innermost line + the full inline chain (outermost function attribution)
 line_of, in_k, cur = {}, False, None
 for l in dis:
