@@ -1,5 +1,6 @@
-"""Committed golden rollouts (tests/golden/*.npz, written by tools/make_golden.py from the fp64 oracle - pybullet is
-absent).  CPU: the oracle and the g++ build of the kernel code reproduce them; GPU (-m gpu):
+"""REGRESSION FIXTURES, not parity evidence: committed rollouts of the repo's OWN fp64 oracle (tests/golden/*.npz, written by
+tools/make_golden.py and regenerated whenever the oracle changes on purpose - pybullet is absent).
+They pin the oracle and the compiler against silent change and give the CUDA path a fixed target that travels to the GPU box.  CPU: the oracle and the g++ build of the kernel code reproduce them; GPU (-m gpu):
 the CUDA path reproduces them through the C ABI."""
 import os
 
