@@ -95,7 +95,6 @@ class World:
         q = lambda k: int(L.dg_query(h, Q[k]))
         self.S, self.P, self.n_act, self.n_obs, self.n_rew, self.n_term = q('STATE_SIZE'), q('PARAM_SIZE'), q('N_ACT'), q('N_OBS'), q('N_REW'), q('N_TERM')
         self.team, self.block_threads, self.grid_blocks, self.smem_bytes, self.ws_floats = q('TEAM'), q('BLOCK_THREADS'), q('GRID_BLOCKS'), q('SMEM_BYTES'), q('WS_FLOATS')
-        self.split = bool(q('SPLIT'))
         N, dev = self.n_envs, self.device
         self.state = torch.zeros((N, self.S), dtype=torch.float32, device=dev)
         self.param = torch.zeros((N, self.P), dtype=torch.float32, device=dev)
@@ -130,6 +129,11 @@ class World:
             self.close()
         except Exception:
             pass
+
+    @property
+    def split(self):
+        """True while a step runs as stage launches around the contact-sweep kernel (adaptive: see dg_kernels.cu)."""
+        return bool(self.L.dg_query(self._h, Q['SPLIT']))
 
     @property
     def launches(self):

@@ -43,6 +43,7 @@ struct Env {
   int* rs_list[2];                // deferred environments: <= 32 row positions | <= 64 (local indices), or null
   int* rs_count;                  // [2] their counts (atomically incremented)
   int e_local;                    // index of this environment in the launch
+  unsigned* rs_used;              // counter of environment sub-steps solved in row space (any schedule), or null
 };
 
 #define SC (*C.sc)
@@ -1098,6 +1099,7 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
   if (ln == 0) {
     hdr[WH_RS_R] = L.Rp; hdr[WH_RS_K] = K;
 #if defined(__CUDA_ARCH__)
+    if (C.rs_used) atomicAdd(C.rs_used, 1u);   // how many environment sub-steps needed the row-space solver (steers the schedule)
     if (defer) { const int cls = hdr[WH_RS_DEFER] - 1; const int slot = atomicAdd(C.rs_count + cls, 1); C.rs_list[cls][slot] = C.e_local; }
 #endif
   }

@@ -27,7 +27,7 @@ struct LaunchArgs {
   unsigned* dropped;         // contacts lost to the max_contacts cap (one counter per world)
   // split schedule (mode 0 only): which stages of the step this launch runs (ST_*), the per-environment carry of the hot
   // workspace between launches, and the lists of environments left to the sweep kernel
-  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count;
+  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count; unsigned* rs_used;
 };
 
 template <int T>
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
   C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.seed = a.seed;
   C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg; C.dropped = a.dropped;
-  C.split = (a.mode == 0 && a.stages != ST_ALL) ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count;
+  C.split = (a.mode == 0 && a.stages != ST_ALL) ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count; C.rs_used = a.rs_used;
   { // environments that share a warp once the row-space sweeps remap the threads (thread t -> lane t % T of environment t / T)
     const int G = T >= 32 ? 1 : 32 / T, g0 = ei / G * G;
     C.grp0 = g0 - ei; C.grp1 = (g0 + G < E ? g0 + G : E) - ei;
@@ -297,26 +297,33 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
   return hit;
 }
 
-// per visual shape in shared memory: R(9) p(3) dims(4) rgb(3) type(1) bound radius(1), then the camera-relative part that
-// is the same for every pixel: M = R_shape^T R_cam (9), ray origin in the shape frame (3), |origin|^2 - radius^2 (1)
-#define VS_W 36
-#ifndef DG_TILE
-#define DG_TILE 32   // square pixel tile per block; 256 threads, 4 pixels each
-#endif
-__global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
+// per visual shape in shared memory, in FRONT-TO-BACK order (by the nearest eye-space depth of its oriented bounding box):
+//   R(9) p(3) dims(4) rgb(3) type(1) bound radius(1) | M = R_shape^T R_cam (9), ray origin in the shape frame (3),
+//   |origin|^2 - radius^2 (1) | nearest depth zmin (1), screen rectangle x0 x1 y0 y1 of the box (4, pixels, inclusive), body id (1)
+#define VS_W 40
+#define VS_ZMIN 34
+#define VS_RECT 35
+#define VS_BODY 39
+__global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
-  // a block = one environment and every `groups`-th pixel tile of its image: the world pose and camera-relative
-  // constants of all visual shapes are worked out once per block, then the tiles are culled and ray-cast one by one
-  extern __shared__ __align__(16) float vs[];       // [nv][VS_W] then the candidate bit set
+  // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
+  // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 4 pixel patches:
+  // the shapes whose rectangle overlaps the patch (a bit per shape, in that order), per pixel the ray against those shapes,
+  // nearest first, until the next shape's nearest depth is behind the hit already found; the patch is staged in shared memory
+  // and written as whole 128-bit pieces of image rows.
+  extern __shared__ __align__(16) float vs[];       // [nv][VS_W], then keys [nv], then the candidate bit set
   __shared__ float camRp[12];
-  __shared__ float cone[5];                          // unit axis of the tile (3), tan and 1/cos of its half angle
-  const int tiles = tiles_x * tiles_y;
+  __shared__ __align__(16) float t_rgb[8 * 96];   // per warp: a patch of 32 pixels
+  __shared__ __align__(16) float t_dep[8 * 32];
+  __shared__ __align__(16) float t_seg[8 * 32];
+  (void)tiles_x; (void)tiles_y;
   const int e = blockIdx.x / groups, grp = blockIdx.x % groups;
   const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
   const int width = ci[1], height = ci[2];
-  unsigned* cand = reinterpret_cast<unsigned*>(vs + VS_W * sc.nv);
+  float* key = vs + VS_W * sc.nv;
+  unsigned* cand = reinterpret_cast<unsigned*>(key + ((sc.nv + 3) & ~3));
   const int ncw = (sc.nv + 31) / 32;
-  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr;
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr; C.rs_used = nullptr;
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
   const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
@@ -326,83 +333,151 @@ __global__ void __launch_bounds__(256) dg_render_kernel(const __grid_constant__ 
     q_to_mat(Rl, cf + 3); m_mul(camRp, Rp, Rl); m_vec(t, Rp, cf); v_add(camRp + 9, pp, t);
   }
   __syncthreads();
-  for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
-    const int* vi = sc.vis_i + DG_VIS_I_W * s; const float* vf = sc.vis_f + DG_VIS_F_W * s; float* o = vs + VS_W * s;
-    if (vi[2]) { for (int i = 0; i < 12; i++) o[i] = sc.vis_wb[12 * s + i]; }
-    else {
-      float p[3], q[4], v[3], w[3], R[9], Rs[9], t[3];
-      frame_com_state(C, vi[0], p, q, v, w); q_to_mat(R, q); q_to_mat(Rs, vf + 3); m_mul(o, R, Rs);
-      m_vec(t, R, vf); v_add(o + 9, p, t);
+  // ---- per-shape records (registers), keys, ranks, records to their sorted slot --------------------------------------------------
+  for (int s0 = 0; s0 < sc.nv; s0 += blockDim.x) {
+    const int s = s0 + threadIdx.x; float o[VS_W];
+    if (s < sc.nv) {
+      const int* vi = sc.vis_i + DG_VIS_I_W * s; const float* vf = sc.vis_f + DG_VIS_F_W * s;
+      if (vi[2]) { for (int i = 0; i < 12; i++) o[i] = sc.vis_wb[12 * s + i]; }
+      else {
+        float p[3], q[4], v[3], w[3], R[9], Rs[9], t[3];
+        frame_com_state(C, vi[0], p, q, v, w); q_to_mat(R, q); q_to_mat(Rs, vf + 3); m_mul(o, R, Rs);
+        m_vec(t, R, vf); v_add(o + 9, p, t);
+      }
+      for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
+      for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
+      o[19] = int_as_float(vi[1]); o[20] = vf[15];
+      const float r = o[20];
+      float oc[3], ol[3]; v_sub(oc, camRp + 9, o + 9); mT_vec(ol, o, oc);
+      mT_mul(o + 21, o, camRp);                                   // camera-space direction -> shape-frame direction
+      o[30] = ol[0]; o[31] = ol[1]; o[32] = ol[2]; o[33] = v_dot(ol, ol) - r * r;
+      // oriented bounding box of the shape -> nearest eye-space depth and screen rectangle (whole screen if it reaches behind the eye)
+      const int type = vi[1]; const float* d = o + 12;
+      float hx = d[0], hy = d[1], hz = d[2];
+      if (type == SHAPE_SPHERE) { hy = d[0]; hz = d[0]; } else if (type == SHAPE_CAPSULE) { hy = d[0]; hz = d[1] + d[0]; } else if (type == SHAPE_CYLINDER) { hy = d[0]; hz = d[1]; }
+      // corners in camera space; the part of the box in front of the eye plane z = -zc is what can be seen: its screen rectangle
+      // comes from the corners in front and from the points where edges cross that plane
+      const float zc = fmaxf(0.5f * nearp, 1e-4f);
+      float ccx[8], ccy[8], ccd[8];
+      float zmin = 1e30f, x0 = 1e30f, x1 = -1e30f, y0 = 1e30f, y1 = -1e30f;
+      const float sx = 0.5f * width / (th * aspect), sy = 0.5f * height / th;
+      auto add_pt = [&](float cx, float cy, float dep) {
+        const float px = fminf(fmaxf(cx / dep * sx, -1e6f), 1e6f) + 0.5f * width - 0.5f, py = fminf(fmaxf(-cy / dep * sy, -1e6f), 1e6f) + 0.5f * height - 0.5f;
+        x0 = fminf(x0, px); x1 = fmaxf(x1, px); y0 = fminf(y0, py); y1 = fmaxf(y1, py);
+      };
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const float cl[3] = {(k & 1) ? hx : -hx, (k & 2) ? hy : -hy, (k & 4) ? hz : -hz};
+        float cw[3], rel[3], cc[3]; m_vec(cw, o, cl); v_add(cw, cw, o + 9); v_sub(rel, cw, camRp + 9); mT_vec(cc, camRp, rel);
+        ccx[k] = cc[0]; ccy[k] = cc[1]; ccd[k] = -cc[2];
+        zmin = fminf(zmin, ccd[k]);
+        if (ccd[k] > zc) add_pt(cc[0], cc[1], ccd[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+#pragma unroll
+        for (int bit = 1; bit < 8; bit <<= 1) {
+          if (k & bit) continue;
+          const int k2 = k | bit;
+          if ((ccd[k] > zc) == (ccd[k2] > zc)) continue;
+          const float t = (zc - ccd[k]) / (ccd[k2] - ccd[k]);
+          add_pt(ccx[k] + t * (ccx[k2] - ccx[k]), ccy[k] + t * (ccy[k2] - ccy[k]), zc);
+        }
+      }
+      if (x1 < x0) { x0 = y0 = 1e9f; x1 = y1 = -1e9f; }   // nothing of the box in front of the eye: never a candidate
+      zmin = fmaxf(zmin, 0.f);
+      o[VS_ZMIN] = zmin;
+      o[VS_RECT] = floorf(fmaxf(x0, -1e6f)) - 1.f; o[VS_RECT + 1] = ceilf(fminf(x1, 1e6f)) + 1.f;
+      o[VS_RECT + 2] = floorf(fmaxf(y0, -1e6f)) - 1.f; o[VS_RECT + 3] = ceilf(fminf(y1, 1e6f)) + 1.f;
+      o[VS_BODY] = (float)vi[3];
+      key[s] = zmin;
     }
-    for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
-    for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
-    o[19] = int_as_float(vi[1]); o[20] = vf[15];
-    const float r = o[20];
-    float oc[3], ol[3]; v_sub(oc, camRp + 9, o + 9); mT_vec(ol, o, oc);
-    mT_mul(o + 21, o, camRp);                                   // camera-space direction -> shape-frame direction
-    o[30] = ol[0]; o[31] = ol[1]; o[32] = ol[2]; o[33] = v_dot(ol, ol) - r * r;
+    __syncthreads();
+    if (s < sc.nv) {
+      int rank = 0; const float ks = key[s];
+      for (int s2 = 0; s2 < sc.nv; s2++) { const float k2 = key[s2]; rank += (k2 < ks || (k2 == ks && s2 < s)) ? 1 : 0; }
+      float* dst = vs + VS_W * rank;
+#pragma unroll
+      for (int i = 0; i < VS_W; i += 4) st4(dst + i, o[i], o[i + 1], o[i + 2], o[i + 3]);
+    }
   }
+  __syncthreads();
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
   const int npx = width * height;
-  float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx;
-  for (int tile = grp; tile < tiles; tile += groups) {
-    const int ty = tile / tiles_x, tx = tile % tiles_x;
-    __syncthreads();                                   // shapes staged / the previous tile's candidates no longer read
-    if (threadIdx.x < ncw) cand[threadIdx.x] = 0u;
-    if (threadIdx.x == 32) {
-      // cone around the tile: axis through the tile centre, half angle to the farthest corner
-      float x0 = tx * DG_TILE, x1 = fminf((float)width, x0 + DG_TILE), y0 = ty * DG_TILE, y1 = fminf((float)height, y0 + DG_TILE);
-      float dcc[3] = {((0.5f * (x0 + x1)) / width * 2 - 1) * th * aspect, (1 - (0.5f * (y0 + y1)) / height * 2) * th, -1.0f}, axis[3];
-      m_vec(axis, camRp, dcc); float an = 1.0f / v_len(axis); v_scale(axis, axis, an);
-      float cmin = 1.0f;
-      for (int k = 0; k < 4; k++) {
-        float cx = (k & 1) ? x1 : x0, cy = (k & 2) ? y1 : y0;
-        float dk[3] = {(cx / width * 2 - 1) * th * aspect, (1 - cy / height * 2) * th, -1.0f}, dw[3];
-        m_vec(dw, camRp, dk); cmin = fminf(cmin, v_dot(dw, axis) / v_len(dw));
+  float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx; float* seg_e = seg ? seg + (size_t)e * npx : nullptr;
+  // Every WARP renders patches of MT_W x MT_H = 32 pixels on its own (no block barrier in this loop): the lanes test the shapes'
+  // screen rectangles against the patch (ballots -> candidate bits in registers, front to back), every lane casts the ray of its
+  // pixel, and the patch goes out as 128-bit pieces of image rows through the warp's slice of the staging buffers.
+  constexpr int MT_W = 8, MT_H = 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int mtx = (width + MT_W - 1) / MT_W, mty = (height + MT_H - 1) / MT_H, nmt = mtx * mty;
+  const bool vec_ok = (width % 4) == 0;   // image rows and patch offsets keep 16-byte alignment
+  float* w_rgb = t_rgb + 96 * warp; float* w_dep = t_dep + 32 * warp; float* w_seg = t_seg + 32 * warp;
+  const int ncw2 = ncw < 4 ? ncw : 4;     // candidate words kept in registers (128 shapes; beyond that: see below)
+  for (int mt = grp * nwarp + warp; mt < nmt; mt += groups * nwarp) {
+    const int px0 = (mt % mtx) * MT_W, py0 = (mt / mtx) * MT_H;
+    unsigned cw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int wd = 0; wd < 4; wd++) if (wd < ncw2) {
+      const int s = 32 * wd + lane; bool hit = false;
+      if (s < sc.nv) {
+        const float* o = vs + VS_W * s;
+        hit = o[VS_RECT] <= (float)(px0 + MT_W - 1) && o[VS_RECT + 1] >= (float)px0 && o[VS_RECT + 2] <= (float)(py0 + MT_H - 1) && o[VS_RECT + 3] >= (float)py0;
       }
-      cmin = fmaxf(cmin * 0.9999f, 0.05f);
-      cone[0] = axis[0]; cone[1] = axis[1]; cone[2] = axis[2]; cone[3] = sqrtf(fmaxf(1.0f - cmin * cmin, 0.f)) / cmin; cone[4] = 1.0f / cmin;
+      cw[wd] = __ballot_sync(0xffffffffu, hit);
     }
-    __syncthreads();
-    for (int s = threadIdx.x; s < sc.nv; s += blockDim.x) {
-      // bounding sphere against the tile cone (conservative): perpendicular distance <= depth * tan(a) + r / cos(a)
-      const float* o = vs + VS_W * s;
-      float vc[3]; v_sub(vc, o + 9, camRp + 9);
-      float t_ax = v_dot(vc, cone), perp2 = fmaxf(v_dot(vc, vc) - t_ax * t_ax, 0.f), r = o[20];
-      float lim = fmaxf(t_ax, 0.f) * cone[3] + r * cone[4];
-      if (t_ax > -r && perp2 <= lim * lim) atomicOr(&cand[s >> 5], 1u << (s & 31));
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < DG_TILE * DG_TILE; k += blockDim.x) {
-      int i = tx * DG_TILE + (k % DG_TILE), j = ty * DG_TILE + (k / DG_TILE);
-      if (i >= width || j >= height) continue;
-      int px = j * width + i;
+    const int li = lane % MT_W, lj = lane / MT_W, i = px0 + li, j = py0 + lj;
+    float r = 1.0f, g = 1.0f, bl = 1.0f, dz = -farp, sid = -1.0f;
+    if (i < width && j < height) {
       const float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f};
       const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
       float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
-      for (int wd = 0; wd < ncw; wd++) {
-        unsigned bits = cand[wd];
-        while (bits) {
-          int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1;
-          const float* o = vs + VS_W * s;
-          float dl[3]; m_vec(dl, o + 21, dc);
-          const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
-          if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) continue;
-          float tt, nn[3];
-          if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
+      bool done = false;
+      auto try_shape = [&](int s) {
+        const float* o = vs + VS_W * s;
+        // the ray parameter IS the eye-space depth (the camera-space direction has z = -1): nothing behind `best` can win
+        if (o[VS_ZMIN] >= best) { done = true; return; }
+        float dl[3]; m_vec(dl, o + 21, dc);
+        const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
+        if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) return;
+        float tt, nn[3];
+        if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
+      };
+#pragma unroll
+      for (int wd = 0; wd < 4; wd++) {
+        unsigned bits = (wd < ncw2 && !done) ? cw[wd] : 0u;
+        while (bits && !done) { const int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1; try_shape(s); }
+      }
+      for (int s = 128; s < sc.nv && !done; s++) {              // scenes with more than 128 visual shapes: the rest one by one
+        const float* o = vs + VS_W * s;
+        if (o[VS_RECT] <= (float)i && o[VS_RECT + 1] >= (float)i && o[VS_RECT + 2] <= (float)j && o[VS_RECT + 3] >= (float)j) try_shape(s);
+      }
+      if (hs >= 0) {
+        float hn[3]; m_vec(hn, vs + VS_W * hs, hnl);
+        const float* col = vs + VS_W * hs + 16; const float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
+        r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best; sid = vs[VS_W * hs + VS_BODY];
+      }
+    }
+    const int wt = min(MT_W, width - px0), ht = min(MT_H, height - py0);
+    if (vec_ok && wt == MT_W) {
+      __syncwarp();
+      w_rgb[3 * lane] = r; w_rgb[3 * lane + 1] = g; w_rgb[3 * lane + 2] = bl; w_dep[lane] = dz; w_seg[lane] = sid;
+      __syncwarp();
+      // 6 float4 of colour and 2 of depth per patch row: lanes 0..23 colour, 24..31 depth (and mask)
+      if (lane < 24) {
+        const int row = lane / 6, c = lane % 6;
+        if (row < ht) *reinterpret_cast<float4*>(rgb_e + ((size_t)(py0 + row) * width + px0) * 3 + 4 * c) = *reinterpret_cast<const float4*>(w_rgb + 24 * row + 4 * c);
+      } else {
+        const int row = (lane - 24) / 2, c = (lane - 24) % 2;
+        if (row < ht) {
+          *reinterpret_cast<float4*>(dep_e + (size_t)(py0 + row) * width + px0 + 4 * c) = *reinterpret_cast<const float4*>(w_dep + 8 * row + 4 * c);
+          if (seg_e) *reinterpret_cast<float4*>(seg_e + (size_t)(py0 + row) * width + px0 + 4 * c) = *reinterpret_cast<const float4*>(w_seg + 8 * row + 4 * c);
         }
       }
-      float hn[3] = {0, 0, 1};
-      if (hs >= 0) m_vec(hn, vs + VS_W * hs, hnl);
-      float r, g, bl, dz;
-      if (hs < 0) { r = g = bl = 1.0f; dz = -farp; }
-      else {
-        const float* col = vs + VS_W * hs + 16; float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
-        r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best;
-      }
+    } else if (i < width && j < height) {
+      const size_t px = (size_t)j * width + i;
       rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
-      // segmentation mask (camera.py:89-90): unique id of the visible body, -1 where the ray hits nothing
-      if (seg != nullptr) seg[(size_t)e * npx + px] = hs < 0 ? -1.0f : (float)sc.vis_i[DG_VIS_I_W * hs + 3];
+      if (seg_e) seg_e[px] = sid;
     }
   }
 }
@@ -430,7 +505,15 @@ struct DgWorld {
   float* carry = nullptr;              // [n_envs + slack][w_total] hot workspaces between stage launches
   int* rs_lists = nullptr;             // [2][n_envs] environments deferred to the sweep kernel (K = 1 | K = 2)
   int* rs_counts = nullptr;            // [substeps][2]
-  cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the K = 2 sweeps run beside the K = 1 sweeps
+  cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the one-per-warp sweeps run beside the two-per-warp sweeps
+  // Which schedule a step takes is decided from how many environments actually needed the contact solver lately: the stage
+  // launches + carry traffic cost ~0.3 ms per step, which only pays when a good share of the environments is in contact
+  // (a drone in the air, an R2D2 still falling: fused launch).  The device counter is copied to pinned memory every
+  // kAdaptPeriod steps, asynchronously, and read one period later - no host synchronisation on the step path.
+  bool split_ok = false;               // the scene and team allow the split schedule at all
+  int split_mode = -1;                 // DG_SPLIT: 0 never, 1 always, -1 adaptive
+  unsigned* rs_used = nullptr; unsigned* h_rs_used = nullptr; cudaEvent_t ev_stat = nullptr;
+  int steps_in_period = 0; bool stat_pending = false;
   int64_t launches = 0;
   std::string err;
 };
@@ -563,19 +646,20 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
     w->dev.g_total = w->hs.dev.g_total;
   }
   {
-    // split schedule: scenes in which a floating body rests on contacts (contacts are the norm, not the exception) leave the
-    // contact sweeps to the sweep kernel; DG_SPLIT=0/1 overrides.  Needs the row-space solver (team of >= 2 lanes).
-    bool floating = false;
-    const int32_t* bsec = ibuf + ibuf[2 + 3 * SEC_BODY_I + 1];
-    for (int b = 0; b < w->hs.dev.nb; b++) floating = floating || bsec[DG_BODY_I_W * b] == 2;
-    w->split = w->hs.dev.rs_cap > 0 && w->hs.dev.solver == 1 && ((floating && w->hs.dev.npair > 0) || w->hs.dev.ncons > 0);
-    if (const char* env_split = getenv("DG_SPLIT")) w->split = atoi(env_split) != 0 && w->hs.dev.rs_cap > 0 && w->hs.dev.solver == 1;
-    if (w->split) {
+    // split schedule: possible for every scene with contacts or welds and a team of >= 2 lanes (row-space solver); taken when
+    // enough environments are in contact (adaptive, see DgWorld).  DG_SPLIT=0 / 1 forces never / always.
+    w->split_ok = w->hs.dev.rs_cap > 0 && w->hs.dev.solver == 1 && (w->hs.dev.npair > 0 || w->hs.dev.ncons > 0);
+    if (const char* env_split = getenv("DG_SPLIT")) w->split_mode = atoi(env_split) != 0 ? 1 : 0;
+    if (w->split_mode == 0) w->split_ok = false;
+    w->split = w->split_ok && (w->split_mode == 1 || w->hs.dev.ncons > 0);   // welded models always have rows; else start fused and adapt
+    if (w->split_ok) {
       const size_t nc = ((size_t)w->n_envs + 256) * (size_t)w->hs.dev.w_total * sizeof(float);
       bool ok = cudaMalloc(&w->carry, nc) == cudaSuccess && cudaMalloc(&w->rs_lists, 2 * (size_t)w->n_envs * sizeof(int)) == cudaSuccess &&
                 cudaMalloc(&w->rs_counts, 2 * (size_t)std::max(w->hs.dev.substeps, 1) * sizeof(int)) == cudaSuccess &&
                 cudaStreamCreateWithFlags(&w->aux, cudaStreamNonBlocking) == cudaSuccess &&
-                cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess;
+                cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&w->ev_stat, cudaEventDisableTiming) == cudaSuccess && cudaMalloc(&w->rs_used, sizeof(unsigned)) == cudaSuccess &&
+                cudaMemset(w->rs_used, 0, sizeof(unsigned)) == cudaSuccess && cudaMallocHost(&w->h_rs_used, sizeof(unsigned)) == cudaSuccess;
       if (!ok) { g_create_err = "allocation of the split-schedule buffers failed"; cudaGetLastError(); dg_world_destroy(w); return DG_E_CUDA; }
     }
   }
@@ -598,6 +682,9 @@ void dg_world_destroy(DgWorld* w) {
   if (w->aux) cudaStreamDestroy(w->aux);
   if (w->ev_fork) cudaEventDestroy(w->ev_fork);
   if (w->ev_join) cudaEventDestroy(w->ev_join);
+  if (w->ev_stat) cudaEventDestroy(w->ev_stat);
+  if (w->rs_used) cudaFree(w->rs_used);
+  if (w->h_rs_used) cudaFreeHost(w->h_rs_used);
   delete w;
 }
 
@@ -660,8 +747,25 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   DeviceGuard guard(w->device);
   if (!guard.ok) { w->err = "cudaSetDevice failed"; cudaGetLastError(); return DG_E_CUDA; }
   LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg, w->dropped,
-               ST_ALL, nullptr, nullptr, nullptr, nullptr};
+               ST_ALL, nullptr, nullptr, nullptr, nullptr, mode == 0 ? w->rs_used : nullptr};
   cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 0 && w->split_ok && w->split_mode < 0 && w->dev.ncons == 0) {
+    // adaptive schedule: share of environment sub-steps that needed the contact solver over the last period
+    constexpr int kAdaptPeriod = 16;
+    const cudaError_t qe = w->stat_pending ? cudaEventQuery(w->ev_stat) : cudaErrorNotReady;
+    if (qe != cudaSuccess) cudaGetLastError();   // (cudaErrorNotReady is no error: keep it out of the next launch check)
+    if (w->stat_pending && qe == cudaSuccess) {
+      const double share = (double)*w->h_rs_used / ((double)kAdaptPeriod * std::max(w->dev.substeps, 1) * w->n_envs);
+      if (share > 0.30) w->split = true; else if (share < 0.15) w->split = false;
+      w->stat_pending = false;
+    }
+    if (++w->steps_in_period >= kAdaptPeriod && !w->stat_pending) {
+      CK(w, cudaMemcpyAsync(w->h_rs_used, w->rs_used, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+      CK(w, cudaMemsetAsync(w->rs_used, 0, sizeof(unsigned), s));
+      CK(w, cudaEventRecord(w->ev_stat, s));
+      w->stat_pending = true; w->steps_in_period = 0;
+    }
+  }
   if (mode != 0 || !w->split) { CK(w, launch_any(w, a, s)); return DG_OK; }
   // Split schedule of one step with n sub-steps (2 for the reference's settings, diy_gym.py:76-79):
   //   stage launch [add-on update, load | sub-step 0 up to the row-space system] -> sweeps ->
@@ -719,11 +823,11 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   if (cam < 0 || cam >= d.ncam) { w->err = "dg_render: no such camera"; return DG_E_ARG; }
   DeviceGuard guard(w->device);
   const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
-  int tiles_x = (ci[1] + DG_TILE - 1) / DG_TILE, tiles_y = (ci[2] + DG_TILE - 1) / DG_TILE;
-  size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)(d.nv + 31) / 32 + 4) * sizeof(float);
+  int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 3) / 4;   // patches of 8 x 4 pixels, one per warp at a time
+  size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)((d.nv + 3) & ~3) + (size_t)(d.nv + 31) / 32 + 8) * sizeof(float);
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
-  int groups = std::max(1, std::min(tiles_x * tiles_y, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
+  int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
   w->launches++;
   dg_render_kernel<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
   CK(w, cudaGetLastError());

@@ -345,6 +345,8 @@ struct HostScene {
               " rows need a team of at least " + std::to_string((rows_pad + RS_KMAX - 1) / RS_KMAX) + " lanes (and at most " + std::to_string((int)RS_GVMAX) + " generalized coordinates)";
       return false;
     }
+    // every environment with contacts is solved in row space (round 1 kept uncoupled ones on the per-body sweeps: its row-space
+    // sweeps were slower, profiles/r1_rs_min_sweep.log; DG_RS_MIN restores that for A/B runs)
     d.solver = 1; d.rs_min = 0;   // every environment with contacts is solved in row space (round 1 kept uncoupled ones on the per-body sweeps: its row-space sweeps were slower, profiles/r1_rs_min_sweep.log; DG_RS_MIN restores that for A/B runs)
     d.rs_ashared = 0; d.X_RSAS = 0; (void)rs_ashared;   // (shared-memory home of A: measured slower, removed)
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);

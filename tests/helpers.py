@@ -109,6 +109,7 @@ def strict_single_step_parity(env, n_envs, steps, seed=4321, presteps=3, action_
         for _ in range(presteps + i % 4):      # decorrelate the environments
             o.env_step(rng.uniform(lo, hi))
     recs = []
+    ncon_prev = np.array([len(o.contacts()) for o in oracles])
     for k in range(steps):
         st = np.stack([o.state for o in oracles]).astype(np.float32)
         w.state.copy_(torch.from_numpy(st))
@@ -126,13 +127,15 @@ def strict_single_step_parity(env, n_envs, steps, seed=4321, presteps=3, action_
         sg = w.state.cpu().numpy().astype(np.float64)
         so = np.stack([o.state for o in oracles])
         rec = {'step': k, 'contacts': ncon, 'err': {}, 'bar': {}, 'err_free': {}}
-        free = ncon == 0
+        free = (ncon == 0) & (ncon_prev == 0)   # contact-free: no contact in the oracle before or after the step
+        ncon_prev = ncon
         for key, nm, n, floor in (('q', 'S_Q', nd, 0.0), ('qd', 'S_QD', nd, 1e-2), ('base_pos', 'S_BPOS', 3 * nb, 0.0), ('base_quat', 'S_BQUAT', 4 * nb, 0.0),
                                   ('base_vel', 'S_BVEL', 3 * nb, 1e-2), ('base_omega', 'S_BOMEGA', 3 * nb, 1e-2)):
             if n == 0:
                 continue
             g, o_ = sg[:, h[nm]:h[nm] + n], so[:, h[nm]:h[nm] + n]
             rec['err'][key] = float(np.abs(g - o_).max())
+            rec.setdefault('err_env', {})[key] = np.abs(g - o_).max(axis=1)   # per environment
             rec['err_free'][key] = float(np.abs(g - o_)[free].max()) if free.any() else 0.0
             rec['bar'][key] = 1e-4 * max(float(np.abs(o_).max()), floor)
         rec['obs'] = (w.obs.cpu().numpy().astype(np.float64), np.stack([x[0] for x in outs]))
