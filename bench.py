@@ -39,6 +39,7 @@ CONFIGS = {
     'basic_env': ('examples/basic_env/basic_env.yaml', 4096),
     'ur_admittance': ('examples/ur_admittance/ur_admittance.yaml', 8192),
     'ur_gripper': ('examples/ur_gripper/ur_gripper.yaml', 4096),
+    'ur_extras': ('examples/ur_extras/ur_extras.yaml', 4096),
 }
 METRIC = 'aggregate env-steps/sec'
 UNIT = 'env-steps/s'

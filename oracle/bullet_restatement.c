@@ -1187,3 +1187,48 @@ void dgo_render_seg(DgoWorld* W, int cam, double* rgb, double* depth, double* se
   free(VR);
 }
 void dgo_render(DgoWorld* W, int cam, double* rgb, double* depth) { dgo_render_seg(W, cam, rgb, depth, (double*)0); }
+
+/* p.getCameraImage(width, height, viewMatrix, projectionMatrix) as the reference calls it (camera.py:70-74): the camera is given
+ * ONLY by the two column-major 4x4 OpenGL matrices the caller hands over - nothing of this repo's camera tables is consulted, so a
+ * pose / field-of-view / row-order convention that differs between the reference's add-on and the compiled camera shows up as a
+ * different image.  Returns what pybullet returns: rgba bytes [height][width][4], the NON-linear depth buffer in [0,1]
+ * (z_ndc * 0.5 + 0.5, which camera.py:80-85 turns back into eye-space z) and the body id per pixel (-1 background).
+ * Shading and intersection routines are those of dgo_render_seg (the renderer itself is this repo's, TinyRenderer is absent). */
+void dgo_get_camera_image(DgoWorld* W, int width, int height, const double* view, const double* proj, unsigned char* rgba, double* depth01, int* segm) {
+  /* view = [R^T | -R^T p] column-major: eye axes are the rows of its rotation block */
+  double Rc[9], pc[3], tv[3] = {view[12], view[13], view[14]};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rc[3 * i + j] = view[4 * i + j];     /* world_from_eye rotation = (R^T)^T */
+  for (int i = 0; i < 3; i++) pc[i] = -(Rc[3 * i] * tv[0] + Rc[3 * i + 1] * tv[1] + Rc[3 * i + 2] * tv[2]);
+  const double p00 = proj[0], p11 = proj[5], p22 = proj[10], p32 = proj[14];                   /* column-major: proj[4 c + r] */
+  const double nearp = p32 / (p22 - 1.0), farp = p32 / (p22 + 1.0);
+  int nv = W->nv; double* VR = (double*)malloc(sizeof(double) * 12 * (size_t)(nv > 0 ? nv : 1)); double t[3];
+  for (int s = 0; s < nv; s++) {
+    const int32_t* vi = W->vis_i + DG_VIS_I_W * s; const double* vf = W->vis_f + DG_VIS_F_W * s;
+    double p[3], q[4], v[3], o[3], R[9], Rs[9];
+    frame_com_state(W, vi[0], p, q, v, o); q_to_mat(R, q); q_to_mat(Rs, vf + 3); m_mul(VR + 12 * s, R, Rs);
+    m_vec(t, R, vf); v_add(VR + 12 * s + 9, p, t);
+  }
+  const double light[3] = {0.4082482904638631, 0.4082482904638631, 0.8164965809277261};
+  for (int j = 0; j < height; j++) for (int i = 0; i < width; i++) {
+    /* pixel centre -> normalised device coordinates (row 0 is the top of the image) -> eye-space direction with z = -1 */
+    const double xn = (i + 0.5) / width * 2 - 1, yn = 1 - (j + 0.5) / height * 2;
+    double dc[3] = {xn / p00, yn / p11, -1.0}, dw[3];
+    m_vec(dw, Rc, dc);
+    double best = farp; int hs = -1; double hn[3] = {0, 0, 1};
+    for (int s = 0; s < nv; s++) {
+      const int32_t* vi = W->vis_i + DG_VIS_I_W * s; const double* vf = W->vis_f + DG_VIS_F_W * s;
+      double oc[3], ol[3], dl[3], tt, nn[3];
+      v_sub(oc, pc, VR + 12 * s + 9); mT_vec(ol, VR + 12 * s, oc); mT_vec(dl, VR + 12 * s, dw);
+      if (ray_shape(vi[1], vf + 7, ol, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; m_vec(hn, VR + 12 * s, nn); }
+    }
+    const int px = j * width + i;
+    double col[3] = {1, 1, 1};
+    if (hs >= 0) { const double* c = W->vis_f + DG_VIS_F_W * hs + 11; double nl = v_dot(hn, light); if (nl < 0) nl = 0; const double sh = 0.4 + 0.6 * nl; for (int k = 0; k < 3; k++) col[k] = c[k] * sh; }
+    for (int k = 0; k < 3; k++) { double b = floor(col[k] * 255.0 + 0.5); rgba[4 * px + k] = (unsigned char)(b < 0 ? 0 : (b > 255 ? 255 : b)); }
+    rgba[4 * px + 3] = 255;
+    /* eye depth `best` -> z_ndc = (p22 * (-best) + p32) / best -> depth buffer value */
+    depth01[px] = 0.5 * ((p22 * (-best) + p32) / best) + 0.5;
+    if (segm) segm[px] = hs < 0 ? -1 : W->vis_i[DG_VIS_I_W * hs + 3];
+  }
+  free(VR);
+}

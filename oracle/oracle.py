@@ -54,6 +54,7 @@ def lib():
         L.dgo_env_step.argtypes = [vp, dp, dp, dp, u8]
         L.dgo_render.argtypes = [vp, ctypes.c_int, dp, dp]
         L.dgo_render_seg.argtypes = [vp, ctypes.c_int, dp, dp, dp]
+        L.dgo_get_camera_image.argtypes = [vp, ctypes.c_int, ctypes.c_int, dp, dp, ctypes.POINTER(ctypes.c_uint8), dp, ctypes.POINTER(ctypes.c_int32)]
         L.dgo_batch_max_threads.restype = ctypes.c_int
         L.dgo_batch_step.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, dp, ctypes.c_int, dp,
                                      ctypes.c_int, u8, ctypes.c_int, ctypes.c_int]
@@ -147,6 +148,16 @@ class OracleWorld:
             lib().dgo_get_contact(self._w, i, _dp(c))
             out.append(dict(fa=int(c[0]), fb=int(c[1]), pa=c[2:5], pb=c[5:8], n=c[8:11], dist=c[11], mu=c[12]))
         return out
+
+    def get_camera_image(self, width, height, view, proj):
+        """p.getCameraImage: camera given by column-major view / projection matrices only -> (rgba u8 [H,W,4], depth buffer [H,W], ids [H,W])."""
+        rgba = np.zeros((height, width, 4), np.uint8)
+        depth = np.zeros((height, width))
+        segm = np.zeros((height, width), np.int32)
+        v, pm = np.ascontiguousarray(view, np.float64).reshape(-1), np.ascontiguousarray(proj, np.float64).reshape(-1)
+        lib().dgo_get_camera_image(self._w, int(width), int(height), _dp(v), _dp(pm), rgba.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), _dp(depth),
+                                   segm.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+        return rgba, depth, segm
 
     def render(self, cam=0, seg=False):
         w, hgt = int(self.scene.sec['CAM_I'][cam][1]), int(self.scene.sec['CAM_I'][cam][2])

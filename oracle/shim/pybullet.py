@@ -52,7 +52,7 @@ class _Sim:
         p = self.params
         sb = SceneBuilder(timestep=p['timestep'], substeps=max(int(p['substeps']), 1), iterations=int(p['iterations']), gravity=p['gravity'], hot_start=0)
         for i, s in enumerate(self.specs):
-            sb.add_body('body%d' % i, s['desc'], xyz=s['pos'], quat=s['quat'], scale=s['scale'], fixed_base=s['fixed'], mass=s['mass'])
+            sb.add_body('body%d' % i, s['desc'], xyz=s['pos'], quat=s['quat'], scale=s['scale'], fixed_base=s['fixed'], mass=s['mass'], color=s.get('color'))
         for c in self.constraints:
             sb.add_fixed_constraint(sb.bodies[c[0]], c[1], sb.bodies[c[2]], c[3], c[4], c[5], c[6], c[7])
         sb.need_jreact = self.ft_sensors
@@ -169,8 +169,11 @@ def changeDynamics(uid, link, mass=None, angularDamping=None, **k):
     raise error('changeDynamics: only the base mass is supported by the oracle shim')
 
 
-def changeVisualShape(*a, **k):
-    pass
+def changeVisualShape(uid, link=-1, rgbaColor=None, **k):
+    """model.py:82-83: the colour of the BASE link's visual shapes (link -1); other arguments (textures) are ignored."""
+    if rgbaColor is not None and link == -1:
+        _sim.specs[uid]['color'] = [float(c) for c in rgbaColor]
+        _sim.dirty = _sim.world is not None
 
 
 def loadTexture(*a, **k):
@@ -438,8 +441,12 @@ def computeProjectionMatrixFOV(fov, aspect, nearVal, farVal, **k):
     return (f / aspect, 0, 0, 0, 0, f, 0, 0, 0, 0, (n + fa) / (n - fa), -1, 0, 0, 2 * fa * n / (n - fa), 0)
 
 
-def getCameraImage(*a, **k):
-    raise error('getCameraImage is not implemented by the oracle shim (the camera is checked against the oracle ray caster directly)')
+def getCameraImage(width, height, viewMatrix=None, projectionMatrix=None, flags=0, **k):
+    """(width, height, rgba u8 [H,W,4], depth buffer [H,W] in [0,1], body ids [H,W]) from the two matrices the caller hands over
+    - oracle.dgo_get_camera_image consults nothing else, so the reference's own camera conventions decide the image."""
+    w = _sim.ensure()
+    rgba, depth, segm = w.get_camera_image(width, height, viewMatrix, projectionMatrix)
+    return (width, height, rgba, depth, segm)
 
 
 def getKeyboardEvents(*a, **k):

@@ -16,7 +16,7 @@ from bench import CONFIGS, register_example_addons
 from diy_gym_b200 import Configuration, DIYGym
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze', 'ur_admittance', 'ur_gripper']
+NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze', 'ur_admittance', 'ur_gripper', 'ur_extras']
 # ur_gripper: the welded child's spawn transient is solved with clamped, unconverged sweeps whose result depends on
 # rounding; the x86 build of the kernel code follows the fp64 rollout from reset, the GPU build is
 # compared after the transient in tests/test_gpu_parity.py instead

@@ -37,6 +37,7 @@ CONFIGS = {
     # the reference ships no config for these add-ons / nested models; these two use its schema and its own classes
     'ur_admittance': os.path.join(ROOT, 'examples', 'ur_admittance', 'ur_admittance.yaml'),
     'ur_gripper': os.path.join(ROOT, 'examples', 'ur_gripper', 'ur_gripper.yaml'),
+    'ur_extras': os.path.join(ROOT, 'examples', 'ur_extras', 'ur_extras.yaml'),
 }
 
 
