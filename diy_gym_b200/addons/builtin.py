@@ -322,9 +322,13 @@ class DynamicsRandomizer(_OpAddon):
         super().__init__(parent, config)
         self.mass_range = list(config.get('mass_range', [0.25, 4.0]))
         self.damping_range = list(config.get('damping_range', [0.2, 20]))
+        # extension keys (BASELINE.json config 5 / SURVEY 8d): lateral friction drawn uniformly per environment and reset, and a
+        # nominal joint damping for models whose URDF gives none (the UR5: damping 0, so damping_range alone would do nothing)
+        self.friction_range = [float(v) for v in config.get('friction_range', [0.0, 0.0])]
+        self.nominal_damping = float(config.get('nominal_damping', 0.0))
 
     def compile(self, sb):
-        self.op = sb.add_op('DYN_RANDOMIZE', [self.parent.body.index], self.mass_range + self.damping_range)
+        self.op = sb.add_op('DYN_RANDOMIZE', [self.parent.body.index], self.mass_range + self.damping_range + self.friction_range + [self.nominal_damping])
 
 
 class SpawnMultiple(Addon):
@@ -414,7 +418,53 @@ class VisualRandomizer(_Unsupported):
     reason = 'downloads a texture dataset over HTTP in the reference; out of scope'
 
 
+class FilteredLinkWrench(_OpAddon):
+    """Building block for USER add-ons that would otherwise run as eager PyTorch every step: a scalar action in [0, 1] goes
+    through a first-order filter (state += (action - state) * rate) and scales a force and a torque given in the frame of a
+    link (applyExternalForce / applyExternalTorque with LINK_FRAME).  One op of the fused step (`FILTERED_WRENCH`); the filter
+    state lives in the state row and is the add-on's observation.  The reference's examples/drone_pilot `Propellor`
+    (drone_pilot.py:10-40) is exactly this - examples/drone_pilot/drone_pilot.py subclasses it.
+    Keys: frame (joint name, default base), force [3], torque [3], position [3] (point of application, link frame), rate,
+    reset_state (default no: the reference's Propellor keeps its rotor speed across resets)."""
+    def __init__(self, parent, config):
+        super().__init__(parent, config)
+        self.frame_id = parent.get_frame_id(config.get('frame')) if 'frame' in config else -1
+        self.force = [float(v) for v in config.get('force', [0.0, 0.0, 0.0])]
+        self.torque = [float(v) for v in config.get('torque', [0.0, 0.0, 0.0])]
+        self.position = [float(v) for v in config.get('position', [0.0, 0.0, 0.0])]
+        self.rate = float(config.get('rate', 0.1))
+        self.reset_state = bool(config.get('reset_state', False))
+        self.observation_space = spaces.Box(0.0, 1.0, shape=(1, ), dtype='float32')
+        self.action_space = spaces.Box(0.0, 1.0, shape=(1, ), dtype='float32')
+
+    def compile(self, sb):
+        slot = sb.alloc_addon_state(1)
+        self.op = sb.add_op('FILTERED_WRENCH', [self.parent.body.frame(self.frame_id), int(self.reset_state), slot],
+                            [self.rate] + self.force + self.torque + self.position, n_act=1, n_obs=1)
+
+    def update(self, action):
+        self._put(self._act, action)
+
+    def observe(self):
+        return self._obs
+
+
+class TiltTerminal(_OpAddon):
+    """Terminal when the base of the parent model is tilted by more than `angle` degrees (op `TILT_TERMINAL`); the reference's
+    examples/drone_pilot `FellOver` (drone_pilot.py:43-55) with its 10 degrees."""
+    def __init__(self, parent, config):
+        super().__init__(parent, config)
+        self.angle = float(config.get('angle', 10.0))
+
+    def compile(self, sb):
+        self.op = sb.add_op('TILT_TERMINAL', [self.parent.body.index], [float(np.radians(self.angle))], n_term=1)
+
+    def is_terminal(self):
+        return self._term.bool()
+
+
 BUILTIN_ADDONS = {
+    'filtered_link_wrench': FilteredLinkWrench, 'tilt_terminal': TiltTerminal,
     'ik_controller': InverseKinematicsController, 'joint_controller': JointController, 'admittance_controller': AdmittanceController,
     'camera': Camera, 'joint_state_sensor': JointStateSensor, 'object_state_sensor': ObjectStateSensor,
     'force_torque_sensor': ForceTorqueSensor, 'reach_target': ReachTarget, 'stuck_joint_cost': StuckJointCost,

@@ -55,7 +55,8 @@ SHAPE_TYPES = {'sphere': 0, 'box': 1, 'capsule': 2, 'cylinder': 3}
 JOINT_TYPES = {'fixed': 0, 'revolute': 1, 'continuous': 1, 'prismatic': 2}
 
 OP = dict(JOINT_CTRL=1, EXT_FORCE=2, IK_CTRL=3, JOINT_SENSOR=4, OBJECT_SENSOR=5, REACH_TARGET=6, ELECTRICITY=7,
-          STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13, ADMITTANCE=14, FT_SENSOR=15)
+          STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13, ADMITTANCE=14, FT_SENSOR=15,
+          FILTERED_WRENCH=16, TILT_TERMINAL=17)
 
 DEFAULT_LATERAL_FRICTION = 0.5
 DEFAULT_DAMPING = 0.04  # multibody linear/angular velocity damping (App. A.2)
@@ -448,6 +449,15 @@ class Scene:
 
     def state_slice(self, name, n):
         return slice(self.hdr[name], self.hdr[name] + n)
+
+
+def write_c_headers():
+    """Regenerates the two copies of scene_sections.h (csrc/ for the kernels, oracle/ for the checker)."""
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    for dst in (os.path.join(here, '..', 'csrc', 'scene_sections.h'), os.path.join(here, '..', '..', 'oracle', 'scene_sections.h')):
+        with open(dst, 'w') as f:
+            f.write(emit_c_header())
 
 
 def emit_c_header():

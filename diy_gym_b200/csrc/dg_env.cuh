@@ -1666,6 +1666,15 @@ DG_FN void phase_actions(const Env& C, int ln, int nt) {
       if (ia[1] == 0) { v_cpy(F, a); v_sub(rel, fa, pos); }
       else { float R[9]; q_to_mat(R, quat); m_vec(F, R, a); m_vec(rel, R, fa); }
       v_add(ST(S_EXTF) + 3 * f, ST(S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(ST(S_EXTT) + 3 * f, ST(S_EXTT) + 3 * f, t);
+    } else if (op[0] == OP_FILTERED_WRENCH && ln == 0) {     // user add-ons lowered to the kernel: examples/drone_pilot Propellor
+      // (drone_pilot.py:31-37 of the reference): first-order filter of the action, link-frame force / torque scaled by its state
+      float* st_ = ST(S_ADDON) + ia[2]; const float s_ = st_[0] + (a[0] - st_[0]) * fa[0];
+      st_[0] = s_;
+      const int f = ia[0]; float pos[3], quat[4], v[3], o[3], R[9], F[3], T[3], rel[3], t[3];
+      frame_com_state(C, f, pos, quat, v, o); q_to_mat(R, quat);
+      const float Fl[3] = {fa[1] * s_, fa[2] * s_, fa[3] * s_}, Tl[3] = {fa[4] * s_, fa[5] * s_, fa[6] * s_};
+      m_vec(F, R, Fl); m_vec(T, R, Tl); m_vec(rel, R, fa + 7);
+      v_add(ST(S_EXTF) + 3 * f, ST(S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(t, t, T); v_add(ST(S_EXTT) + 3 * f, ST(S_EXTT) + 3 * f, t);
     } else if (op[0] == OP_ADMITTANCE && ln == 0) {          // admittance_controller.py:36-55
       admittance_update(C, ia, fa, a);
     } else if (op[0] == OP_IK_CTRL) {                         // ik_controller.py:51-80
@@ -1770,6 +1779,11 @@ DG_FN void phase_observe(const Env& C, int ln, int nt) {
       C.rew[op[5]] = stuck ? -fa[0] : 0.0f;
     } else if (op[0] == OP_TIME_PENALTY) {              // time_penalty.py:11-12
       C.rew[op[5]] = fa[0];
+    } else if (op[0] == OP_FILTERED_WRENCH) {           // Propellor.observe: the filter state (drone_pilot.py:39-40)
+      o[0] = ST(S_ADDON)[ia[2]];
+    } else if (op[0] == OP_TILT_TERMINAL) {             // FellOver.is_terminal (drone_pilot.py:52-55): base tilted by more than fa[0] rad
+      const float* q = ST(S_BQUAT) + 4 * ia[0];
+      C.term[op[6]] = 2.0f * atan2f(sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), fabsf(q[3])) > fa[0];
     } else if (op[0] == OP_EPISODE_TIMER) {             // diy_gym.py:180-183
       C.term[op[6]] = ST(S_STEP)[0] >= fa[0];
     }
@@ -1783,7 +1797,9 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
   uint32_t epoch = (uint32_t)ST(S_RESETS)[0];
   for (int k = 0; k < sc.nop; k++) {
     const int* op = gc(sc.op_i) + DG_OP_I_W * k; const int* ia = gc(sc.oparg_i) + op[1]; const float* fa = gc(sc.oparg_f) + op[2];
-    if (op[0] == OP_JOINT_RESET) {                      // joint_controller.py:36-38, ik_controller.py:47-49
+    if (op[0] == OP_FILTERED_WRENCH) {                  // ia[1]: clear the filter state on reset (the reference's Propellor keeps it)
+      if (ia[1]) ST(S_ADDON)[ia[2]] = 0.f;
+    } else if (op[0] == OP_JOINT_RESET) {               // joint_controller.py:36-38, ik_controller.py:47-49
       for (int i = 0; i < ia[0]; i++) { ST(S_Q)[ia[1 + i]] = fa[i]; ST(S_QD)[ia[1 + i]] = 0.f; }
     } else if (op[0] == OP_RESPAWN) {                   // respawn.py:31-39
       int b = ia[0]; uint32_t ep = ia[1] ? 0u : epoch; const float* ip = PR(P_INITPOSE) + 7 * b;
@@ -1803,7 +1819,15 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
         float ms = expf(logf(fa[0]) + u1 * (logf(fa[1]) - logf(fa[0]))), ds = expf(logf(fa[2]) + u2 * (logf(fa[3]) - logf(fa[2])));
         PR(P_MASS)[f] = gc(sc.param_def)[DG_PO(C.sc, P_MASS) + f] * ms;
         for (int i = 0; i < 3; i++) PR(P_INERTIA)[3 * f + i] = gc(sc.param_def)[DG_PO(C.sc, P_INERTIA) + 3 * f + i] * ms;
-        if (d >= 0) PR(P_JDAMP)[d] = gc(sc.param_def)[DG_PO(C.sc, P_JDAMP) + d] * ds;
+        // fa[6]: nominal joint damping for joints whose URDF gives none (UR5: 0 - scaling it would do nothing; extension key)
+        if (d >= 0) { const float nom = gc(sc.param_def)[DG_PO(C.sc, P_JDAMP) + d]; PR(P_JDAMP)[d] = (nom > 0.f ? nom : fa[6]) * ds; }
+      }
+      // extension key friction_range (BASELINE.json config 5, SURVEY 8d: lateral friction U[0.5, 1.25] per environment): one draw
+      // per body and reset, every collision shape of the body gets it
+      if (fa[5] > 0.f) {
+        const float u3 = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 63));
+        const float fr = fa[4] + u3 * (fa[5] - fa[4]);
+        for (int s2 = 0; s2 < sc.ns; s2++) if (gc(sc.shape_i)[DG_SHAPE_I_W * s2] == b) PR(P_FRICTION)[s2] = fr;
       }
     }
   }

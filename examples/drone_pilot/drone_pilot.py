@@ -1,8 +1,10 @@
 """drone_pilot on the batched backend: N quadrotors, each chasing its own random target.
 
-Shows the user add-on surface: `Propellor` (stateful, link-frame thrust + torque) and `FellOver` (terminal) are
-written once with batched torch ops on the views the parent Model exposes, registered exactly like in the
-reference (`AddonFactory.register_addon`), and used from the unchanged YAML.
+Shows the user add-on surface: `Propellor` (stateful, link-frame thrust + torque) and `FellOver` (terminal) are registered
+exactly like in the reference (`AddonFactory.register_addon`) and used from the unchanged YAML.  They come in two forms: lowered
+to ops of the fused CUDA step (subclasses of the `filtered_link_wrench` / `tilt_terminal` building blocks - the default) and as
+plain batched torch code on the views the parent Model exposes (`PropellorTorch`, `FellOverTorch`: the general path for
+arbitrary user code).
 Semantics follow the reference's examples/drone_pilot/drone_pilot.py:10-59.
 
     python examples/drone_pilot/drone_pilot.py [num_envs] [steps]
@@ -17,10 +19,29 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from diy_gym_b200 import DIYGym, spaces  # noqa: E402
 from diy_gym_b200 import torch_math as tm  # noqa: E402
 from diy_gym_b200.addons.addon import Addon, AddonFactory  # noqa: E402
+from diy_gym_b200.addons.builtin import FilteredLinkWrench, TiltTerminal  # noqa: E402
 
 
-class Propellor(Addon):
-    """First-order rotor spool-up, thrust along the motor link's z axis and a reaction torque about it."""
+class Propellor(FilteredLinkWrench):
+    """First-order rotor spool-up, thrust along the motor link's z axis and a reaction torque about it - the reference's
+    user add-on (examples/drone_pilot/drone_pilot.py:10-40), LOWERED to one op of the fused step: a user add-on may emit scene
+    ops from compile() instead of running Python every step.  Same config keys as the reference's class."""
+    def __init__(self, parent, config):
+        super().__init__(parent, config)
+        self.max_thrust = config.get('max_thrust', 20.0)
+        self.max_torque = config.get('max_torque', 0.1) * (1.0 if config.get('rotor_direction') == 'CCW' else -1.0)
+        self.spool_up_rate = 0.1
+        self.force, self.torque, self.rate = [0.0, 0.0, float(self.max_thrust)], [0.0, 0.0, float(self.max_torque)], self.spool_up_rate
+
+
+class FellOver(TiltTerminal):
+    """Terminal when the base is tilted by more than 10 degrees (drone_pilot.py:43-55 of the reference), as an op."""
+
+
+class PropellorTorch(Addon):
+    """The same add-on as plain batched PyTorch on the views the parent Model exposes - the general path for arbitrary user
+    code (a few small torch kernels per add-on per step).  Registered as `propellor_torch`; DG_DRONE_TORCH=1 makes the example
+    YAML use it (A/B against the lowered form: tests/test_host_layer.py)."""
     def __init__(self, parent, config):
         super().__init__(parent, config)
         self.frame_id = parent.get_frame_id(config.get('frame'))
@@ -34,12 +55,6 @@ class Propellor(Addon):
     def bind(self, env):
         self.rotor_speed = torch.zeros((env.num_envs, 1), device=env.world.state.device)
 
-    def reset(self, mask=None):
-        if mask is None:
-            self.rotor_speed.zero_()
-        else:
-            self.rotor_speed[mask.bool()] = 0.0
-
     def update(self, action):
         a = torch.as_tensor(action, device=self.rotor_speed.device, dtype=torch.float32).reshape(-1, 1)
         self.rotor_speed += (a - self.rotor_speed) * self.spool_up_rate
@@ -51,15 +66,18 @@ class Propellor(Addon):
         return self.rotor_speed
 
 
-class FellOver(Addon):
-    """Terminal when the base is tilted by more than 10 degrees."""
+class FellOverTorch(Addon):
+    """Terminal when the base is tilted by more than 10 degrees, in PyTorch."""
     def is_terminal(self):
         quat = self.parent.base_pose()[1]
         return 2.0 * torch.atan2(quat[:, :3].norm(dim=1), quat[:, 3].abs()) > math.radians(10)
 
 
-AddonFactory.register_addon('propellor', Propellor)
-AddonFactory.register_addon('fell_over', FellOver)
+_TORCH = os.environ.get('DG_DRONE_TORCH', '0') == '1'
+AddonFactory.register_addon('propellor', PropellorTorch if _TORCH else Propellor)
+AddonFactory.register_addon('fell_over', FellOverTorch if _TORCH else FellOver)
+AddonFactory.register_addon('propellor_torch', PropellorTorch)
+AddonFactory.register_addon('fell_over_torch', FellOverTorch)
 
 # thrust, roll, pitch, yaw torque -> four motor speeds (same mixer as the reference's example)
 MIXER = torch.linalg.inv(torch.tensor([[1., 1, 1, 1], [0, -1, 0, 1], [1, 0, -1, 0], [1, -1, 1, -1]]))

@@ -994,6 +994,14 @@ void dgo_apply_actions(DgoWorld* W, const double* act) {
       if (ia[1] == 0) { v_cpy(F, a); v_sub(rel, fa, pos); }
       else { double R[9]; q_to_mat(R, quat); m_vec(F, R, a); m_vec(rel, R, fa); }
       v_add(ST(W, S_EXTF) + 3 * f, ST(W, S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(ST(W, S_EXTT) + 3 * f, ST(W, S_EXTT) + 3 * f, t);
+    } else if (op[0] == OP_FILTERED_WRENCH) {           /* examples/drone_pilot/drone_pilot.py:31-37 (Propellor.update): first-order
+                                                           filter of the action, applyExternalForce / Torque in LINK_FRAME scaled by it */
+      double* st_ = ST(W, S_ADDON) + ia[2]; st_[0] = st_[0] + (a[0] - st_[0]) * fa[0];
+      int f = ia[0]; double pos[3], quat[4], v[3], o[3], R[9], F[3], T[3], rel[3], t[3];
+      frame_com_state(W, f, pos, quat, v, o); q_to_mat(R, quat);
+      double Fl[3] = {fa[1] * st_[0], fa[2] * st_[0], fa[3] * st_[0]}, Tl[3] = {fa[4] * st_[0], fa[5] * st_[0], fa[6] * st_[0]};
+      m_vec(F, R, Fl); m_vec(T, R, Tl); m_vec(rel, R, fa + 7);
+      v_add(ST(W, S_EXTF) + 3 * f, ST(W, S_EXTF) + 3 * f, F); v_cross(t, rel, F); v_add(t, t, T); v_add(ST(W, S_EXTT) + 3 * f, ST(W, S_EXTT) + 3 * f, t);
     } else if (op[0] == OP_ADMITTANCE) {                /* admittance_controller.py:36-55 */
       admittance_update(W, ia, fa, a);
     } else if (op[0] == OP_IK_CTRL) {                   /* ik_controller.py:51-80 */
@@ -1058,6 +1066,11 @@ void dgo_observe(DgoWorld* W, double* obs, double* rew, uint8_t* term) {
       rew[op[5]] = stuck ? -fa[0] : 0.0;
     } else if (op[0] == OP_TIME_PENALTY) {              /* time_penalty.py:11-12 */
       rew[op[5]] = fa[0];
+    } else if (op[0] == OP_FILTERED_WRENCH) {           /* Propellor.observe (drone_pilot.py:39-40) */
+      o[0] = ST(W, S_ADDON)[ia[2]];
+    } else if (op[0] == OP_TILT_TERMINAL) {             /* FellOver.is_terminal (drone_pilot.py:52-55) */
+      const double* q = ST(W, S_BQUAT) + 4 * ia[0];
+      term[op[6]] = 2.0 * atan2(sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]), fabs(q[3])) > fa[0];
     } else if (op[0] == OP_EPISODE_TIMER) {             /* diy_gym.py:180-183 */
       term[op[6]] = ST(W, S_STEP)[0] >= fa[0];
     }
@@ -1069,7 +1082,8 @@ void dgo_env_reset(DgoWorld* W) {
   uint32_t epoch = (uint32_t)ST(W, S_RESETS)[0];
   for (int k = 0; k < W->nop; k++) {
     const int32_t* op = W->op_i + DG_OP_I_W * k; const int32_t* ia = W->oparg_i + op[1]; const double* fa = W->oparg_f + op[2];
-    if (op[0] == OP_JOINT_RESET) {                      /* joint_controller.py:36-38, ik_controller.py:47-49 */
+    if (op[0] == OP_FILTERED_WRENCH) { if (ia[1]) ST(W, S_ADDON)[ia[2]] = 0; }
+    else if (op[0] == OP_JOINT_RESET) {                 /* joint_controller.py:36-38, ik_controller.py:47-49 */
       for (int i = 0; i < ia[0]; i++) { ST(W, S_Q)[ia[1 + i]] = fa[i]; ST(W, S_QD)[ia[1 + i]] = 0; }
     } else if (op[0] == OP_RESPAWN) {                   /* respawn.py:31-39 */
       int b = ia[0]; uint32_t ep = ia[1] ? 0u : epoch; const double* ip = PR(W, P_INITPOSE) + 7 * b;
@@ -1089,7 +1103,15 @@ void dgo_env_reset(DgoWorld* W) {
         double ms = exp(log(fa[0]) + u1 * (log(fa[1]) - log(fa[0]))), ds = exp(log(fa[2]) + u2 * (log(fa[3]) - log(fa[2])));
         PR(W, P_MASS)[f] = W->param_def[HI(W, P_MASS) + f] * ms;
         for (int i = 0; i < 3; i++) PR(W, P_INERTIA)[3 * f + i] = W->param_def[HI(W, P_INERTIA) + 3 * f + i] * ms;
-        if (d >= 0) PR(W, P_JDAMP)[d] = W->param_def[HI(W, P_JDAMP) + d] * ds;
+        /* fa[6]: nominal joint damping for joints whose URDF gives none (UR5: 0 - the scaling would be a no-op; extension key) */
+        if (d >= 0) { double nom = W->param_def[HI(W, P_JDAMP) + d]; PR(W, P_JDAMP)[d] = (nom > 0 ? nom : fa[6]) * ds; }
+      }
+      /* extension key friction_range (BASELINE.json config 5, SURVEY 8d: lateral friction U[0.5, 1.25] per environment): one draw per
+         body and reset, every collision shape of the body gets it */
+      if (fa[5] > 0) {
+        double u3 = urand(W->seed, (uint32_t)W->env_id, epoch, (uint32_t)(k * 8 + 63));
+        double fr = fa[4] + u3 * (fa[5] - fa[4]);
+        for (int s2 = 0; s2 < W->ns; s2++) if (W->shape_i[DG_SHAPE_I_W * s2] == b) PR(W, P_FRICTION)[s2] = fr;
       }
     }
   }

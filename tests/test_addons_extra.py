@@ -198,3 +198,44 @@ def test_auto_reset_returns_terminal_reward_cpu():
 @pytest.mark.gpu
 def test_auto_reset_returns_terminal_reward_gpu():
     _auto_reset(None)
+
+
+# ---------------------------------------------------------------- config 5: per-environment parameters -----------------------
+def _config5(factory):
+    """BASELINE.json config 5: link masses x log-U[0.25, 4], lateral friction U[0.5, 1.25], joint damping x log-U[0.2, 20]
+    of the nominal 0.1, base pose +-5 cm / +-0.1 rad - per environment, from the (seed, global environment id, reset count) stream,
+    identical on the oracle."""
+    n = 32
+    env = _env('ur_high_5_randomised', n, factory, seed=21)
+    w, sc, h = env.world, env.scene, env.scene.hdr
+    p = w.param.cpu().numpy()
+    nb, nl, ns, nd = sc['nb'], sc['nl'], sc['ns'], sc['nd']
+    fr = p[:, h['P_FRICTION']:h['P_FRICTION'] + ns]
+    assert fr.min() >= 0.5 and fr.max() <= 1.25 and fr[:, 0].std() > 0.1          # drawn per environment
+    shape_body = sc.sec['SHAPE_I'][:, 0]
+    for b in range(nb):
+        cols = np.nonzero(shape_body == b)[0]
+        assert np.allclose(fr[:, cols], fr[:, cols[:1]])                            # one draw per body
+    damp = p[:, h['P_JDAMP']:h['P_JDAMP'] + nd]
+    assert damp.min() >= 0.1 * 0.2 * 0.999 and damp.max() <= 0.1 * 20 * 1.001 and damp.std() > 0.1
+    mass = p[:, h['P_MASS']:h['P_MASS'] + nb + nl]
+    nominal = sc.sec['PARAM_DEFAULT'][h['P_MASS']:h['P_MASS'] + nb + nl]
+    ratio = mass[:, nominal > 0] / nominal[nominal > 0]
+    assert ratio.min() >= 0.25 * 0.999 and ratio.max() <= 4.0 * 1.001
+    pos = w.state[:, h['S_BPOS']:h['S_BPOS'] + 3 * nb].cpu().numpy().reshape(n, nb, 3)
+    init = sc.sec['PARAM_DEFAULT'][h['P_INITPOSE']:h['P_INITPOSE'] + 7 * nb].reshape(nb, 7)[:, :3]
+    assert np.abs(pos - init).max() <= 0.05 + 1e-6 and np.abs(pos - init)[..., :2].std() > 0.01
+    for i in (0, 7, 31):
+        o = OracleWorld(sc, seed=21, env_id=i)
+        o.env_reset()
+        assert np.allclose(p[i], o.param, rtol=1e-5, atol=1e-7)
+    env.close()
+
+
+def test_config5_randomised_parameters_cpu():
+    _config5(_factory())
+
+
+@pytest.mark.gpu
+def test_config5_randomised_parameters_gpu():
+    _config5(None)

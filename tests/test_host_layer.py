@@ -289,3 +289,36 @@ def test_nested_model_is_welded_to_the_parent_frame():
     assert gap.max() < 0.02                      # held by the 6 constraint rows (soft: erp 0.2 per sub-step, under gravity)
     assert pos[0, 0] - pos[1, 0] > 0.02          # environment 0 was driven along +x, its payload came along
     assert (payload.base_pose()[0][0, 0] - payload.base_pose()[0][1, 0]) > 0.02
+
+
+def test_drone_pilot_lowered_user_addons_equal_the_torch_forms():
+    """examples/drone_pilot: `Propellor` / `FellOver` as ops of the fused step (the default) against the same add-ons as eager
+    PyTorch (`propellor_torch`, `fell_over_torch` - the general path for arbitrary user code): same observations, rewards and
+    terminals over a rollout.  (CPU build of the kernel source; the GPU leg is tests/test_gpu_parity.py.)"""
+    import yaml
+    from bench import CONFIGS, register_example_addons
+    from tests.emul.world import factory
+    register_example_addons()
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+    node = yaml.load(open(os.path.join(root, CONFIGS['drone_pilot'][0])), Loader=yaml.FullLoader)
+    envs = []
+    for torch_form in (False, True):
+        nd = yaml.load(yaml.dump(node), Loader=yaml.FullLoader)
+        if torch_form:
+            for k, v in nd['drone'].items():
+                if isinstance(v, dict) and v.get('addon') in ('propellor', 'fell_over'):
+                    v['addon'] += '_torch'
+        envs.append(DIYGym(Configuration.from_dict('drone_pilot', nd), num_envs=3, world_factory=factory(4), seed=11))
+    a, b = envs
+    assert a.scene['nop'] > b.scene['nop']                      # four FILTERED_WRENCH ops and one TILT_TERMINAL more
+    g = torch.Generator().manual_seed(5)
+    for k in range(25):
+        act = {'drone': {'motor%d' % (i + 1): torch.rand((3, 1), generator=g) * (1.5 if k > 10 else 0.3) for i in range(4)}}
+        oa, ra, ta, _ = a.step(act)
+        ob, rb, tb, _ = b.step(act)
+        for m in ('motor1', 'motor4'):
+            assert torch.allclose(oa['drone'][m], ob['drone'][m], atol=1e-6)
+        assert torch.allclose(oa['drone']['pose']['position'], ob['drone']['pose']['position'], atol=1e-5)
+        assert torch.allclose(oa['drone']['pose']['rotation'], ob['drone']['pose']['rotation'], atol=1e-5)
+        assert torch.equal(ta, tb)
+    assert float(oa['drone']['motor1'].min()) > 0.3                  # the rotors spooled up

@@ -17,7 +17,8 @@ from tests.helpers import strict_single_step_parity
 EX = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'examples')
 # contact-free configs: the north_star bar applies to every environment.  Contact configs: the bar applies to the environments
 # without contacts; environments WITH contacts get the stated exception (150 clamped Gauss-Seidel sweeps in fp32 vs fp64).
-CONFIGS = [('ur_high_5', 'ur_high_5'), ('ur_high_5', 'ur_high_5_randomised'), ('ur_admittance', 'ur_admittance')]
+CONFIGS = [('ur_high_5', 'ur_high_5'), ('ur_high_5', 'ur_high_5_randomised'), ('ur_admittance', 'ur_admittance'), ('drone_pilot', 'drone_pilot')]
+# (drone_pilot - BASELINE.json's "PR1 ref" config: the quadrotor is in the air during these steps; its user add-ons are ops of the fused step)
 CONTACT_CONFIGS = [('from_the_readme', 'from_the_readme'), ('r2d2_maze', 'r2d2_maze'), ('basic_env', 'basic_env')]
 # Environments WITH contacts: a contact that exists in one arm and not (yet) in the other, or a friction row that sits on its
 # bound in one and not in the other, changes the step's outcome by a few percent of the velocity scale - in the g++ build of the
@@ -27,7 +28,9 @@ CONTACT_MEDIAN, CONTACT_P90, CONTACT_WORST = 2e-3, 3e-2, 0.5
 
 
 def _env(folder, name, n, factory=None):
+    from bench import register_example_addons
     from diy_gym_b200 import DIYGym
+    register_example_addons()
     return DIYGym(os.path.join(EX, folder, name + '.yaml'), num_envs=n, device=0, seed=4321, world_factory=factory)
 
 
