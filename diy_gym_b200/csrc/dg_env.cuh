@@ -44,6 +44,7 @@ struct Env {
   int* rs_count;                  // [2] their counts (atomically incremented)
   int e_local;                    // index of this environment in the launch
   unsigned* rs_used;              // counter of environment sub-steps solved in row space (any schedule), or null
+  int no_hot;                     // reset launch without the hot-start steps (they follow as stage launches)
 };
 
 #define SC (*C.sc)
@@ -236,6 +237,47 @@ DG_FN int invert_small(float* M, int n, float* inv) {
   return 0;
 }
 
+// inverse of a symmetric positive definite N x N matrix held in registers: A = L L^T, L^-1 by forward substitution,
+// A^-1 = L^-T L^-1.  Every index is a compile-time constant after unrolling.  (A pivot that is not positive - a body without
+// mass - is clamped: the result is then meaningless but finite, as with the pivoting elimination it replaces.)
+template <int N> DG_HD void inv_spd(const float (&A)[N][N], float (&Out)[N][N]) {
+  float L[N][N], Li[N][N], invd[N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < N; k++) if (k < j) d -= L[j][k] * L[j][k];
+    const float ljj = sqrtf(fmaxf(d, 1e-30f)), inv = 1.0f / ljj;
+    L[j][j] = ljj; invd[j] = inv;
+#pragma unroll
+    for (int i = 0; i < N; i++) if (i > j) {
+      float v = A[i][j];
+#pragma unroll
+      for (int k = 0; k < N; k++) if (k < j) v -= L[i][k] * L[j][k];
+      L[i][j] = v * inv;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    Li[j][j] = invd[j];
+#pragma unroll
+    for (int i = 0; i < N; i++) if (i > j) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < N; k++) if (k >= j && k < i) v -= L[i][k] * Li[k][j];
+      Li[i][j] = v * invd[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      float v = 0.f;
+#pragma unroll
+      for (int k = 0; k < N; k++) if (k >= i && k >= j) v += Li[k][i] * Li[k][j];
+      Out[i][j] = v;
+    }
+}
 // forward dynamics of dynamic body b (passes 2 and 3 of the ABA; pass 1 ran inside fk_vel_body<true>), then the
 // velocity half of the semi-implicit Euler step.  Every per-link record is pulled into registers with 128-bit loads,
 // worked on there, and written back once.
@@ -289,6 +331,7 @@ DG_FN void aba_body(const Env& C, int b, float h) {
   }
   // base acceleration
   float* X0 = ABA(s0); float* a0 = X0 + AB_ACC;
+#if defined(DG_OLD_INV)
   if (kind == 2) {
     float* M = WSG(C, sc.X_I0T) + bp[BP_I0OFF]; float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
     const float *A = X0 + AB_A, *B = X0 + AB_B, *Cm = X0 + AB_C;
@@ -296,6 +339,32 @@ DG_FN void aba_body(const Env& C, int b, float h) {
     invert_small(M, 6, Iv);
     for (int i = 0; i < 6; i++) { float sum = 0.f; for (int j = 0; j < 6; j++) sum -= Iv[6 * i + j] * X0[AB_PA + j]; a0[i] = sum; }
   } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
+#else
+  if (kind == 2) {
+    // inverse of the base's articulated inertia [A B; B^T C] (symmetric positive definite): Cholesky in registers, fully
+    // unrolled (round 1 ran a pivoting Gauss-Jordan on the cold workspace: ~300 dependent memory operations per body)
+    float* Iv = WSG(C, sc.W_I0) + bp[BP_I0OFF];
+    float Xr[40]; ldn<40>(X0, Xr);
+    const float *A = Xr + AB_A, *B = Xr + AB_B, *Cm = Xr + AB_C;
+    float M[6][6], Inv[6][6];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) { M[i][j] = A[3 * i + j]; M[i][3 + j] = B[3 * i + j]; M[3 + i][j] = B[3 * j + i]; M[3 + i][3 + j] = Cm[3 * i + j]; }
+    inv_spd<6>(M, Inv);
+    float iv[36];
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = 0; j < 6; j++) iv[6 * i + j] = Inv[i][j];
+    stn<36>(Iv, iv);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; j++) sum -= Inv[i][j] * Xr[AB_PA + j];
+      a0[i] = sum; }
+  } else for (int i = 0; i < 6; i++) a0[i] = 0.f;
+#endif
   // pass 3: accelerations, root to leaves
   float ap[8]; int prev = s0;
   ldn<8>(a0, ap);
@@ -1930,12 +1999,16 @@ DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_for
 // One DIYGym.step cut into kernel launches around the sweep kernel (dg_kernels.cu, "split schedule"):
 //   ST_ACT  add-on update + state row -> workspace      ST_PRE  physics_pre of one sub-step
 //   ST_POST physics_post of one sub-step                ST_END  link cache + state row back, sensors / rewards / terminals
+//   ST_LOAD: state row -> workspace without add-on update: the hot-start steps of DIYGym.reset (the reset hooks themselves run as
+//   one fused launch with Env::no_hot set).  (Calling phase_reset_ops + run_physics from here as well made nvcc 12.9 emit a step
+//   kernel whose IK returned its input - 10 MB more code per object, results wrong on the B200, right in the g++ build.)
 // The hot workspace travels between launches through the per-environment carry buffer (ST_SAVEC / ST_LOADC, done by the
 // kernel around this call); the cold workspace is per environment anyway.
 DG_FN void run_env_step_stages(const Env& C, int nt, int stages, int ln) {
   const DevScene& sc = SC;
   const float h = sc.dt / (float)sc.substeps;
   if (stages & ST_ACT) { DG_PHASE(phase_actions(C, ln, nt)); DG_PHASE(phase_load(C, ln, nt)); }
+  if (stages & ST_LOAD) { DG_PHASE(phase_load(C, ln, nt)); }                                        // a hot-start step has no add-on update
   if (stages & ST_POST) physics_post(C, nt, h, ln);
   if (stages & ST_PRE) physics_pre(C, nt, h, ln);
   if (stages & ST_END) { DG_PHASE(phase_final_kin(C, ln, nt)); DG_PHASE(phase_store(C, ln, nt, 1)); DG_PHASE(phase_observe(C, ln, nt)); }
@@ -1969,7 +2042,7 @@ DG_FN void run_env_reset(const Env& C, int nt, DG_LANE_ARGS) {
 #if defined(__CUDA_ARCH__)
   DG_PHASE(phase_reset_ops(C, ln, nt));
   run_physics(C, nt, 0, 0, ln);
-  for (int i = 0; i < SC.hot_start; i++) run_physics(C, nt, SC.substeps, 1, ln);
+  for (int i = 0; i < (C.no_hot ? 0 : SC.hot_start); i++) run_physics(C, nt, SC.substeps, 1, ln);
   DG_PHASE(phase_observe(C, ln, nt));
 #else
   DG_PHASE(phase_reset_ops(C, ln, nt));

@@ -27,7 +27,7 @@ struct LaunchArgs {
   unsigned* dropped;         // contacts lost to the max_contacts cap (one counter per world)
   // split schedule (mode 0 only): which stages of the step this launch runs (ST_*), the per-environment carry of the hot
   // workspace between launches, and the lists of environments left to the sweep kernel
-  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count; unsigned* rs_used;
+  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count; unsigned* rs_used; int no_hot;
 };
 
 template <int T>
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
   C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.seed = a.seed;
   C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg; C.dropped = a.dropped;
-  C.split = (a.mode == 0 && a.stages != ST_ALL) ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count; C.rs_used = a.rs_used;
+  C.split = a.stages != ST_ALL ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count; C.rs_used = a.rs_used; C.no_hot = a.no_hot;
   { // environments that share a warp once the row-space sweeps remap the threads (thread t -> lane t % T of environment t / T)
     const int G = T >= 32 ? 1 : 32 / T, g0 = ei / G * G;
     C.grp0 = g0 - ei; C.grp1 = (g0 + G < E ? g0 + G : E) - ei;
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
       for (int i = threadIdx.x; i < ncarry / 4; i += blockDim.x) dst[i] = src[i];
       __syncthreads();
     }
-    if (a.mode == 0) { if (a.stages == ST_ALL) run_env_step(C, T, ln); else run_env_step_stages(C, T, a.stages, ln); }
-    else if (a.mode == 1) run_env_reset(C, T, ln); else run_env_observe(C, T, ln);
+    if (a.stages != ST_ALL) run_env_step_stages(C, T, a.stages, ln);
+    else if (a.mode == 0) run_env_step(C, T, ln); else if (a.mode == 1) run_env_reset(C, T, ln); else run_env_observe(C, T, ln);
     if (T > 1 || (a.stages & ST_SAVEC)) __syncthreads();
     if (a.stages & ST_SAVEC) {
       float4* dst = reinterpret_cast<float4*>(a.carry + (size_t)base * sc.w_total); const float4* src = reinterpret_cast<const float4*>(smem);
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
   float* key = vs + VS_W * sc.nv;
   unsigned* cand = reinterpret_cast<unsigned*>(key + ((sc.nv + 3) & ~3));
   const int ncw = (sc.nv + 31) / 32;
-  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr; C.rs_used = nullptr;
+  Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr; C.rs_used = nullptr; C.no_hot = 0;
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
   const float th = tanf(fov * kPi / 360.0f), aspect = (float)width / (float)height;
@@ -747,7 +747,7 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   DeviceGuard guard(w->device);
   if (!guard.ok) { w->err = "cudaSetDevice failed"; cudaGetLastError(); return DG_E_CUDA; }
   LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg, w->dropped,
-               ST_ALL, nullptr, nullptr, nullptr, nullptr, mode == 0 ? w->rs_used : nullptr};
+               ST_ALL, nullptr, nullptr, nullptr, nullptr, mode == 0 ? w->rs_used : nullptr, 0};
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 0 && w->split_ok && w->split_mode < 0 && w->dev.ncons == 0) {
     // adaptive schedule: share of environment sub-steps that needed the contact solver over the last period
@@ -766,7 +766,8 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
       w->stat_pending = true; w->steps_in_period = 0;
     }
   }
-  if (mode != 0 || !w->split) { CK(w, launch_any(w, a, s)); return DG_OK; }
+  const int nhot = mode == 1 ? w->dev.hot_start : 1;
+  if (mode == 2 || !w->split || nhot < 1) { CK(w, launch_any(w, a, s)); return DG_OK; }
   // Split schedule of one step with n sub-steps (2 for the reference's settings, diy_gym.py:76-79):
   //   stage launch [add-on update, load | sub-step 0 up to the row-space system] -> sweeps ->
   //   stage launch [impulses + integration of sub-step k-1 | sub-step k up to its system] -> sweeps -> ... ->
@@ -776,10 +777,17 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   // queue behind the others).
   const int nsub = std::max(w->dev.substeps, 1);
   a.carry = w->carry; a.rs_list0 = w->rs_lists; a.rs_list1 = w->rs_lists + w->n_envs;
+  if (mode == 1) { a.no_hot = 1; CK(w, launch_any(w, a, s)); a.no_hot = 0; }   // reset hooks + link cache of the masked environments, one fused launch
   CK(w, cudaMemsetAsync(w->rs_counts, 0, 2 * (size_t)nsub * sizeof(int), s));
+  // (DIYGym.reset of the masked environments: reset hooks + link cache as one fused launch, then every hot-start step takes the
+  // same cut as a step, without add-on update; blocks without a masked environment return at once, the sweep kernel only sees
+  // the listed ones)
+  for (int hot = 0; hot < nhot; hot++)
   for (int sub = 0; sub <= nsub; sub++) {
-    a.stages = (sub == 0 ? ST_ACT : (ST_LOADC | ST_POST)) | (sub < nsub ? (ST_PRE | ST_SAVEC) : ST_END);
+    const int first = mode == 0 ? ST_ACT : ST_LOAD;
+    a.stages = (sub == 0 ? first : (ST_LOADC | ST_POST)) | (sub < nsub ? (ST_PRE | ST_SAVEC) : ST_END);
     a.rs_count = w->rs_counts + 2 * std::min(sub, nsub - 1);
+    if (sub == 0 && hot > 0) CK(w, cudaMemsetAsync(w->rs_counts, 0, 2 * (size_t)nsub * sizeof(int), s));
     CK(w, launch_any(w, a, s));
     if (sub == nsub) break;
     CK(w, cudaEventRecord(w->ev_fork, s));

@@ -21,7 +21,7 @@ enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_
 // workspace header ints
 enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_RS_DEFER, WH_COUNT = 12 };
 // stages of one DIYGym.step when the contact sweeps run in their own kernel (dg_kernels.cu): see dg_env.cuh "the phase schedule"
-enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC = 32, ST_ALL = 15 };
+enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC = 32, ST_LOAD = 128, ST_ALL = 15 };
 // row capacity of the sweep kernel: a warp per environment, K = 1 (<= 32 rows) or 2 (<= 64 rows) rows per lane, A in registers
 enum { RS_WARP_R1 = 32, RS_WARP_R2 = 64 };
 // row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j

@@ -296,7 +296,7 @@ def test_split_schedule_matches_fused_launch(monkeypatch, name, scale):
     step as ONE fused launch with the in-kernel team sweeps: same row order and arithmetic, so the states agree to rounding of
     the few fused multiply-adds the two compilations contract differently."""
     n, steps = 96, 12
-    states = {}
+    states, resets = {}, {}
     for split in ('0', '1'):
         monkeypatch.setenv('DG_SPLIT', split)
         env = _env(name, n, seed=5)
@@ -306,8 +306,17 @@ def test_split_schedule_matches_fused_launch(monkeypatch, name, scale):
             env.world.action.copy_((torch.rand(env.world.action.shape, device='cuda', generator=g) * 2 - 1) * scale)
             env.world.step()
         torch.cuda.synchronize()
-        states[split] = (env.world.state.clone(), env.world.obs.clone(), env.world.launches)
+        after_steps = env.world.state.clone()
+        # masked reset (every third environment) through the same schedule: untouched rows stay bit-identical
+        mask = (torch.arange(n, device='cuda') % 3 == 0)
+        env.world.reset(mask)
+        torch.cuda.synchronize()
+        assert torch.equal(env.world.state[~mask], after_steps[~mask])
+        assert float(env.world.state[mask][:, env.scene.hdr['S_STEP']].max()) == 0.0
+        resets[split] = env.world.state[mask].clone()
+        states[split] = (after_steps, env.world.obs.clone(), env.world.launches)
         env.close()
+    assert torch.isclose(resets['0'], resets['1'], rtol=1e-4, atol=1e-5).float().mean().item() > 0.99
     a, b = states['0'], states['1']
     assert torch.isfinite(b[0]).all()
     assert b[2] > a[2]                                       # several launches per step
