@@ -1088,7 +1088,6 @@ DG_FN void phase_pgs_unit(const Env& C, int ln, int nt, int it0, int it1) {
   for (int di = ln; di < SC.ndyn; di += nt) pgs_unit_any(C, gc(SC.dyn_body)[di], di, it0, it1);
 }
 DG_FN void phase_pgs_contact(const Env& C, int ln, int nt) { if (ln == 0) pgs_contact_sweep(C); }
-
 // ------------------------------------------------------------------ row-space team solver ----------------------
 // Environments with contacts (or welded models) are solved by the WHOLE team in row space: y_p = J_p dv is carried for
 // every unit, constraint and contact row, A[p][s] = J_s M^-1 J_p^T is built once per sub-step by all lanes, and one
@@ -1187,7 +1186,8 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
       Jd[go + col] = sg;
       for (int i = 0; i < gs; i++) Md[go + i] = sg * Mc[i];
       float* rc = REC + RR_W * r;
-      st4(rc, u[UR_RHS], u[UR_DINV], u[UR_LO], u[UR_HI]); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float((di << 16) | j));
+      // (RR_APPLIED carries, until the sweeps overwrite it, the support of the row's J: [lo, hi) in floats, lo | hi << 16)
+      st4(rc, u[UR_RHS], u[UR_DINV], u[UR_LO], u[UR_HI]); st4(rc + 4, 0.f, int_as_float(-1), int_as_float(((go + col) & ~3) | ((((go + col) & ~3) + 4) << 16)), int_as_float((di << 16) | j));
     }
   }
   // fixed constraints between models (model.py:69-77): three point rows along the world axes, three angular rows
@@ -1223,7 +1223,7 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     }
     const float dinv = den > 1e-30f ? 1.0f / den : 0.f, lim = cf[14] * sc.dt, hsub = sc.dt / (float)sc.substeps;
     float* rc = REC + RR_W * r2;
-    st4(rc, (-rel - err * sc.erp / hsub) * dinv, dinv, -lim, lim); st4(rc + 4, 0.f, int_as_float(-1), 0.f, int_as_float(RS_CONTACT | 0xffff));
+    st4(rc, (-rel - err * sc.erp / hsub) * dinv, dinv, -lim, lim); st4(rc + 4, 0.f, int_as_float(-1), int_as_float(0 | (GV << 16)), int_as_float(RS_CONTACT | 0xffff));
   }
   const int nc = ncr / 3;
   for (int rr = 0; rr < ncr; rr++) {
@@ -1233,11 +1233,12 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     const int dia = float_as_int(row[CR_DA]), dib = float_as_int(row[CR_DB]);
     float* Jd = RSV + (size_t)r2 * 2 * GV; float* Md = Jd + GV;
     for (int i = 0; i < 2 * GV; i += 4) st4(Jd + i, 0.f, 0.f, 0.f, 0.f);
-    int off = 0;
-    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[i]; Md[go + i] += M[i]; } off = g; }
-    if (dib >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } }
+    int off = 0, slo = GV, shi = 0;
+    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[i]; Md[go + i] += M[i]; } off = g; slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
+    if (dib >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
+    if (shi <= slo) { slo = 0; shi = 0; }
     float* rc = REC + RR_W * r2;
-    st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], 0.f, int_as_float(RS_CONTACT | rr));
+    st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], int_as_float(slo | (shi << 16)), int_as_float(RS_CONTACT | rr));
   }
 }
 // A[p * cap + s] = J_s M^-1 J_p^T for real positions p, s < Rp; zero rows / columns for the padding positions and for the
@@ -1246,14 +1247,20 @@ DG_FN void phase_rs_build(const Env& C, int ln, int nt) {
   const DevScene& sc = SC;
   const RsLayout L = rs_layout_of(C); const int GV = sc.GV, cap = sc.rs_cap;
   int ncol = L.K * nt; if (ncol > cap) ncol = cap; if (ncol < L.Rp) ncol = L.Rp;
-  const float* RSV = WSG(C, sc.X_RSV); float* A = WSG(C, sc.X_RSA);
-  for (int p = 0; p < L.Rp; p++) {
-    const float* Md = RSV + (size_t)p * 2 * GV + GV; const bool rp = rs_real(L, p);
-    for (int s2 = ln; s2 < ncol; s2 += nt) {
+  const float* RSV = WSG(C, sc.X_RSV); const float* REC = WSG(C, sc.X_RSREC); float* A = WSG(C, sc.X_RSA);
+  // column s of A needs J_s only where it is non-zero: one generalized coordinate for a motor / limit row, the coordinates of the
+  // one or two bodies it touches for a contact row (phase_rs_setup left that range in the row record).  The terms left out
+  // are exact zeros, so the sums are the ones the full dot products give.
+  for (int s2 = ln; s2 < ncol; s2 += nt) {
+    const bool rs2 = s2 < L.Rp && rs_real(L, s2);
+    int c0 = 0, c1 = 0;
+    if (rs2) { const int sup = float_as_int(REC[RR_W * s2 + RR_APPLIED]); c0 = sup & 0xffff; c1 = (sup >> 16) & 0xffff; if (c1 > GV) c1 = GV; }
+    const float* Jd = RSV + (size_t)s2 * 2 * GV;
+    for (int p = 0; p < L.Rp; p++) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      if (rp && s2 < L.Rp && rs_real(L, s2)) {
-        const float* Jd = RSV + (size_t)s2 * 2 * GV;
-        for (int c = 0; c < GV; c += 4) { const F4 jv = ld4(Jd + c), mv = ld4(Md + c); a0 = fmaf(jv.x, mv.x, a0); a1 = fmaf(jv.y, mv.y, a1); a2 = fmaf(jv.z, mv.z, a2); a3 = fmaf(jv.w, mv.w, a3); }
+      if (rs2 && rs_real(L, p)) {
+        const float* Md = RSV + (size_t)p * 2 * GV + GV;
+        for (int c = c0; c < c1; c += 4) { const F4 jv = ld4(Jd + c), mv = ld4(Md + c); a0 = fmaf(jv.x, mv.x, a0); a1 = fmaf(jv.y, mv.y, a1); a2 = fmaf(jv.z, mv.z, a2); a3 = fmaf(jv.w, mv.w, a3); }
       }
       A[p * cap + s2] = (a0 + a1) + (a2 + a3);
     }
