@@ -32,7 +32,7 @@ MAGIC = 0x44594742  # 'DYGB'
 
 HDR_I_FIELDS = [
     'nb', 'nl', 'nd', 'ns', 'nv', 'npair', 'ncam', 'nop', 'n_act', 'n_obs', 'n_rew', 'n_term', 'substeps', 'iterations',
-    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn', 'ncons',
+    'S', 'P', 'max_contacts', 'nframes', 'hot_start', 'ik_iters', 'ndyn', 'ncons', 'semantics',
     # state offsets
     'S_BPOS', 'S_BQUAT', 'S_BVEL', 'S_BOMEGA', 'S_Q', 'S_QD', 'S_MKP', 'S_MKD', 'S_MTPOS', 'S_MTVEL', 'S_MMAXF',
     'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_JREACT', 'S_STEP', 'S_RESETS',
@@ -57,6 +57,16 @@ JOINT_TYPES = {'fixed': 0, 'revolute': 1, 'continuous': 1, 'prismatic': 2}
 OP = dict(JOINT_CTRL=1, EXT_FORCE=2, IK_CTRL=3, JOINT_SENSOR=4, OBJECT_SENSOR=5, REACH_TARGET=6, ELECTRICITY=7,
           STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13, ADMITTANCE=14, FT_SENSOR=15,
           FILTERED_WRENCH=16, TILT_TERMINAL=17)
+
+# Engine semantics that SURVEY Appendix A could only RECALL (no pybullet here to check): each is a named switch of the scene
+# header, honoured by the kernels and by the oracle alike, so that the day a pybullet golden vector disagrees the fix is a flag.
+# The defaults (all off) are what both arms implemented in round 1.
+SEMANTICS = dict(
+    wrench_first_substep=1,   # external forces / torques and TORQUE_CONTROL torques act during the first internal sub-step only
+                              # (App. A.2 "believed to be cleared after the first substep"); default: during the whole outer step
+    motor_clamp_substep=2,    # motor impulse clamp = max force x sub-step dt; default: x fixedTimeStep, the outer dt (App. A.3)
+    damping_linear=4,         # multibody velocity damping -m v k only; default: -m v (k + k |v|) (App. A.2)
+)
 
 DEFAULT_LATERAL_FRICTION = 0.5
 DEFAULT_DAMPING = 0.04  # multibody linear/angular velocity damping (App. A.2)
@@ -146,7 +156,8 @@ class BodyInfo:
 
 
 class SceneBuilder:
-    def __init__(self, timestep=1 / 240., substeps=2, iterations=150, gravity=(0, 0, -9.81), hot_start=1, max_contacts=16):
+    def __init__(self, timestep=1 / 240., substeps=2, iterations=150, gravity=(0, 0, -9.81), hot_start=1, max_contacts=16, semantics=()):
+        self.semantics = sum(SEMANTICS[k] for k in semantics)
         self.timestep, self.substeps, self.iterations = float(timestep), int(substeps), int(iterations)
         self.gravity, self.hot_start, self.max_contacts = tuple(float(g) for g in gravity), int(hot_start), int(max_contacts)
         self.bodies = []
@@ -407,11 +418,11 @@ class SceneBuilder:
             raise ValueError('max_contacts is limited to 21 (the solver tracks at most 63 contact rows per environment)')
         hdr = dict(nb=nb, nl=nl, nd=nd, ns=ns, nv=nv, npair=len(pairs), ncam=ncam, nop=nop, n_act=n_act, n_obs=n_obs,
                    n_rew=n_rew, n_term=n_term, substeps=self.substeps, iterations=self.iterations, S=S, P=P,
-                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=int(__import__('os').environ.get('DG_DBG_IKIT', 20)), ndyn=ndyn, ncons=ncons)
+                   max_contacts=self.max_contacts, nframes=nframes, hot_start=self.hot_start, ik_iters=20, ndyn=ndyn, ncons=ncons, semantics=self.semantics)
         hdr.update(lay)
         hdr_i = np.array([hdr[k] for k in HDR_I_FIELDS], np.int32)
         hf = dict(dt=self.timestep, gx=self.gravity[0], gy=self.gravity[1], gz=self.gravity[2], erp=0.2, contact_erp=0.2,
-                  linear_slop=0.0, contact_margin=0.0, ik_damping=0.5, ik_threshold=float(__import__('os').environ.get('DG_DBG_IKTHR', 1e-4)), max_joint_vel=100.0,
+                  linear_slop=0.0, contact_margin=0.0, ik_damping=0.5, ik_threshold=1e-4, max_joint_vel=100.0,
                   default_motor_impulse=1.0, limit_max_impulse=100.0, ik_null_lambda_sq=0.36)
         hdr_f = np.array([hf[k] for k in HDR_F_FIELDS])
 
@@ -477,6 +488,8 @@ def emit_c_header():
         out.append('#define DG_%s %d' % (k, v))
     for k, v in OP.items():
         out.append('#define OP_%s %d' % (k, v))
+    for k, v in SEMANTICS.items():
+        out.append('#define SEM_%s %d' % (k.upper(), v))
     for k, v in SHAPE_TYPES.items():
         out.append('#define SHAPE_%s %d' % (k.upper(), v))
     out.append('#endif')

@@ -193,7 +193,10 @@ DG_FN void fk_vel_body(const Env& C, int b) {
       for (int i = 0; i < 6; i++) z[AB_WV + i] = V[i];
       stn<40>(X, z);
     } else {
-      const float* ef = ST(S_EXTF) + 3 * f; const float* et = ST(S_EXTT) + 3 * f;
+      // SEM_WRENCH_FIRST_SUBSTEP: applied wrenches act during the first internal sub-step only
+      const float wsc = ((sc.sem & SEM_WRENCH_FIRST_SUBSTEP) && WSI(C)[sc.W_HDR + WH_SUB] > 0) ? 0.f : 1.f;
+      const float efv[3] = {wsc * ST(S_EXTF)[3 * f], wsc * ST(S_EXTF)[3 * f + 1], wsc * ST(S_EXTF)[3 * f + 2]}, etv[3] = {wsc * ST(S_EXTT)[3 * f], wsc * ST(S_EXTT)[3 * f + 1], wsc * ST(S_EXTT)[3 * f + 2]};
+      const float *ef = efv, *et = etv;
       const float m = mass[f]; const float* I = inertia + 3 * f; const float *w = V, *v = V + 3;
       float Iw[3] = {I[0] * w[0], I[1] * w[1], I[2] * w[2]}, t[3], fw[3], pa[3], pl[3];
       v_cross(pa, w, Iw);
@@ -202,8 +205,9 @@ DG_FN void fk_vel_body(const Env& C, int b) {
       mT_vec(t, K, fw); v_sub(pl, pl, t);
       mT_vec(t, K, et); v_sub(pa, pa, t);
       const float wn = v_len(w), vn = v_len(v);
-      v_madd(pa, Iw, ka + ka * wn);
-      float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, kl + kl * vn);
+      const bool dlin = (sc.sem & SEM_DAMPING_LINEAR) != 0;   // damping -m v k instead of -m v (k + k |v|)
+      v_madd(pa, Iw, dlin ? ka : ka + ka * wn);
+      float mv[3]; v_scale(mv, v, m); v_madd(pl, mv, dlin ? kl : kl + kl * vn);
       float z[40]; for (int i = 0; i < 40; i++) z[i] = 0.f;
       for (int i = 0; i < 3; i++) { z[AB_PA + i] = pa[i]; z[AB_PA + 3 + i] = pl[i]; z[AB_WV + i] = w[i]; z[AB_WV + 3 + i] = v[i]; }
       z[AB_A] = I[0]; z[AB_A + 4] = I[1]; z[AB_A + 8] = I[2]; z[AB_C] = m; z[AB_C + 4] = m; z[AB_C + 8] = m;
@@ -820,7 +824,8 @@ DG_FN void phase_unit_rows(const Env& C, int ln, int nt, float h) {
       float den = Minv[col * gs + col], dinv = den > 1e-30f ? 1.0f / den : 0.f, qd = DOF(D_QD, d);
       float desired = ST(S_MKP)[d] * (ST(S_MTPOS)[d] - DOF(D_Q, d)) / h + qd + ST(S_MKD)[d] * (ST(S_MTVEL)[d] - qd);
       float* r = rows + UR_W * n++;
-      r[UR_RHS] = (desired - qd) * dinv; r[UR_DINV] = dinv; r[UR_LO] = -maxf * sc.dt; r[UR_HI] = maxf * sc.dt; r[UR_APPLIED] = 0.f;
+      r[UR_RHS] = (desired - qd) * dinv; r[UR_DINV] = dinv; const float cdt = (sc.sem & SEM_MOTOR_CLAMP_SUBSTEP) ? h : sc.dt;   // impulse clamp: max force x outer dt (default) or x sub-step dt
+      r[UR_LO] = -maxf * cdt; r[UR_HI] = maxf * cdt; r[UR_APPLIED] = 0.f;
       r[UR_COL] = int_as_float(col); r[UR_MOTOR] = int_as_float(d);
     }
     WSI(C)[sc.W_UCNT + di] = n;
@@ -1439,9 +1444,13 @@ DG_FN void phase_integrate(const Env& C, int ln, int nt, float h) {
       int d = bi[3] + i; float qd = DOF(D_QD, d) + dv[jo + i];
       qd = clampf(qd, -sc.max_joint_vel, sc.max_joint_vel);
       DOF(D_QD, d) = qd; DOF(D_Q, d) += h * qd;
+      // SEM_WRENCH_FIRST_SUBSTEP: the applied joint torque leaves the generalized force after the first sub-step (damping stays)
+      if ((sc.sem & SEM_WRENCH_FIRST_SUBSTEP) && WSI(C)[sc.W_HDR + WH_SUB] == 0) DOF(D_TAU, d) -= ST(S_JTORQUE)[d];
     }
   }
 }
+// (after phase_integrate, its own phase: every lane above read the counter)
+DG_FN void phase_next_substep(const Env& C, int ln, int nt) { (void)nt; if (ln == 0) WSI(C)[SC.W_HDR + WH_SUB] += 1; }
 DG_FN void phase_final_kin(const Env& C, int ln, int nt) {
   for (int di = ln; di < SC.ndyn; di += nt) fk_vel_body<false>(C, gc(SC.dyn_body)[di]);
 }
@@ -1986,6 +1995,7 @@ DG_NOINLINE DG_FN void physics_pre(const Env& C, int nt, float h, DG_LANE_ARGS) 
 DG_NOINLINE DG_FN void physics_post(const Env& C, int nt, float h, DG_LANE_ARGS) {
   if (SC.solver == 1 && nt > 1 && C.split) DG_PHASE(if (HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) != 0) phase_rs_finish(C, ln, nt));
   DG_PHASE(phase_integrate(C, ln, nt, h));
+  if (SC.sem & SEM_WRENCH_FIRST_SUBSTEP) DG_PHASE(phase_next_substep(C, ln, nt));
 }
 // p.stepSimulation() (diy_gym.py:146,207); nsub = 0 only refreshes the link cache
 DG_NOINLINE DG_FN void run_physics(const Env& C, int nt, int nsub, int clear_forces, DG_LANE_ARGS) {

@@ -19,7 +19,7 @@ enum { D_Q = 0, D_QD, D_APPLIED, D_TAU, D_COUNT };
 // body plan columns
 enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_DEPTH, BP_NRS, BP_AOFF, BP_GS, BP_W };
 // workspace header ints
-enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_RS_DEFER, WH_COUNT = 12 };
+enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_RS_DEFER, WH_SUB, WH_COUNT = 12 };
 // stages of one DIYGym.step when the contact sweeps run in their own kernel (dg_kernels.cu): see dg_env.cuh "the phase schedule"
 enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC = 32, ST_LOAD = 128, ST_ALL = 15 };
 // row capacity of the sweep kernel: a warp per environment, K = 1 (<= 32 rows) or 2 (<= 64 rows) rows per lane, A in registers
@@ -76,6 +76,7 @@ struct DevScene {
   int rs_min;   // contact rows an uncoupled environment needs before the team solves it in row space (fewer: per-body sweeps)
   int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
+  int sem;      // SEM_* switches of the engine semantics that could only be recalled (compiler/scene.py SEMANTICS)
   int precise;  // 1: libm sincosf in FK / IK instead of the SFU approximation (scenes with fixed constraints; DG_PRECISE=0/1 overrides)
 };
 
@@ -269,7 +270,7 @@ struct HostScene {
     int n_ik = 0;
     for (int k = 0; k < d.nop; k++) n_ik += op_i[DG_OP_I_W * k] == OP_IK_CTRL;
     d.need_react = hi[HI_S_STEP] > hi[HI_S_JREACT];
-    d.precise = d.ncons > 0;   // the state row holds reaction wrenches only when a sensor asked for them
+    d.precise = d.ncons > 0; d.sem = hi[HI_semantics];   // the state row holds reaction wrenches only when a sensor asked for them
 
     auto put_vi = [&](const std::vector<int>& v) { size_t o = ints.size(); ints.insert(ints.end(), v.begin(), v.end()); ints.push_back(0); return o; };
     auto put_vf = [&](const std::vector<float>& v) { size_t o = floats.size(); floats.insert(floats.end(), v.begin(), v.end()); floats.push_back(0.f); return o; };

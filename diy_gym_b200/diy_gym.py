@@ -7,7 +7,7 @@
 Same constructor argument, YAML schema, nested-dict structure (receptors and add-ons in sorted-name order), same
 `observation_space` / `action_space` trees (per-environment shapes) and the same options (`sum_rewards`,
 `terminal_if_any`, `terminal_if_all`, `flatten_observations`, `flatten_actions`, `max_episode_steps`, `hot_start`,
-`timestep`, `update_freq`, `solver_iterations`, `gravity`).  New keyword arguments, never required in the YAML:
+`timestep`, `update_freq`, `solver_iterations`, `gravity`; extension keys `max_contacts`, `engine_semantics`).  New keyword arguments, never required in the YAML:
 `num_envs`, `device`, `seed`, `auto_reset`, `team`, `env_id_offset` (global id of environment 0, for multi-GPU).
 
 Construction compiles the whole scene (models + add-on program) into flat buffers (`compiler/scene.py`) and
@@ -48,7 +48,8 @@ class DIYGym(Receptor):
         iterations = config.get('solver_iterations', 150)
         gravity = config.get('gravity', [0.0, 0.0, -9.81])
         self.builder = SceneBuilder(timestep=timestep, substeps=max(sub_steps, 1), iterations=iterations, gravity=gravity,
-                                    hot_start=self.hot_start, max_contacts=int(config.get('max_contacts', 0)))
+                                    hot_start=self.hot_start, max_contacts=int(config.get('max_contacts', 0)),
+                                    semantics=tuple(config.get('engine_semantics', ())))   # compiler/scene.py SEMANTICS (extension key)
         self.world = None
 
         self.models = OrderedDict(sorted({child.name: Model(child, env=self) for child in config.find_all('model')}.items(),

@@ -118,7 +118,7 @@ typedef struct {
 } Row;
 
 typedef struct DgoWorld {
-  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react, ncons;
+  int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react, ncons, sem;
   const int32_t* cons_i; const double* cons_f;
   int32_t* ibuf; double* fbuf;
   const int32_t *hi, *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
@@ -160,7 +160,7 @@ DgoWorld* dgo_create(const int32_t* ibuf, int ni, const double* fbuf, int nf) {
   W->nb = HI(W, nb); W->nl = HI(W, nl); W->nd = HI(W, nd); W->ns = HI(W, ns); W->nv = HI(W, nv); W->npair = HI(W, npair);
   W->ncam = HI(W, ncam); W->nop = HI(W, nop); W->nframes = HI(W, nframes); W->S = HI(W, S); W->P = HI(W, P);
   W->substeps = HI(W, substeps); W->iters = HI(W, iterations); W->maxc = HI(W, max_contacts); W->hot_start = HI(W, hot_start);
-  W->ik_iters = HI(W, ik_iters);
+  W->ik_iters = HI(W, ik_iters); W->sem = HI(W, semantics);   /* SEM_* switches (compiler/scene.py SEMANTICS) */
   W->ncons = HI(W, ncons); W->cons_i = sec_i(ib, SEC_CONS_I); W->cons_f = sec_f(ib, fb, SEC_CONS_F);
   W->need_react = HI(W, S_STEP) > HI(W, S_JREACT);   /* the state row holds reaction wrenches only when a sensor asked for them */
   int nf_ = W->nframes, nl = W->nl > 0 ? W->nl : 1;
@@ -293,8 +293,9 @@ static void aba_body(DgoWorld* W, int b, const double* tau_damp) {
     mT_vec(t, W->Rw + 9 * f, fw); v_sub(pA + 3, pA + 3, t);
     mT_vec(tw, W->Rw + 9 * f, extt + 3 * f); v_sub(pA, pA, tw);
     double wn = v_len(w), vn = v_len(v);                  /* velocity damping, App. A.2 */
-    v_madd(pA, Iw, ka + ka * wn);
-    double mv[3]; v_scale(mv, v, m); v_madd(pA + 3, mv, kl + kl * vn);
+    int dlin = (W->sem & SEM_DAMPING_LINEAR) != 0;   /* damping -m v k instead of -m v (k + k |v|) */
+    v_madd(pA, Iw, dlin ? ka : ka + ka * wn);
+    double mv[3]; v_scale(mv, v, m); v_madd(pA + 3, mv, dlin ? kl : kl + kl * vn);
     double* A = W->IAa + 9 * f; memset(A, 0, 72); A[0] = I[0]; A[4] = I[1]; A[8] = I[2];
     memset(W->IAb + 9 * f, 0, 72);
     double* C = W->IAc + 9 * f; memset(C, 0, 72); C[0] = C[4] = C[8] = m;
@@ -675,7 +676,7 @@ static void build_rows(DgoWorld* W, double h) {
       double rel = finish_row(W, r);
       double kp = ST(W, S_MKP)[d], kd = ST(W, S_MKD)[d], tp = ST(W, S_MTPOS)[d], tv = ST(W, S_MTVEL)[d];
       double desired = kp * (tp - q[d]) / h + qd[d] + kd * (tv - qd[d]);
-      r->rhs = (desired - rel) * r->diag_inv; r->lo = -maxf * dt; r->hi = maxf * dt;
+      r->rhs = (desired - rel) * r->diag_inv; { double cdt = (W->sem & SEM_MOTOR_CLAMP_SUBSTEP) ? h : dt; r->lo = -maxf * cdt; r->hi = maxf * cdt; }
     }
   }
   /* fixed constraints between models (diy_gym/model.py:69-77, p.createConstraint(..., JOINT_FIXED, ...)): the joint frame on
@@ -797,6 +798,11 @@ void dgo_step_physics(DgoWorld* W) {
         if (qd[d] > maxv) qd[d] = maxv; else if (qd[d] < -maxv) qd[d] = -maxv;
         q[d] += h * qd[d];
       }
+    }
+    if ((W->sem & SEM_WRENCH_FIRST_SUBSTEP) && sub == 0) {   /* applied wrenches / joint torques act during the first internal sub-step only */
+      memset(ST(W, S_EXTF), 0, sizeof(double) * 3 * (size_t)W->nframes);
+      memset(ST(W, S_EXTT), 0, sizeof(double) * 3 * (size_t)W->nframes);
+      memset(ST(W, S_JTORQUE), 0, sizeof(double) * (size_t)W->nd);
     }
   }
   write_link_cache(W);
