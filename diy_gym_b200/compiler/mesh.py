@@ -89,7 +89,7 @@ def fit_proxy(verts):
         corners = np.array([[x, y, z] for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])])
         d = np.abs(uniq[:, None, :] - corners[None, :, :]).sum(-1).min(axis=1)
         if np.all(d < 1e-6 * max(1.0, ext.max())):
-            return dict(type='box', dims=(0.5 * ext).tolist(), center=center.tolist(), axis=2, half=(0.5 * ext).tolist())
+            return dict(type='box', dims=(0.5 * ext).tolist(), center=center.tolist(), axis=2, half=(0.5 * ext).tolist(), exact=True)
     order = np.argsort(ext)
     a, b, c = ext[order]
     if c > 0 and b > 0 and (b - a) <= 0.25 * b and c >= 1.05 * b:
@@ -98,3 +98,50 @@ def fit_proxy(verts):
         return dict(type='capsule', dims=[float(radius), float(half), 0.0], center=center.tolist(), axis=int(order[2]),
                     half=(0.5 * ext).tolist())
     return dict(type='box', dims=(0.5 * ext).tolist(), center=center.tolist(), axis=2, half=(0.5 * ext).tolist())
+
+
+def reduced_hull(verts, max_verts=32, max_planes=64):
+    """Convex hull of a vertex cloud reduced to at most `max_verts` vertices (SURVEY hard part 6): the support points of the cloud
+    along a fixed fan of directions (the six axes + a Fibonacci sphere), thinned by farthest-point selection - an INNER
+    approximation of the true hull (pybullet collides the full hull, 72-1500 vertices for the vendored meshes).
+    Returns (V [n, 3], P [m, 4]) with the half-spaces  P[:, :3] . x <= P[:, 3]  of the reduced hull, or None if the cloud is flat.
+    Needs scipy (build container / asset compilation only: the result is stored in the compiled model descriptor)."""
+    from scipy.spatial import ConvexHull, QhullError
+    verts = np.asarray(verts, np.float64)
+    if len(verts) < 4:
+        return None
+    try:
+        full = ConvexHull(verts)
+    except QhullError:
+        return None
+    hv = verts[full.vertices]
+    if len(hv) > max_verts:
+        n = 96
+        k = np.arange(n) + 0.5
+        phi, th = np.arccos(1 - 2 * k / n), np.pi * (1 + 5 ** 0.5) * k
+        dirs = np.concatenate([np.eye(3), -np.eye(3), np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], 1)])
+        idx = np.unique(np.argmax(hv @ dirs.T, axis=0))
+        cand = hv[idx]
+        if len(cand) > max_verts:   # farthest-point thinning, seeded with the extreme points along the axes
+            keep = list(np.unique(np.concatenate([np.argmax(cand, axis=0), np.argmin(cand, axis=0)])))
+            d = np.min(np.linalg.norm(cand[:, None, :] - cand[keep][None, :, :], axis=2), axis=1)
+            while len(keep) < max_verts:
+                j = int(np.argmax(d))
+                keep.append(j)
+                d = np.minimum(d, np.linalg.norm(cand - cand[j], axis=1))
+            cand = cand[sorted(keep)]
+        hv = cand
+    try:
+        red = ConvexHull(hv)
+    except QhullError:
+        return None
+    V = hv[red.vertices]
+    eq = red.equations                                   # n . x + d <= 0 inside
+    planes = np.concatenate([eq[:, :3], -eq[:, 3:4]], axis=1)
+    key = np.round(planes / np.maximum(np.abs(planes).max(), 1e-12), 5)
+    _, first = np.unique(key, axis=0, return_index=True)
+    planes = planes[np.sort(first)]
+    if len(planes) > max_planes:                         # keep the largest facets' planes: merge by dropping near-duplicates of kept normals
+        order = np.argsort(-np.array([np.sum(np.isclose(eq[:, :3] @ pl[:3], 1.0, atol=1e-3)) for pl in planes]))
+        planes = planes[np.sort(order[:max_planes])]
+    return V, planes

@@ -26,6 +26,7 @@ SECTIONS = [
     ('HDR_I', 'i'), ('HDR_F', 'f'), ('BODY_I', 'i'), ('BODY_F', 'f'), ('LINK_I', 'i'), ('LINK_F', 'f'), ('SHAPE_I', 'i'),
     ('SHAPE_F', 'f'), ('PAIR_I', 'i'), ('VIS_I', 'i'), ('VIS_F', 'f'), ('OP_I', 'i'), ('OPARG_I', 'i'), ('OPARG_F', 'f'),
     ('PARAM_DEFAULT', 'f'), ('STATE_DEFAULT', 'f'), ('CAM_I', 'i'), ('CAM_F', 'f'), ('CONS_I', 'i'), ('CONS_F', 'f'),
+    ('HULL_F', 'f'),   # reduced convex hulls of mesh collision shapes: per hull its vertices (3 floats each), then its planes (4 each)
 ]
 SECTION_ID = {name: i for i, (name, _) in enumerate(SECTIONS)}
 MAGIC = 0x44594742  # 'DYGB'
@@ -45,7 +46,7 @@ HDR_F_FIELDS = ['dt', 'gx', 'gy', 'gz', 'erp', 'contact_erp', 'linear_slop', 'co
 
 BODY_I_W, BODY_F_W = 8, 8
 LINK_I_W, LINK_F_W = 6, 28
-SHAPE_I_W, SHAPE_F_W = 4, 20
+SHAPE_I_W, SHAPE_F_W = 8, 20   # ints: body, frame, type, baked, hull vertex offset (floats into HULL_F), vertices, plane offset, planes
 VIS_I_W, VIS_F_W = 4, 24
 OP_I_W = 8
 CAM_I_W, CAM_F_W = 8, 16
@@ -156,7 +157,8 @@ class BodyInfo:
 
 
 class SceneBuilder:
-    def __init__(self, timestep=1 / 240., substeps=2, iterations=150, gravity=(0, 0, -9.81), hot_start=1, max_contacts=16, semantics=()):
+    def __init__(self, timestep=1 / 240., substeps=2, iterations=150, gravity=(0, 0, -9.81), hot_start=1, max_contacts=16, semantics=(), convex=True):
+        self.convex = bool(convex)   # collide mesh links as reduced convex hulls (against boxes and other hulls); False: fitted proxies only
         self.semantics = sum(SEMANTICS[k] for k in semantics)
         self.timestep, self.substeps, self.iterations = float(timestep), int(substeps), int(iterations)
         self.gravity, self.hot_start, self.max_contacts = tuple(float(g) for g in gravity), int(hot_start), int(max_contacts)
@@ -294,7 +296,8 @@ class SceneBuilder:
                     dims = np.asarray(c['dims'], float) * s
                     Tw = Transform(b.base_pos, b.base_quat) * T
                     shapes.append(dict(body=b.index, frame=fr, type=SHAPE_TYPES[c['type']], pos=T.p, quat=T.q, dims=dims,
-                                       friction=fric, baked=int(b.kind == 0 and not b.per_env_pose), wpos=Tw.p, wquat=Tw.q))
+                                       friction=fric, baked=int(b.kind == 0 and not b.per_env_pose), wpos=Tw.p, wquat=Tw.q,
+                                       hull=c.get('hull') if self.convex else None, scale=s))
                 for v in l['visuals']:
                     T = Tci * Transform(np.asarray(v['xyz']) * s, v['quat'])
                     dims = np.asarray(v['dims'], float) * s
@@ -307,15 +310,23 @@ class SceneBuilder:
 
         ns, nv = len(shapes), len(visuals)
         shape_i = np.zeros((ns, SHAPE_I_W), np.int32)
+        hull_f = []
         shape_f = np.zeros((ns, SHAPE_F_W))
         friction = np.zeros(ns)
         for i, sh in enumerate(shapes):
-            shape_i[i] = [sh['body'], sh['frame'], sh['type'], sh['baked']]
+            shape_i[i, :4] = [sh['body'], sh['frame'], sh['type'], sh['baked']]
             shape_f[i, 12:15], shape_f[i, 15:19] = sh['wpos'], sh['wquat']
             shape_f[i, 0:3], shape_f[i, 3:7], shape_f[i, 7:11] = sh['pos'], sh['quat'], sh['dims']
             d = sh['dims']
             shape_f[i, 11] = {0: d[0], 1: float(np.linalg.norm(d[:3])), 2: d[0] + d[1], 3: float(np.hypot(d[0], d[1]))}[sh['type']]
             friction[i] = sh['friction']
+            if sh.get('hull'):   # reduced convex hull of a mesh link, in the shape frame, scaled like the model
+                V = np.asarray(sh['hull']['verts'], float) * sh['scale']
+                Pl = np.asarray(sh['hull']['planes'], float).copy()
+                Pl[:, 3] *= sh['scale']
+                shape_i[i, 4:8] = [len(hull_f), len(V), len(hull_f) + 3 * len(V), len(Pl)]
+                hull_f += V.reshape(-1).tolist() + Pl.reshape(-1).tolist()
+                shape_f[i, 11] = max(shape_f[i, 11], float(np.linalg.norm(V, axis=1).max()))   # the bound the broad phase uses covers the hull
         vis_i = np.zeros((nv, VIS_I_W), np.int32)
         vis_f = np.zeros((nv, VIS_F_W))
         for i, v in enumerate(visuals):
@@ -428,7 +439,8 @@ class SceneBuilder:
 
         sec = dict(HDR_I=hdr_i, HDR_F=hdr_f, BODY_I=body_i, BODY_F=body_f, LINK_I=link_i, LINK_F=link_f, SHAPE_I=shape_i,
                    SHAPE_F=shape_f, PAIR_I=pair_i, VIS_I=vis_i, VIS_F=vis_f, OP_I=op_i, OPARG_I=np.array(oparg_i, np.int32),
-                   OPARG_F=np.array(oparg_f, float), PARAM_DEFAULT=param, STATE_DEFAULT=state, CAM_I=cam_i, CAM_F=cam_f, CONS_I=cons_i, CONS_F=cons_f)
+                   OPARG_F=np.array(oparg_f, float), PARAM_DEFAULT=param, STATE_DEFAULT=state, CAM_I=cam_i, CAM_F=cam_f, CONS_I=cons_i, CONS_F=cons_f,
+                   HULL_F=np.array(hull_f, float))
         self.finalized = Scene(sec, hdr, hf, self)
         return self.finalized
 

@@ -80,10 +80,26 @@ def _geometry(geom_elem, origin_xyz, origin_rpy, urdf_dir, cache):
             else:
                 verts = meshlib.load_vertices(path) * np.asarray(scale)
                 cache[key] = meshlib.fit_proxy(verts) if len(verts) else None
+                if cache[key] is not None and not cache[key].get('exact'):   # (a mesh that IS a box stays a box)
+                    # reduced convex hull of the mesh, in the frame of the fitted proxy (the shape frame the kernels use):
+                    # collided against boxes and other hulls; the proxy stays the broad-phase bound and the partner of spheres,
+                    # capsules and cylinders
+                    try:
+                        hull = meshlib.reduced_hull(verts)
+                    except ImportError:
+                        hull = None
+                    if hull is not None:
+                        Rz = quat_to_mat(np.asarray(_AXIS_TO_Z[cache[key]['axis']], float))
+                        V = (hull[0] - np.asarray(cache[key]['center'])) @ Rz          # R^T (v - c), row vectors
+                        N = hull[1][:, :3] @ Rz
+                        D = hull[1][:, 3] - hull[1][:, :3] @ np.asarray(cache[key]['center'])
+                        cache[key]['hull'] = dict(verts=V.tolist(), planes=np.concatenate([N, D[:, None]], axis=1).tolist())
         fit = cache[key]
         if fit is None:
             return None
         shape = dict(type=fit['type'], dims=list(fit['dims']) + [0.0] * (4 - len(fit['dims'])), mesh=os.path.basename(fname))
+        if 'hull' in fit:
+            shape['hull'] = fit['hull']
         T_aabb = T_link_geom * Transform(fit['center'])
         shape['aabb'] = dict(xyz=T_aabb.p.tolist(), quat=T_aabb.q.tolist(), half=list(fit['half']))
         T_link_geom = T_link_geom * Transform(fit['center'], _AXIS_TO_Z[fit['axis']])

@@ -569,6 +569,41 @@ DG_HD bool pair_in_reach(const Env& C, int sa, int sb) {
   float reach = gc(SC.shape_f)[DG_SHAPE_F_W * sa + 11] + gc(SC.shape_f)[DG_SHAPE_F_W * sb + 11] + SC.margin;
   return v_dot(dc, dc) <= reach * reach;
 }
+// ---- reduced convex hulls (mesh links; model.py:65 loads them as btConvexHullShape) ----------------------------------------
+// signed distance of world point p to the hull (R, pos; planes n . x <= d in its own frame): the largest plane distance.  Inside or
+// within `margin`: returns 1 with the outward normal of that plane (world), the point moved onto it, and the (negative) distance.
+DG_FN int point_hull(const float* p, const float* R, const float* pos, const float* planes, int np_, float margin, float* surf, float* n, float* dist) {
+  float d[3], pl[3]; v_sub(d, p, pos); mT_vec(pl, R, d);
+  float best = -1e30f; int bi = 0;
+  for (int k = 0; k < np_; k++) { const float* q = planes + 4 * k; const float s = q[0] * pl[0] + q[1] * pl[1] + q[2] * pl[2] - q[3]; if (s > best) { best = s; bi = k; } }
+  if (best > margin) return 0;
+  m_vec(n, R, planes + 4 * bi); *dist = best;
+  surf[0] = p[0] - n[0] * best; surf[1] = p[1] - n[1] * best; surf[2] = p[2] - n[2] * best;
+  return 1;
+}
+// Convex pair with at least one hull (the other a hull or a box): the vertices of each that lie inside the other (edge-edge
+// contacts are not generated, as in the box-box routine below); candidates in `loc`, the caller keeps the deepest four.
+// Contact convention: (pa on A, pb on B, normal from B towards A).
+DG_FN void collide_convex(const Env& C, const int* ia, const float* fa, const float* Ra, const float* pa, const int* ib, const float* fb, const float* Rb, const float* pb,
+                          float mu, float margin, Ct* loc, int* nloc) {
+  const float* H = gc(SC.hull_f);
+  for (int side = 0; side < 2; side++) {
+    // X: the shape whose vertices are tested, Y: the shape they are tested against
+    const int* ix = side ? ib : ia; const int* iy = side ? ia : ib; const float* fx = side ? fb : fa; const float* fy = side ? fa : fb;
+    const float *Rx = side ? Rb : Ra, *px = side ? pb : pa, *Ry = side ? Ra : Rb, *py = side ? pa : pb;
+    const int nvx = ix[5] > 0 ? ix[5] : 8;
+    for (int k = 0; k < nvx; k++) {
+      float vl[3], t[3], pt[3], surf[3], n[3], dist;
+      if (ix[5] > 0) { const float* v = H + ix[4] + 3 * k; vl[0] = v[0]; vl[1] = v[1]; vl[2] = v[2]; }
+      else { vl[0] = (k & 1 ? 1 : -1) * fx[7]; vl[1] = (k & 2 ? 1 : -1) * fx[8]; vl[2] = (k & 4 ? 1 : -1) * fx[9]; }
+      m_vec(t, Rx, vl); v_add(pt, px, t);
+      const int hit = iy[5] > 0 ? point_hull(pt, Ry, py, H + iy[6], iy[7], margin, surf, n, &dist) : point_box(pt, Ry, py, fy + 7, margin, surf, n, &dist);
+      if (!hit) continue;
+      if (side == 0) ct_add(loc, nloc, 16, ia[1], ib[1], pt, surf, n, dist, mu, margin);                       // vertex of A in B: normal of B
+      else { float nn[3]; v_scale(nn, n, -1.0f); ct_add(loc, nloc, 16, ia[1], ib[1], surf, pt, nn, dist, mu, margin); }   // vertex of B in A
+    }
+  }
+}
 // narrow phase of one shape pair; writes at most 4 contacts into out, returns the count
 DG_FN int collide_pair(const Env& C, int sa, int sb, Ct* out) {
   const DevScene& sc = SC;
@@ -581,6 +616,16 @@ DG_FN int collide_pair(const Env& C, int sa, int sb, Ct* out) {
   float mu = PR(P_FRICTION)[sa] * PR(P_FRICTION)[sb];
   int nt_ = 0;
   float ca[3], cb[3], n[3], dist;
+  // mesh links: reduced hull against a box or another hull; against spheres / capsules / cylinders the fitted proxy stands in
+  const bool ha = ia[5] > 0, hb_ = ib[5] > 0;
+  if ((ha && (hb_ || tb == SHAPE_BOX)) || (hb_ && (ha || ta == SHAPE_BOX))) {
+    Ct loc[16]; int nloc = 0;
+    collide_convex(C, ia, fa, Ra, pa, ib, fb, Rb, pb, mu, margin, loc, &nloc);
+    for (int i = 0; i < nloc; i++) for (int j = i + 1; j < nloc; j++) if (loc[j].dist < loc[i].dist) { Ct t = loc[i]; loc[i] = loc[j]; loc[j] = t; }
+    if (nloc > 4) nloc = 4;
+    for (int i = 0; i < nloc; i++) out[nt_++] = loc[i];
+    return nt_;
+  }
   if (ta != SHAPE_BOX && tb != SHAPE_BOX) {
     float a0[3], a1[3], b0[3], b1[3], ra, rb, d1[3], d2[3], s, t, c1[3], c2[3];
     as_capsule(ta, fa + 7, Ra, pa, a0, a1, &ra); as_capsule(tb, fb + 7, Rb, pb, b0, b1, &rb);

@@ -43,6 +43,7 @@ struct DevScene {
   float dt, g[3], erp, cerp, slop, margin, ik_damping, ik_threshold, max_joint_vel, limit_max_impulse, ik_null_lambda_sq;
   const int *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
   const float *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *cam_f, *param_def, *state_def;
+  const float* hull_f;    // reduced convex hulls of mesh collision shapes (shape_i[4..7]: vertex offset, vertices, plane offset, planes)
   // ---- plan ----
   int ndyn, nslot, nshw, nfloat, GD, GP, max_depth, max_nlb, n_ik, team;
   const int* dyn_body;    // [ndyn] body index of every body with kind != 0
@@ -103,7 +104,7 @@ struct HostScene {
 
   // offsets of every table inside ints / floats (so a device copy can be re-pointed)
   struct Off { size_t body_i, link_i, shape_i, pair_i, vis_i, op_i, oparg_i, cam_i, dyn_body, body_plan, frame_slot, link_depth, shape_slot, grp_i, grp_pairs, loose_pairs;
-               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x, body_reach, cons_i, cons_f; } off;
+               size_t body_f, link_f, shape_f, vis_f, oparg_f, cam_f, param_def, state_def, shape_wb, vis_wb, link_x, body_reach, cons_i, cons_f, hull_f; } off;
 
   static void quat_to_mat(const double* q, double* m) {
     double x = q[0], y = q[1], z = q[2], w = q[3];
@@ -122,7 +123,7 @@ struct HostScene {
     d.body_f = fb + off.body_f; d.link_f = fb + off.link_f; d.shape_f = fb + off.shape_f; d.vis_f = fb + off.vis_f;
     d.oparg_f = fb + off.oparg_f; d.cam_f = fb + off.cam_f; d.param_def = fb + off.param_def; d.state_def = fb + off.state_def;
     d.shape_wb = fb + off.shape_wb; d.vis_wb = fb + off.vis_wb; d.link_x = fb + off.link_x;
-    d.cons_i = ib + off.cons_i; d.cons_f = fb + off.cons_f;
+    d.cons_i = ib + off.cons_i; d.cons_f = fb + off.cons_f; d.hull_f = fb + off.hull_f;
   }
 
   bool build(const int32_t* ibuf, int ni, const double* fbuf, int nf, int team, int ws_mode = 0, int rs_ashared = 0) {
@@ -156,7 +157,7 @@ struct HostScene {
     off.vis_i = put_i(SEC_VIS_I); off.op_i = put_i(SEC_OP_I); off.oparg_i = put_i(SEC_OPARG_I); off.cam_i = put_i(SEC_CAM_I);
     off.body_f = put_f(SEC_BODY_F); off.link_f = put_f(SEC_LINK_F); off.shape_f = put_f(SEC_SHAPE_F); off.vis_f = put_f(SEC_VIS_F);
     off.oparg_f = put_f(SEC_OPARG_F); off.cam_f = put_f(SEC_CAM_F); off.param_def = put_f(SEC_PARAM_DEFAULT); off.state_def = put_f(SEC_STATE_DEFAULT);
-    off.cons_i = put_i(SEC_CONS_I); off.cons_f = put_f(SEC_CONS_F);
+    off.cons_i = put_i(SEC_CONS_I); off.cons_f = put_f(SEC_CONS_F); off.hull_f = put_f(SEC_HULL_F);
     d.ncons = hi[HI_ncons];
 
     const int32_t* body_i = ibuf + sec_off(SEC_BODY_I);

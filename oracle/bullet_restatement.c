@@ -120,6 +120,7 @@ typedef struct {
 typedef struct DgoWorld {
   int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters, need_react, ncons, sem;
   const int32_t* cons_i; const double* cons_f;
+  const double* hull_f;   /* reduced convex hulls of mesh collision shapes (shape_i[4..7]) */
   int32_t* ibuf; double* fbuf;
   const int32_t *hi, *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
   const double *hf, *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *param_def, *state_def, *cam_f;
@@ -161,7 +162,7 @@ DgoWorld* dgo_create(const int32_t* ibuf, int ni, const double* fbuf, int nf) {
   W->ncam = HI(W, ncam); W->nop = HI(W, nop); W->nframes = HI(W, nframes); W->S = HI(W, S); W->P = HI(W, P);
   W->substeps = HI(W, substeps); W->iters = HI(W, iterations); W->maxc = HI(W, max_contacts); W->hot_start = HI(W, hot_start);
   W->ik_iters = HI(W, ik_iters); W->sem = HI(W, semantics);   /* SEM_* switches (compiler/scene.py SEMANTICS) */
-  W->ncons = HI(W, ncons); W->cons_i = sec_i(ib, SEC_CONS_I); W->cons_f = sec_f(ib, fb, SEC_CONS_F);
+  W->ncons = HI(W, ncons); W->cons_i = sec_i(ib, SEC_CONS_I); W->cons_f = sec_f(ib, fb, SEC_CONS_F); W->hull_f = sec_f(ib, fb, SEC_HULL_F);
   W->need_react = HI(W, S_STEP) > HI(W, S_JREACT);   /* the state row holds reaction wrenches only when a sensor asked for them */
   int nf_ = W->nframes, nl = W->nl > 0 ? W->nl : 1;
 #define ALLOC(p, n) W->p = (double*)calloc((size_t)(n) > 0 ? (size_t)(n) : 1, sizeof(double))
@@ -495,6 +496,39 @@ static void as_capsule(int type, const double* dims, const double* R, const doub
   double ax[3] = {R[2] * half, R[5] * half, R[8] * half};
   v_sub(e0, p, ax); v_add(e1, p, ax);
 }
+/* ---- reduced convex hulls: mesh links (diy_gym/model.py:65 loads them as convex hulls; here at most 32 vertices, compiler/mesh.py).
+ * Signed distance of world point p to the hull = the largest plane distance; inside or within `margin`: the outward normal of that
+ * plane, the point moved onto it, and the (negative) distance. */
+static int point_hull(const double* p, const double* R, const double* pos, const double* planes, int np_, double margin, double* surf, double* n, double* dist) {
+  double d[3], pl[3]; v_sub(d, p, pos); mT_vec(pl, R, d);
+  double best = -1e300; int bi = 0;
+  for (int k = 0; k < np_; k++) { const double* q = planes + 4 * k; double s = q[0] * pl[0] + q[1] * pl[1] + q[2] * pl[2] - q[3]; if (s > best) { best = s; bi = k; } }
+  if (best > margin) return 0;
+  m_vec(n, R, planes + 4 * bi); *dist = best;
+  for (int i = 0; i < 3; i++) surf[i] = p[i] - n[i] * best;
+  return 1;
+}
+/* convex pair with at least one hull (the other a hull or a box): vertices of each inside the other (no edge-edge contacts, as in the
+ * box-box routine); contact convention (pa on A, pb on B, normal from B towards A) */
+static void collide_convex(DgoWorld* W, const int32_t* ia, const double* fa, const double* Ra, const double* pa, const int32_t* ib, const double* fb,
+                           const double* Rb, const double* pb, double mu, double margin, Contact* loc, int* nloc) {
+  const double* H = W->hull_f;
+  for (int side = 0; side < 2; side++) {
+    const int32_t *ix = side ? ib : ia, *iy = side ? ia : ib; const double *fx = side ? fb : fa, *fy = side ? fa : fb;
+    const double *Rx = side ? Rb : Ra, *px = side ? pb : pa, *Ry = side ? Ra : Rb, *py = side ? pa : pb;
+    int nvx = ix[5] > 0 ? ix[5] : 8;
+    for (int k = 0; k < nvx; k++) {
+      double vl[3], t[3], pt[3], surf[3], n[3], dist;
+      if (ix[5] > 0) { const double* v = H + ix[4] + 3 * k; v_cpy(vl, v); }
+      else { vl[0] = (k & 1 ? 1 : -1) * fx[7]; vl[1] = (k & 2 ? 1 : -1) * fx[8]; vl[2] = (k & 4 ? 1 : -1) * fx[9]; }
+      m_vec(t, Rx, vl); v_add(pt, px, t);
+      int hit = iy[5] > 0 ? point_hull(pt, Ry, py, H + iy[6], iy[7], margin, surf, n, &dist) : point_box(pt, Ry, py, fy + 7, margin, surf, n, &dist);
+      if (!hit) continue;
+      if (side == 0) add_contact(W, ia[1], ib[1], pt, surf, n, dist, mu, margin, loc, nloc);
+      else { double nn[3]; v_scale(nn, n, -1.0); add_contact(W, ia[1], ib[1], surf, pt, nn, dist, mu, margin, loc, nloc); }
+    }
+  }
+}
 static void collide_pair(DgoWorld* W, int sa, int sb, double margin) {
   const int32_t *ia = W->shape_i + DG_SHAPE_I_W * sa, *ib = W->shape_i + DG_SHAPE_I_W * sb;
   const double *fa = W->shape_f + DG_SHAPE_F_W * sa, *fb = W->shape_f + DG_SHAPE_F_W * sb;
@@ -507,7 +541,15 @@ static void collide_pair(DgoWorld* W, int sa, int sb, double margin) {
   double mu = PR(W, P_FRICTION)[sa] * PR(W, P_FRICTION)[sb];
   Contact tmp[16]; int nt = 0;
   double ca[3], cb[3], n[3], dist;
-  if (ta != SHAPE_BOX && tb != SHAPE_BOX) {
+  int ha = ia[5] > 0, hb_ = ib[5] > 0;
+  if ((ha && (hb_ || tb == SHAPE_BOX)) || (hb_ && (ha || ta == SHAPE_BOX))) {
+    /* mesh links: reduced hull against a box or another hull (spheres / capsules / cylinders meet the fitted proxy below) */
+    Contact loc[16]; int nloc = 0;
+    collide_convex(W, ia, fa, Ra, pa, ib, fb, Rb, pb, mu, margin, loc, &nloc);
+    for (int i = 0; i < nloc; i++) for (int j = i + 1; j < nloc; j++) if (loc[j].dist < loc[i].dist) { Contact t = loc[i]; loc[i] = loc[j]; loc[j] = t; }
+    if (nloc > 4) nloc = 4;
+    for (int i = 0; i < nloc; i++) tmp[nt++] = loc[i];
+  } else if (ta != SHAPE_BOX && tb != SHAPE_BOX) {
     double a0[3], a1[3], b0[3], b1[3], ra, rb, d1[3], d2[3], s, t, c1[3], c2[3];
     as_capsule(ta, fa + 7, Ra, pa, a0, a1, &ra); as_capsule(tb, fb + 7, Rb, pb, b0, b1, &rb);
     v_sub(d1, a1, a0); v_sub(d2, b1, b0); seg_closest(a0, d1, b0, d2, &s, &t);
