@@ -115,7 +115,7 @@ def test_free_body_and_contacts_drone_lands_on_plane():
         w.step()
         o.step_physics()
     torch.cuda.synchronize()
-    assert len(o.contacts()) >= 3
+    assert len(o.contacts()) >= 2                    # (the body mesh is a convex hull now: it may rest on an edge of it)
     assert abs(w.s('S_BPOS', 6).cpu().numpy()[2, 5] - o.s('S_BPOS', 6)[5]) < 1e-3
     assert np.abs(w.s('S_BVEL', 6).cpu().numpy()[:, 3:]).max() < 1e-3
     w.close()
