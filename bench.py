@@ -40,6 +40,7 @@ CONFIGS = {
     'ur_admittance': ('examples/ur_admittance/ur_admittance.yaml', 8192),
     'ur_gripper': ('examples/ur_gripper/ur_gripper.yaml', 4096),
     'ur_extras': ('examples/ur_extras/ur_extras.yaml', 4096),
+    'ur_robotiq': ('examples/ur_gripper/ur_robotiq.yaml', 4096),
 }
 METRIC = 'aggregate env-steps/sec'
 UNIT = 'env-steps/s'

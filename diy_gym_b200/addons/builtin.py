@@ -414,8 +414,13 @@ class ForceTorqueSensor(_OpAddon):
         return {'force': self._obs[:, 0:3], 'torque': self._obs[:, 3:6]}
 
 
-class VisualRandomizer(_Unsupported):
-    reason = 'downloads a texture dataset over HTTP in the reference; out of scope'
+class VisualRandomizer(_OpAddon):
+    """`misc/visual_randomizer.py`: a new look for the parent model on every reset.  The reference applies a random texture of a
+    dataset it downloads on first use (visual_randomizer.py:41-60); this backend has no textures, so the randomisation is a random
+    colour per visual shape of the model, per environment and reset, from the same counter-based stream as respawn /
+    dynamics_randomizer (op `VIS_RANDOMIZE`, stored in the parameter rows, read by the camera kernel)."""
+    def compile(self, sb):
+        self.op = sb.add_op('VIS_RANDOMIZE', [self.parent.body.index], [])
 
 
 class FilteredLinkWrench(_OpAddon):

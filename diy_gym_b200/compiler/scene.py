@@ -39,7 +39,7 @@ HDR_I_FIELDS = [
     'S_MAPPLIED', 'S_JTORQUE', 'S_EXTF', 'S_EXTT', 'S_LPOS', 'S_LQUAT', 'S_LVEL', 'S_LOMEGA', 'S_JREACT', 'S_STEP', 'S_RESETS',
     'S_ADDON',
     # param offsets
-    'P_MASS', 'P_INERTIA', 'P_LINDAMP', 'P_ANGDAMP', 'P_JDAMP', 'P_FRICTION', 'P_INITPOSE', 'P_RESTQ',
+    'P_MASS', 'P_INERTIA', 'P_LINDAMP', 'P_ANGDAMP', 'P_JDAMP', 'P_FRICTION', 'P_INITPOSE', 'P_RESTQ', 'P_COLOR',
 ]
 HDR_F_FIELDS = ['dt', 'gx', 'gy', 'gz', 'erp', 'contact_erp', 'linear_slop', 'contact_margin', 'ik_damping',
                 'ik_threshold', 'max_joint_vel', 'default_motor_impulse', 'limit_max_impulse', 'ik_null_lambda_sq']
@@ -57,7 +57,7 @@ JOINT_TYPES = {'fixed': 0, 'revolute': 1, 'continuous': 1, 'prismatic': 2}
 
 OP = dict(JOINT_CTRL=1, EXT_FORCE=2, IK_CTRL=3, JOINT_SENSOR=4, OBJECT_SENSOR=5, REACH_TARGET=6, ELECTRICITY=7,
           STUCK_JOINT=8, TIME_PENALTY=9, EPISODE_TIMER=10, RESPAWN=11, JOINT_RESET=12, DYN_RANDOMIZE=13, ADMITTANCE=14, FT_SENSOR=15,
-          FILTERED_WRENCH=16, TILT_TERMINAL=17)
+          FILTERED_WRENCH=16, TILT_TERMINAL=17, VIS_RANDOMIZE=18)
 
 # Engine semantics that SURVEY Appendix A could only RECALL (no pybullet here to check): each is a named switch of the scene
 # header, honoured by the kernels and by the oracle alike, so that the day a pybullet golden vector disagrees the fix is a flag.
@@ -360,7 +360,7 @@ class SceneBuilder:
         S = off
         off = 0
         for name, n in [('P_MASS', nframes), ('P_INERTIA', 3 * nframes), ('P_LINDAMP', nb), ('P_ANGDAMP', nb), ('P_JDAMP', nd),
-                        ('P_FRICTION', ns), ('P_INITPOSE', 7 * nb), ('P_RESTQ', nd)]:
+                        ('P_FRICTION', ns), ('P_INITPOSE', 7 * nb), ('P_RESTQ', nd), ('P_COLOR', 3 * nv)]:   # P_COLOR: rgb per visual shape (visual_randomizer)
             lay[name] = off
             off += n
         P = off
@@ -374,6 +374,7 @@ class SceneBuilder:
         param[lay['P_FRICTION']:lay['P_FRICTION'] + ns] = friction
         param[lay['P_INITPOSE']:lay['P_INITPOSE'] + 7 * nb] = init_pose.reshape(-1)
         param[lay['P_RESTQ']:lay['P_RESTQ'] + nd] = restq
+        param[lay['P_COLOR']:lay['P_COLOR'] + 3 * nv] = vis_f[:, 11:14].reshape(-1)
 
         state = np.zeros(S)
         state[lay['S_BPOS']:lay['S_BPOS'] + 3 * nb] = init_pose[:, 0:3].reshape(-1)

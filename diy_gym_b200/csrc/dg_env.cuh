@@ -1938,6 +1938,10 @@ DG_FN void phase_reset_ops(const Env& C, int ln, int nt) {
       for (int i = 0; i < 3; i++) e[i] = (urand(C.seed, (uint32_t)C.env_id, ep, (uint32_t)(k * 8 + 3 + i)) - 0.5f) * fa[3 + i];
       q_from_euler(dq, e); q_mul(qo, ip + 3, dq); for (int i = 0; i < 4; i++) ST(S_BQUAT)[4 * b + i] = qo[i];
       v_set(ST(S_BVEL) + 3 * b, 0, 0, 0); v_set(ST(S_BOMEGA) + 3 * b, 0, 0, 0);
+    } else if (op[0] == OP_VIS_RANDOMIZE) {             // visual_randomizer.py:41-46: a new look for the model on every reset - here a random
+      // colour per visual shape of the body (the reference picks a random texture of a dataset it downloads; out of scope)
+      for (int v = 0; v < sc.nv; v++) if (gc(sc.vis_i)[DG_VIS_I_W * v + 3] == ia[0])
+        for (int i = 0; i < 3; i++) PR(P_COLOR)[3 * v + i] = urand(C.seed, (uint32_t)C.env_id, epoch, (uint32_t)(k * 8 + 128 + 3 * v + i));
     } else if (op[0] == OP_DYN_RANDOMIZE) {             // dynamics_randomizer.py:24-32 (log-uniform on nominal values)
       int b = ia[0]; const int* bi = gc(sc.body_i) + DG_BODY_I_W * b;
       for (int l = -1; l < bi[2]; l++) {

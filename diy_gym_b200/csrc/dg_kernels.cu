@@ -304,7 +304,7 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_ZMIN 34
 #define VS_RECT 35
 #define VS_BODY 39
-__global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, int cam, float* rgb, float* depth,
+__global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
   // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
   // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 4 pixel patches:
@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
         m_vec(t, R, vf); v_add(o + 9, p, t);
       }
       for (int i = 0; i < 4; i++) o[12 + i] = vf[7 + i];
-      for (int i = 0; i < 3; i++) o[16 + i] = vf[11 + i];
+      for (int i = 0; i < 3; i++) o[16 + i] = param[(size_t)e * sc.P + DG_PO(&sc, P_COLOR) + 3 * s + i];   // per-environment colour (visual_randomizer)
       o[19] = int_as_float(vi[1]); o[20] = vf[15];
       const float r = o[20];
       float oc[3], ol[3]; v_sub(oc, camRp + 9, o + 9); mT_vec(ol, o, oc);
@@ -866,7 +866,7 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
   int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
   w->launches++;
-  dg_render_kernel<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
+  dg_render_kernel<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
   CK(w, cudaGetLastError());
   return DG_OK;
 }

@@ -39,7 +39,7 @@ struct DevScene {
   int nb, nl, nd, ns, nv, npair, ncam, nop, nframes, S, P, substeps, iters, maxc, hot_start, ik_iters;
   int n_act, n_obs, n_rew, n_term;
   int so[24];  // state offsets:  so[HI_S_x - HI_S_BPOS]
-  int po[8];   // param offsets:  po[HI_P_x - HI_P_MASS]
+  int po[12];  // param offsets:  po[HI_P_x - HI_P_MASS]
   float dt, g[3], erp, cerp, slop, margin, ik_damping, ik_threshold, max_joint_vel, limit_max_impulse, ik_null_lambda_sq;
   const int *body_i, *link_i, *shape_i, *pair_i, *vis_i, *op_i, *oparg_i, *cam_i;
   const float *body_f, *link_f, *shape_f, *vis_f, *oparg_f, *cam_f, *param_def, *state_def;
@@ -143,7 +143,7 @@ struct HostScene {
     d.substeps = hi[HI_substeps]; d.iters = hi[HI_iterations]; d.maxc = hi[HI_max_contacts]; d.hot_start = hi[HI_hot_start];
     d.ik_iters = hi[HI_ik_iters]; d.n_act = hi[HI_n_act]; d.n_obs = hi[HI_n_obs]; d.n_rew = hi[HI_n_rew]; d.n_term = hi[HI_n_term];
     for (int k = HI_S_BPOS; k <= HI_S_ADDON; k++) d.so[k - HI_S_BPOS] = hi[k];
-    for (int k = HI_P_MASS; k <= HI_P_RESTQ; k++) d.po[k - HI_P_MASS] = hi[k];
+    for (int k = HI_P_MASS; k <= HI_P_COLOR; k++) d.po[k - HI_P_MASS] = hi[k];
     d.dt = (float)hf[HF_dt]; d.g[0] = (float)hf[HF_gx]; d.g[1] = (float)hf[HF_gy]; d.g[2] = (float)hf[HF_gz];
     d.erp = (float)hf[HF_erp]; d.cerp = (float)hf[HF_contact_erp]; d.slop = (float)hf[HF_linear_slop]; d.margin = (float)hf[HF_contact_margin];
     d.ik_damping = (float)hf[HF_ik_damping]; d.ik_threshold = (float)hf[HF_ik_threshold]; d.max_joint_vel = (float)hf[HF_max_joint_vel];

@@ -1140,6 +1140,10 @@ void dgo_env_reset(DgoWorld* W) {
       for (int i = 0; i < 3; i++) e[i] = (urand(W->seed, (uint32_t)W->env_id, ep, (uint32_t)(k * 8 + 3 + i)) - 0.5) * fa[3 + i];
       q_from_euler(dq, e); q_mul(qo, ip + 3, dq); memcpy(ST(W, S_BQUAT) + 4 * b, qo, 32);
       v_set(ST(W, S_BVEL) + 3 * b, 0, 0, 0); v_set(ST(W, S_BOMEGA) + 3 * b, 0, 0, 0);
+    } else if (op[0] == OP_VIS_RANDOMIZE) {             /* visual_randomizer.py:41-46: a new look per reset - a random colour per visual shape of the
+                                                           body (the reference's random texture comes from a dataset it downloads) */
+      for (int v = 0; v < W->nv; v++) if (W->vis_i[DG_VIS_I_W * v + 3] == ia[0])
+        for (int i = 0; i < 3; i++) PR(W, P_COLOR)[3 * v + i] = urand(W->seed, (uint32_t)W->env_id, epoch, (uint32_t)(k * 8 + 128 + 3 * v + i));
     } else if (op[0] == OP_DYN_RANDOMIZE) {             /* dynamics_randomizer.py:24-32 (log-uniform on nominal values) */
       int b = ia[0]; const int32_t* bi = W->body_i + DG_BODY_I_W * b;
       for (int l = -1; l < bi[2]; l++) {
@@ -1248,7 +1252,7 @@ void dgo_render_seg(DgoWorld* W, int cam, double* rgb, double* depth, double* se
     if (seg) seg[px] = hs < 0 ? -1.0 : (double)W->vis_i[DG_VIS_I_W * hs + 3];   /* camera.py:89-90: unique id of the visible body */
     if (hs < 0) { rgb[3 * px] = rgb[3 * px + 1] = rgb[3 * px + 2] = 1.0; depth[px] = -farp; }
     else {
-      const double* col = W->vis_f + DG_VIS_F_W * hs + 11; double nl = v_dot(hn, light); if (nl < 0) nl = 0;
+      const double* col = PR(W, P_COLOR) + 3 * hs; double nl = v_dot(hn, light); if (nl < 0) nl = 0;   /* per-environment colour (visual_randomizer) */
       double sh = 0.4 + 0.6 * nl;
       for (int k = 0; k < 3; k++) rgb[3 * px + k] = col[k] * sh;
       depth[px] = -best;
@@ -1293,7 +1297,7 @@ void dgo_get_camera_image(DgoWorld* W, int width, int height, const double* view
     }
     const int px = j * width + i;
     double col[3] = {1, 1, 1};
-    if (hs >= 0) { const double* c = W->vis_f + DG_VIS_F_W * hs + 11; double nl = v_dot(hn, light); if (nl < 0) nl = 0; const double sh = 0.4 + 0.6 * nl; for (int k = 0; k < 3; k++) col[k] = c[k] * sh; }
+    if (hs >= 0) { const double* c = PR(W, P_COLOR) + 3 * hs; double nl = v_dot(hn, light); if (nl < 0) nl = 0; const double sh = 0.4 + 0.6 * nl; for (int k = 0; k < 3; k++) col[k] = c[k] * sh; }
     for (int k = 0; k < 3; k++) { double b = floor(col[k] * 255.0 + 0.5); rgba[4 * px + k] = (unsigned char)(b < 0 ? 0 : (b > 255 ? 255 : b)); }
     rgba[4 * px + 3] = 255;
     /* eye depth `best` -> z_ndc = (p22 * (-best) + p32) / best -> depth buffer value */

@@ -66,6 +66,7 @@ class EmulTorchWorld:
         mask = np.zeros((self.n_envs, hgt, w), np.float32)
         for e in range(self.n_envs):
             self._oracle.state[:] = self.e.state[e]
+            self._oracle.param[:] = self.e.param[e]
             out = self._oracle.render(cam, seg=seg)
             rgb[e], depth[e] = out[0], out[1]
             if seg:

@@ -239,3 +239,47 @@ def test_config5_randomised_parameters_cpu():
 @pytest.mark.gpu
 def test_config5_randomised_parameters_gpu():
     _config5(None)
+
+
+# ---------------------------------------------------------------- visual_randomizer ------------------------------------------
+def _visual_randomizer(factory):
+    """misc/visual_randomizer.py as per-environment colour randomisation: every reset gives the model's visual shapes
+    new colours, different per environment, the same as the oracle's - and the camera shows them."""
+    import yaml
+    node = yaml.load(open(os.path.join(ROOT, CONFIGS['basic_env'][0])), Loader=yaml.FullLoader)
+    node['red_marble']['new_look'] = {'addon': 'visual_randomizer'}
+    n = 3
+    env = DIYGym(Configuration.from_dict('basic_env', node), num_envs=n, device=0, world_factory=factory, seed=5)
+    w, sc, h = env.world, env.scene, env.scene.hdr
+    names = [b.name for b in sc.bodies]
+    red = names.index('red_marble')
+    vis = [v for v in range(sc['nv']) if sc.sec['VIS_I'][v][3] == red]
+    col = lambda: w.param[:, h['P_COLOR']:h['P_COLOR'] + 3 * sc['nv']].cpu().numpy().reshape(n, -1, 3)[:, vis]
+    c0 = col()
+    assert c0.min() >= 0 and c0.max() <= 1 and np.abs(c0[0] - c0[1]).max() > 1e-3            # per environment
+    others = [v for v in range(sc['nv']) if v not in vis]
+    allc = w.param[:, h['P_COLOR']:h['P_COLOR'] + 3 * sc['nv']].cpu().numpy().reshape(n, -1, 3)
+    assert np.allclose(allc[:, others], sc.sec['VIS_F'][others, 11:14][None])                   # the other models keep their colours
+    for i in range(n):
+        o = OracleWorld(sc, seed=5, env_id=i)
+        o.env_reset()
+        assert np.allclose(o.param, w.param[i].cpu().numpy(), rtol=1e-6, atol=1e-7)
+    env.reset()
+    assert np.abs(col() - c0).max() > 1e-3                                                      # a new look on every reset
+    # the camera sees the new colours: the marble's pixels carry its colour (times the shading factor)
+    rgb = env.observe()['basic_env']['camera']['rgb'][0].cpu().numpy()
+    o = OracleWorld(sc, seed=5, env_id=0)
+    o.state[:] = w.state[0].cpu().numpy()
+    o.param[:] = w.param[0].cpu().numpy()
+    o.refresh()
+    assert np.abs(rgb - o.render(0)[0]).max() < 2e-3
+    env.close()
+
+
+def test_visual_randomizer_cpu():
+    _visual_randomizer(_factory())
+
+
+@pytest.mark.gpu
+def test_visual_randomizer_gpu():
+    _visual_randomizer(None)

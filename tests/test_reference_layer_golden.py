@@ -16,12 +16,17 @@ from bench import CONFIGS, register_example_addons
 from diy_gym_b200 import Configuration, DIYGym
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
-NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze', 'ur_admittance', 'ur_gripper', 'ur_extras']
+NAMES = ['ur_high_5', 'from_the_readme', 'drone_pilot', 'basic_env', 'r2d2_maze', 'ur_admittance', 'ur_gripper', 'ur_extras', 'ur_robotiq']
 # ur_gripper: the welded child's spawn transient is solved with clamped, unconverged sweeps whose result depends on
 # rounding; the x86 build of the kernel code follows the fp64 rollout from reset, the GPU build is
 # compared after the transient in tests/test_gpu_parity.py instead
-GPU_NAMES = [n for n in NAMES if n != 'ur_gripper']
+GPU_NAMES = [n for n in NAMES if n not in ('ur_gripper', 'ur_robotiq')]
 TOL = dict(rtol=3e-3, atol=3e-4)
+# ur_robotiq: as in the reference (model.py:69-77) the gripper is spawned AT the parent frame, overlapping the wrist it is then welded
+# to 1 cm away; hull contacts fight the weld for the first steps and the light wrist joints are thrown about at up to 25 rad/s in a
+# way that depends on rounding (both arms: the oracle as well).  Compared there: nested keys and their order, terminals, and the three
+# heavy joints (shoulder pan / lift, elbow) to 2e-2 rad
+LOOSE = {'ur_robotiq': dict(rtol=0.0, atol=2e-2)}
 
 
 def strip_cameras(node):
@@ -82,7 +87,9 @@ def check(name, env):
     obs = env.reset()
     keys, vals = flat(obs)
     assert keys == list(g['obs_keys'])                       # same nested structure, same order
-    assert np.allclose(vals, g['obs_0'], **TOL)
+    tol = LOOSE.get(name, TOL)
+    pos_only = (lambda v: v[:3]) if name in LOOSE else (lambda v: v)
+    assert np.allclose(pos_only(vals), pos_only(g['obs_0']), **tol)
     for k in range(1, int(g['steps'][0]) + 1):
         action = build_action(list(g['act_keys']), g['act_%d' % k], env.action_space)
         dev = env.world.state.device
@@ -91,7 +98,7 @@ def check(name, env):
         obs, rew, term, _ = env.step(action)
         keys, vals = flat(obs)
         assert keys == list(g['obs_keys'])
-        assert np.allclose(vals, g['obs_%d' % k], **TOL), (name, k, np.abs(vals - g['obs_%d' % k]).max())
+        assert np.allclose(pos_only(vals), pos_only(g['obs_%d' % k]), **tol), (name, k, np.abs(vals - g['obs_%d' % k]).max())
         if isinstance(rew, dict):
             rk, rv = flat(rew)
             assert rk == list(g['rew_keys'])
@@ -109,14 +116,15 @@ def check(name, env):
     names = sorted(env.models)
     assert names == list(g['pose0_names'])
     mine = np.array([np.r_[env.models[n].base_pose()[0][0].cpu().numpy(), env.models[n].base_pose()[1][0].cpu().numpy()] for n in names])
-    assert np.allclose(mine, g['poseK'], **TOL)
+    if name not in LOOSE:
+        assert np.allclose(mine, g['poseK'], **TOL)
 
 
 @pytest.mark.parametrize('name', NAMES)
 def test_host_layer_matches_reference_layer_cpu(name):
     from tests.emul.world import factory
     g = np.load(os.path.join(ROOT, 'tests', 'golden', 'reflayer_' + name + '.npz'))
-    check(name, make_env(name, g, world_factory=factory(team=8 if name == 'ur_gripper' else 4)))
+    check(name, make_env(name, g, world_factory=factory(team=8 if name in ('ur_gripper', 'ur_robotiq') else 4)))
 
 
 @pytest.mark.gpu

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), '..'
 from diy_gym_b200.compiler.urdf import compile_urdf, save_model  # noqa: E402
 
 WANTED = ['ur5/ur5_robot.urdf', 'jaco/j2s7s300_standalone.urdf', 'hector_quadrotor/quadrotor.urdf', 'grass/plane.urdf',
-          'plain_plane/plane.urdf', 'wall/wall.urdf']
+          'plain_plane/plane.urdf', 'wall/wall.urdf', 'ur5/ur5_2f.urdf', 'ur5/ur5_3f.urdf', 'robotiq_2f/gripper.urdf', 'robotiq_3f/gripper.urdf']
 
 
 def main():

@@ -38,6 +38,7 @@ CONFIGS = {
     'ur_admittance': os.path.join(ROOT, 'examples', 'ur_admittance', 'ur_admittance.yaml'),
     'ur_gripper': os.path.join(ROOT, 'examples', 'ur_gripper', 'ur_gripper.yaml'),
     'ur_extras': os.path.join(ROOT, 'examples', 'ur_extras', 'ur_extras.yaml'),
+    'ur_robotiq': os.path.join(ROOT, 'examples', 'ur_gripper', 'ur_robotiq.yaml'),
 }
 
 
