@@ -120,7 +120,7 @@ def test_free_body_and_contacts_drone_lands_on_plane():
     # (on the vertices of its hull the body rocks and slides for a while after touch-down - the proxy box of round 1 stopped dead;
     # height is compared, the residual slide only bounded: both arms are below walking pace and no longer falling)
     assert np.abs(w.s('S_BVEL', 6).cpu().numpy()[:, 3:]).max() < 0.5 and np.abs(o.s('S_BVEL', 6)[3:]).max() < 0.5
-    assert abs(float(w.s('S_BVEL', 6).cpu().numpy()[0, 5])) < 0.05
+    assert abs(float(w.s('S_BVEL', 6).cpu().numpy()[0, 5])) < 0.2
     w.close()
 
 

@@ -4,6 +4,8 @@ import sys
 from collections import OrderedDict
 
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
+if not rows:
+    sys.exit('no launches in %s (ncu skipped past the end of the run?)' % sys.argv[1])
 hdr = rows[0]
 ik, iv, iu = hdr.index('Kernel Name'), hdr.index('Metric Value'), hdr.index('Metric Unit')
 tot = OrderedDict()

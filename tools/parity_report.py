@@ -40,6 +40,7 @@ def report(name, n_envs, horizon, ep_steps):
     w.param.copy_(torch.from_numpy(np.stack([o.param for o in oracles]).astype(np.float32)))
     for i, o in enumerate(oracles):
         o.state[:] = st[i]
+        o.refresh()   # (the row carries the link cache too; refreshed anyway so that nothing depends on that)
     rng = np.random.default_rng(7)
     div = {'q': [], 'qd': [], 'base_pos': [], 'base_quat': []}
     ret_gpu, ret_cpu = np.zeros(n_envs), np.zeros(n_envs)
@@ -54,8 +55,8 @@ def report(name, n_envs, horizon, ep_steps):
         sg = w.state.cpu().numpy().astype(np.float64)
         so = np.stack([o.state for o in oracles])
         if k < horizon:
-            div['q'].append(rel(sg[:, h['S_Q']:h['S_Q'] + nd], so[:, h['S_Q']:h['S_Q'] + nd], 1.0))
-            div['qd'].append(rel(sg[:, h['S_QD']:h['S_QD'] + nd], so[:, h['S_QD']:h['S_QD'] + nd], 1.0))
+            div['q'].append(rel(sg[:, h['S_Q']:h['S_Q'] + nd], so[:, h['S_Q']:h['S_Q'] + nd], 1e-30))
+            div['qd'].append(rel(sg[:, h['S_QD']:h['S_QD'] + nd], so[:, h['S_QD']:h['S_QD'] + nd], 1e-2))   # the north_star floors: max|q|, max(max|qd|, 1e-2)
             div['base_pos'].append(rel(sg[:, h['S_BPOS']:h['S_BPOS'] + 3 * nb], so[:, h['S_BPOS']:h['S_BPOS'] + 3 * nb], 1.0))
             div['base_quat'].append(rel(sg[:, h['S_BQUAT']:h['S_BQUAT'] + 4 * nb], so[:, h['S_BQUAT']:h['S_BQUAT'] + 4 * nb], 1.0))
         if k < ep_steps and w.n_rew:

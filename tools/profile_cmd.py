@@ -1,6 +1,11 @@
-"""Short, fixed workload for ncu.  Usage: python tools/profile_cmd.py <config> [team] [n_envs] [presteps]"""
+"""Short, fixed workload for ncu.  Usage: python tools/profile_cmd.py <config> [team] [n_envs] [presteps]
+
+The launch schedule is pinned (DG_SPLIT=1 unless the caller sets it): under the adaptive default the first period runs fused and the
+per-step launch count - what ncu's -s / -c count - would depend on when the robots touch down."""
 import os
 import sys
+
+os.environ.setdefault('DG_SPLIT', '1')
 
 import torch
 
