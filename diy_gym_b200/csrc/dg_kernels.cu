@@ -304,6 +304,7 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_ZMIN 34
 #define VS_RECT 35
 #define VS_BODY 39
+template <int NCW>
 __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
   // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
@@ -321,8 +322,6 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
   const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
   const int width = ci[1], height = ci[2];
   float* key = vs + VS_W * sc.nv;
-  unsigned* cand = reinterpret_cast<unsigned*>(key + ((sc.nv + 3) & ~3));
-  const int ncw = (sc.nv + 31) / 32;
   Env C; C.sc = &sc; C.st = const_cast<float*>(state) + (size_t)e * sc.S; C.ws = nullptr; C.wg = nullptr; C.pr = nullptr; C.dbg = nullptr; C.dropped = nullptr; C.rs_used = nullptr; C.no_hot = 0;
   C.link_i = sc.link_i; C.link_f = sc.link_f; C.link_x = sc.link_x;
   const float fov = cf[7], nearp = cf[8], farp = cf[9];
@@ -413,23 +412,37 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
   const int mtx = (width + MT_W - 1) / MT_W, mty = (height + MT_H - 1) / MT_H, nmt = mtx * mty;
   const bool vec_ok = (width % 4) == 0;   // image rows and patch offsets keep 16-byte alignment
   float* w_rgb = t_rgb + 96 * warp; float* w_dep = t_dep + 32 * warp; float* w_seg = t_seg + 32 * warp;
-  const int ncw2 = ncw < 4 ? ncw : 4;     // candidate words kept in registers (128 shapes; beyond that: see below)
-  for (int mt = grp * nwarp + warp; mt < nmt; mt += groups * nwarp) {
-    const int px0 = (mt % mtx) * MT_W, py0 = (mt / mtx) * MT_H;
-    unsigned cw[4] = {0u, 0u, 0u, 0u};
+  // NCW candidate words live in registers (32 NCW shapes; beyond 128: see below).  Lane l owns shapes l, 32 + l, ...: their screen
+  // rectangles stay in its registers for the whole image, so the per-patch overlap test reads no memory.
+  float rx0[NCW], rx1[NCW], ry0[NCW], ry1[NCW];
 #pragma unroll
-    for (int wd = 0; wd < 4; wd++) if (wd < ncw2) {
-      const int s = 32 * wd + lane; bool hit = false;
-      if (s < sc.nv) {
-        const float* o = vs + VS_W * s;
-        hit = o[VS_RECT] <= (float)(px0 + MT_W - 1) && o[VS_RECT + 1] >= (float)px0 && o[VS_RECT + 2] <= (float)(py0 + MT_H - 1) && o[VS_RECT + 3] >= (float)py0;
-      }
-      cw[wd] = __ballot_sync(0xffffffffu, hit);
+  for (int wd = 0; wd < NCW; wd++) {
+    const int s = 32 * wd + lane; const bool in = s < sc.nv; const float* o = vs + VS_W * (in ? s : 0);
+    rx0[wd] = in ? o[VS_RECT] : 1e9f; rx1[wd] = in ? o[VS_RECT + 1] : -1e9f; ry0[wd] = in ? o[VS_RECT + 2] : 1e9f; ry1[wd] = in ? o[VS_RECT + 3] : -1e9f;
+  }
+  // per-lane constants of the ray direction and of the staged stores
+  const int li = lane % MT_W, lj = lane / MT_W;
+  const float kx = 2.0f * th * aspect / (float)width, ky = 2.0f * th / (float)height, cx0 = th * aspect, cy0 = th;
+  const bool col_lane = lane < 24;
+  const int srow = col_lane ? lane / 6 : (lane - 24) / 2, sc4 = col_lane ? lane % 6 : (lane - 24) % 2;
+  const unsigned off_rgb = (unsigned)(srow * width * 3 + 4 * sc4), off_dep = (unsigned)(srow * width + 4 * sc4);
+  const float* src_rgb = w_rgb + 24 * srow + 4 * sc4; const float* src_dep = w_dep + 8 * srow + 4 * sc4; const float* src_seg = w_seg + 8 * srow + 4 * sc4;
+  // patches in row-major order, mt = grp nwarp + warp, then + groups nwarp: column / row kept incrementally (no division per patch)
+  const int stride = groups * nwarp, dcol = stride % mtx, drow = stride / mtx;
+  int mt = grp * nwarp + warp, pcol = mt % mtx, prow = mt / mtx;
+  for (; mt < nmt; mt += stride, pcol += dcol, prow += drow) {
+    if (pcol >= mtx) { pcol -= mtx; prow++; }
+    const int px0 = pcol * MT_W, py0 = prow * MT_H;
+    unsigned cw[NCW];
+    {
+      const float fx0 = (float)px0, fx1 = (float)(px0 + MT_W - 1), fy0 = (float)py0, fy1 = (float)(py0 + MT_H - 1);
+#pragma unroll
+      for (int wd = 0; wd < NCW; wd++) cw[wd] = __ballot_sync(0xffffffffu, rx0[wd] <= fx1 && rx1[wd] >= fx0 && ry0[wd] <= fy1 && ry1[wd] >= fy0);
     }
-    const int li = lane % MT_W, lj = lane / MT_W, i = px0 + li, j = py0 + lj;
+    const int i = px0 + li, j = py0 + lj;
     float r = 1.0f, g = 1.0f, bl = 1.0f, dz = -farp, sid = -1.0f;
     if (i < width && j < height) {
-      const float dc[3] = {((i + 0.5f) / width * 2 - 1) * th * aspect, (1 - (j + 0.5f) / height * 2) * th, -1.0f};
+      const float dc[3] = {fmaf((float)i + 0.5f, kx, -cx0), fmaf((float)j + 0.5f, -ky, cy0), -1.0f};
       const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
       float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
       bool done = false;
@@ -444,11 +457,11 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
         if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
       };
 #pragma unroll
-      for (int wd = 0; wd < 4; wd++) {
-        unsigned bits = (wd < ncw2 && !done) ? cw[wd] : 0u;
+      for (int wd = 0; wd < NCW; wd++) {
+        unsigned bits = cw[wd];
         while (bits && !done) { const int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1; try_shape(s); }
       }
-      for (int s = 128; s < sc.nv && !done; s++) {              // scenes with more than 128 visual shapes: the rest one by one
+      if (NCW == 4) for (int s = 128; s < sc.nv && !done; s++) {  // scenes with more than 128 visual shapes: the rest one by one
         const float* o = vs + VS_W * s;
         if (o[VS_RECT] <= (float)i && o[VS_RECT + 1] >= (float)i && o[VS_RECT + 2] <= (float)j && o[VS_RECT + 3] >= (float)j) try_shape(s);
       }
@@ -464,14 +477,12 @@ __global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant
       w_rgb[3 * lane] = r; w_rgb[3 * lane + 1] = g; w_rgb[3 * lane + 2] = bl; w_dep[lane] = dz; w_seg[lane] = sid;
       __syncwarp();
       // 6 float4 of colour and 2 of depth per patch row: lanes 0..23 colour, 24..31 depth (and mask)
-      if (lane < 24) {
-        const int row = lane / 6, c = lane % 6;
-        if (row < ht) *reinterpret_cast<float4*>(rgb_e + ((size_t)(py0 + row) * width + px0) * 3 + 4 * c) = *reinterpret_cast<const float4*>(w_rgb + 24 * row + 4 * c);
-      } else {
-        const int row = (lane - 24) / 2, c = (lane - 24) % 2;
-        if (row < ht) {
-          *reinterpret_cast<float4*>(dep_e + (size_t)(py0 + row) * width + px0 + 4 * c) = *reinterpret_cast<const float4*>(w_dep + 8 * row + 4 * c);
-          if (seg_e) *reinterpret_cast<float4*>(seg_e + (size_t)(py0 + row) * width + px0 + 4 * c) = *reinterpret_cast<const float4*>(w_seg + 8 * row + 4 * c);
+      const unsigned pb = (unsigned)(py0 * width + px0);
+      if (srow < ht) {
+        if (col_lane) *reinterpret_cast<float4*>(rgb_e + 3u * pb + off_rgb) = *reinterpret_cast<const float4*>(src_rgb);
+        else {
+          *reinterpret_cast<float4*>(dep_e + pb + off_dep) = *reinterpret_cast<const float4*>(src_dep);
+          if (seg_e) *reinterpret_cast<float4*>(seg_e + pb + off_dep) = *reinterpret_cast<const float4*>(src_seg);
         }
       }
     } else if (i < width && j < height) {
@@ -862,11 +873,13 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
   int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 3) / 4;   // patches of 8 x 4 pixels, one per warp at a time
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)((d.nv + 3) & ~3) + (size_t)(d.nv + 31) / 32 + 8) * sizeof(float);
-  if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(dg_render_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
+  const int ncw = (d.nv + 31) / 32;   // candidate words per patch the kernel keeps in registers: 1, 2 or 4 (then a per-shape tail)
+  auto kern = ncw <= 1 ? dg_render_kernel<1> : ncw == 2 ? dg_render_kernel<2> : dg_render_kernel<4>;
+  if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
   int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
   w->launches++;
-  dg_render_kernel<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
+  kern<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
   CK(w, cudaGetLastError());
   return DG_OK;
 }

@@ -36,18 +36,18 @@ PY
   ncu_step)
     cfg=$1
     # one --set full capture of a stage launch of the step kernel after pre-roll (3 stage launches per step under the split schedule;
-    # SKIP picks which: 181 = [post + pre] of step 60)
-    ncu --set full --clock-control none --import-source on -k regex:dg_step_kernel -s ${SKIP:-181} -c 1 -o $OUT/ncu_full_step_${cfg} -f python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 80 > $OUT/ncu_full_step_${cfg}.log 2>&1
+    # SKIP picks which: 901 = [post + pre] of step 300, the robots are on the ground by then)
+    ncu --set full --clock-control none --import-source on -k regex:dg_step_kernel -s ${SKIP:-901} -c 1 -o $OUT/ncu_full_step_${cfg} -f python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 320 > $OUT/ncu_full_step_${cfg}.log 2>&1
     ncu -i $OUT/ncu_full_step_${cfg}.ncu-rep --page details > $OUT/ncu_details_step_${cfg}.txt 2>&1
     grep -E "Duration|Registers Per|Achieved Occ|Executed Ipc|L1/TEX Hit|Active Warps Per|Avg. Active Threads" $OUT/ncu_details_step_${cfg}.txt
     ;;  # by source function: python tools/ncu_by_func.py <rep> diy_gym_b200/libdiygym_b200.so dg_step_kernelILi8 (run where the .so was built)
   ncu_solve)
     cfg=$1
-    # launch list of 10 steps after 60 steps of pre-roll (7 launches per step under the split schedule + the action fill)
-    ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-480} -c 80 --csv --log-file $OUT/ncu_launches_${cfg}.csv python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 80 > $OUT/ncu_launches_${cfg}.log 2>&1
-    python tools/ncu_launch_summary.py $OUT/ncu_launches_${cfg}.csv > $OUT/ncu_launches_${cfg}_summary.txt 2>&1; cat $OUT/ncu_launches_${cfg}_summary.txt
+    # launch list of 10 steps after 300 steps of pre-roll (7 kernel launches per step under the split schedule: 3 stage + 4 sweep)
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s ${SKIP:-2100} -c 70 --csv --log-file $OUT/ncu_launches_${cfg}.csv python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 320 > $OUT/ncu_launches_${cfg}.log 2>&1
+    python tools/ncu_launch_summary.py $OUT/ncu_launches_${cfg}.csv 10 > $OUT/ncu_launches_${cfg}_summary.txt 2>&1; cat $OUT/ncu_launches_${cfg}_summary.txt
     # the sweep kernel is launched twice per sub-step: rows-per-lane K = 2 first (auxiliary stream), then K = 1
-    ncu --set full --clock-control none --import-source on -k regex:dg_solve_kernel -s 240 -c 2 -o $OUT/ncu_full_solve_${cfg} -f python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 80 > $OUT/ncu_full_solve_${cfg}.log 2>&1
+    ncu --set full --clock-control none --import-source on -k regex:dg_solve_kernel -s 1200 -c 2 -o $OUT/ncu_full_solve_${cfg} -f python tools/profile_cmd.py $cfg 0 ${ENVS:-4096} 320 > $OUT/ncu_full_solve_${cfg}.log 2>&1
     ncu -i $OUT/ncu_full_solve_${cfg}.ncu-rep --page details > $OUT/ncu_details_solve_${cfg}.txt 2>&1 ;;
   ncu_render)
     ncu --set full --clock-control none --import-source on -k regex:dg_render_kernel -s 2 -c 1 -o $OUT/ncu_full_render -f python tools/render_probe.py from_the_readme ${ENVS:-4096} > $OUT/ncu_full_render.log 2>&1
