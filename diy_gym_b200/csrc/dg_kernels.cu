@@ -304,8 +304,8 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_ZMIN 34
 #define VS_RECT 35
 #define VS_BODY 39
-template <int NCW>
-__global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
+template <int NCW, int MINB>
+__global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
   // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
   // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 4 pixel patches:
@@ -874,7 +874,11 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 3) / 4;   // patches of 8 x 4 pixels, one per warp at a time
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)((d.nv + 3) & ~3) + (size_t)(d.nv + 31) / 32 + 8) * sizeof(float);
   const int ncw = (d.nv + 31) / 32;   // candidate words per patch the kernel keeps in registers: 1, 2 or 4 (then a per-shape tail)
-  auto kern = ncw <= 1 ? dg_render_kernel<1> : ncw == 2 ? dg_render_kernel<2> : dg_render_kernel<4>;
+  // resident blocks per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers, the per-block set-up spills a little);
+  // DG_RENDER_MINB selects, for A/B measurements
+  static const int minb = [] { const char* v = getenv("DG_RENDER_MINB"); return v && atoi(v) == 4 ? 4 : 3; }();
+  auto kern = minb == 4 ? (ncw <= 1 ? dg_render_kernel<1, 4> : ncw == 2 ? dg_render_kernel<2, 4> : dg_render_kernel<4, 4>)
+                        : (ncw <= 1 ? dg_render_kernel<1, 3> : ncw == 2 ? dg_render_kernel<2, 3> : dg_render_kernel<4, 3>);
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
   int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
