@@ -207,27 +207,44 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
       v[0] = fmaf(g_[K * (j) + k0_][0], b0_, v[0]); v[1] = fmaf(g_[K * (j) + k0_][1], b0_, v[1]);       \
       v[0] = fmaf(g_[K * (j) + k1_][0], b1_, v[0]); v[1] = fmaf(g_[K * (j) + k1_][1], b1_, v[1]);       \
     }
+    // The sweeps enter the unrolled update sequence through a jump table (switch on a block-uniform index) instead of testing every
+    // position: descending runs fall through to position 0 with no test at all, ascending runs test their end once per pair.
+    // ONE ascending sequence serves the three sections (the section loop is kept rolled: a third of the code, see no_inst stalls).
+#define DG_ASC_(j) case (j): DG_STEP2((j), true) if ((j) + 1 >= e_) break;
+#define DG_DSC_(j) case (j) + 1: DG_STEP2((j), false)
+#define DG_ASC16_ DG_ASC_(0) DG_ASC_(1) DG_ASC_(2) DG_ASC_(3) DG_ASC_(4) DG_ASC_(5) DG_ASC_(6) DG_ASC_(7) DG_ASC_(8) DG_ASC_(9) DG_ASC_(10) DG_ASC_(11) DG_ASC_(12) DG_ASC_(13) DG_ASC_(14) DG_ASC_(15)
+#define DG_ASC32_ DG_ASC16_ DG_ASC_(16) DG_ASC_(17) DG_ASC_(18) DG_ASC_(19) DG_ASC_(20) DG_ASC_(21) DG_ASC_(22) DG_ASC_(23) DG_ASC_(24) DG_ASC_(25) DG_ASC_(26) DG_ASC_(27) DG_ASC_(28) DG_ASC_(29) DG_ASC_(30) DG_ASC_(31)
+#define DG_DSC16_ DG_DSC_(15) DG_DSC_(14) DG_DSC_(13) DG_DSC_(12) DG_DSC_(11) DG_DSC_(10) DG_DSC_(9) DG_DSC_(8) DG_DSC_(7) DG_DSC_(6) DG_DSC_(5) DG_DSC_(4) DG_DSC_(3) DG_DSC_(2) DG_DSC_(1) DG_DSC_(0)
+#define DG_DSC32_ DG_DSC_(31) DG_DSC_(30) DG_DSC_(29) DG_DSC_(28) DG_DSC_(27) DG_DSC_(26) DG_DSC_(25) DG_DSC_(24) DG_DSC_(23) DG_DSC_(22) DG_DSC_(21) DG_DSC_(20) DG_DSC_(19) DG_DSC_(18) DG_DSC_(17) DG_DSC_(16) DG_DSC16_
+    const int n1 = (P1 + K - 1) / K, n2 = (P2 + K - 1) / K, n3 = (Rp + K - 1) / K;   // pair index where a section ends
     for (int it = 0; it < sc.iters; it++) {
-      if (it & 1) {
-#pragma unroll
-        for (int j = 0; j < W; j++) { if (K * j >= P1) break; DG_STEP2(j, true) }
-      } else {
-#pragma unroll
-        for (int j = W - 1; j >= 0; j--) { if (K * j < P1) DG_STEP2(j, false) }
+      const bool fwd1 = (it & 1) != 0;
+      if (!fwd1) {
+        if constexpr (W == 32) { switch (n1) { DG_DSC32_ default: break; } } else { switch (n1) { DG_DSC16_ default: break; } }
       }
+#pragma unroll 1
+      for (int sec = fwd1 ? 0 : 1; sec < 3; sec++) {
+        const int s_ = sec == 0 ? 0 : (sec == 1 ? n1 : n2), e_ = sec == 0 ? n1 : (sec == 1 ? n2 : n3);
+        if (sec == 2) {
+          // friction bounds from the normal impulses this sweep left (the normal of contact c sits at warp position nrm0 + c)
 #pragma unroll
-      for (int j = 0; j < W; j++) { if (K * j >= P2) break; if (K * j >= P1) DG_STEP2(j, true) }
-      // friction bounds from the normal impulses this sweep left (the normal of contact c sits at warp position nrm0 + c)
-#pragma unroll
-      for (int k = 0; k < K; k++) {
-        const int pn = par[k] >= 0 ? nrm0 + par[k] : 0;
-        const float v0 = __shfl_sync(FULL, ap[0], pn / K, W), v1 = __shfl_sync(FULL, ap[1], pn / K, W);
-        const float vn = (pn % K) ? v1 : v0;
-        if (par[k] >= 0) { hi[k] = mu[k] * vn; lo[k] = -hi[k]; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; }
+          for (int k = 0; k < K; k++) {
+            const int pn = par[k] >= 0 ? nrm0 + par[k] : 0;
+            const float v0 = __shfl_sync(FULL, ap[0], pn / K, W), v1 = __shfl_sync(FULL, ap[1], pn / K, W);
+            const float vn = (pn % K) ? v1 : v0;
+            if (par[k] >= 0) { hi[k] = mu[k] * vn; lo[k] = -hi[k]; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; }
+          }
+        }
+        if (s_ >= e_) continue;
+        if constexpr (W == 32) { switch (s_) { DG_ASC32_ default: break; } } else { switch (s_) { DG_ASC16_ default: break; } }
       }
-#pragma unroll
-      for (int j = 0; j < W; j++) { if (K * j >= Rp) break; if (K * j >= P2) DG_STEP2(j, true) }
     }
+#undef DG_ASC_
+#undef DG_DSC_
+#undef DG_ASC16_
+#undef DG_ASC32_
+#undef DG_DSC16_
+#undef DG_DSC32_
 #undef DG_STEP2
     if (writer) {
 #pragma unroll
