@@ -182,6 +182,10 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
       if (q >= 0) { const F4 r0 = ld4(REC + RR_W * q), r1 = ld4(REC + RR_W * q + 4); v[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
       lop[k] = lo[k]; hip[k] = hi[k];   // ap = 0, y = 0 at the start
     }
+    // The owner only CAPTURES its two changes in the update sequence (chg); impulses and shifted bounds are brought up to date once
+    // per section (DG_SETTLE) - a row is updated once per section, and nobody else reads them in between.
+    float chg[K] = {0.f, 0.f};
+#define DG_SETTLE { _Pragma("unroll") for (int k = 0; k < K; k++) { ap[k] += chg[k]; chg[k] = 0.f; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; } }
     float g_[RMAX][K];   // g_[p][k] = -dinv[k] A[row at warp position p][this lane's slot k]
 #pragma unroll
     for (int p = 0; p < RMAX; p++) {
@@ -200,10 +204,7 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
       const float vf_ = fmaf(g_[K * (j) + k0_][k1_], d0_, v[k1_]);                                   \
       const float d1_ = fminf(fmaxf(vf_, lop[k1_]), hip[k1_]);                                     \
       const float b1_ = __shfl_sync(FULL, d1_, (j), W);                                            \
-      if (l == (j)) {                                                                              \
-        ap[k0_] += d0_; lop[k0_] = lo[k0_] - ap[k0_]; hip[k0_] = hi[k0_] - ap[k0_];                \
-        ap[k1_] += d1_; lop[k1_] = lo[k1_] - ap[k1_]; hip[k1_] = hi[k1_] - ap[k1_];                \
-      }                                                                                            \
+      chg[k0_] = (l == (j)) ? d0_ : chg[k0_]; chg[k1_] = (l == (j)) ? d1_ : chg[k1_];              \
       v[0] = fmaf(g_[K * (j) + k0_][0], b0_, v[0]); v[1] = fmaf(g_[K * (j) + k0_][1], b0_, v[1]);       \
       v[0] = fmaf(g_[K * (j) + k1_][0], b1_, v[0]); v[1] = fmaf(g_[K * (j) + k1_][1], b1_, v[1]);       \
     }
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
       const bool fwd1 = (it & 1) != 0;
       if (!fwd1) {
         if constexpr (W == 32) { switch (n1) { DG_DSC32_ default: break; } } else { switch (n1) { DG_DSC16_ default: break; } }
+        DG_SETTLE
       }
 #pragma unroll 1
       for (int sec = fwd1 ? 0 : 1; sec < 3; sec++) {
@@ -237,8 +239,10 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
         }
         if (s_ >= e_) continue;
         if constexpr (W == 32) { switch (s_) { DG_ASC32_ default: break; } } else { switch (s_) { DG_ASC16_ default: break; } }
+        DG_SETTLE
       }
     }
+#undef DG_SETTLE
 #undef DG_ASC_
 #undef DG_DSC_
 #undef DG_ASC16_
