@@ -325,19 +325,19 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_ZMIN 34
 #define VS_RECT 35
 #define VS_BODY 39
-template <int NCW, int MINB>
+template <int NCW, int MINB, int NH>
 __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
   // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
-  // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 4 pixel patches:
+  // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 8 pixel patches (two rays per lane):
   // the shapes whose rectangle overlaps the patch (a bit per shape, in that order), per pixel the ray against those shapes,
   // nearest first, until the next shape's nearest depth is behind the hit already found; the patch is staged in shared memory
   // and written as whole 128-bit pieces of image rows.
   extern __shared__ __align__(16) float vs[];       // [nv][VS_W], then keys [nv], then the candidate bit set
   __shared__ float camRp[12];
-  __shared__ __align__(16) float t_rgb[8 * 96];   // per warp: a patch of 32 pixels
-  __shared__ __align__(16) float t_dep[8 * 32];
-  __shared__ __align__(16) float t_seg[8 * 32];
+  __shared__ __align__(16) float t_rgb[8 * 192];   // per warp: a patch of 64 pixels
+  __shared__ __align__(16) float t_dep[8 * 64];
+  __shared__ __align__(16) float t_seg[8 * 64];
   (void)tiles_x; (void)tiles_y;
   const int e = blockIdx.x / groups, grp = blockIdx.x % groups;
   const int* ci = sc.cam_i + DG_CAM_I_W * cam; const float* cf = sc.cam_f + DG_CAM_F_W * cam;
@@ -425,14 +425,14 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
   const int npx = width * height;
   float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx; float* seg_e = seg ? seg + (size_t)e * npx : nullptr;
-  // Every WARP renders patches of MT_W x MT_H = 32 pixels on its own (no block barrier in this loop): the lanes test the shapes'
+  // Every WARP renders patches of MT_W x MT_H = 64 pixels on its own (no block barrier in this loop): the lanes test the shapes'
   // screen rectangles against the patch (ballots -> candidate bits in registers, front to back), every lane casts the ray of its
   // pixel, and the patch goes out as 128-bit pieces of image rows through the warp's slice of the staging buffers.
-  constexpr int MT_W = 8, MT_H = 4;
+  constexpr int MT_W = 8, MT_H = 4 * NH;   // NH = 2: 8 x 8 patches, two rays per lane; NH = 1: 8 x 4, one ray (small images)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int mtx = (width + MT_W - 1) / MT_W, mty = (height + MT_H - 1) / MT_H, nmt = mtx * mty;
   const bool vec_ok = (width % 4) == 0;   // image rows and patch offsets keep 16-byte alignment
-  float* w_rgb = t_rgb + 96 * warp; float* w_dep = t_dep + 32 * warp; float* w_seg = t_seg + 32 * warp;
+  float* w_rgb = t_rgb + 192 * warp; float* w_dep = t_dep + 64 * warp; float* w_seg = t_seg + 64 * warp;
   // NCW candidate words live in registers (32 NCW shapes; beyond 128: see below).  Lane l owns shapes l, 32 + l, ...: their screen
   // rectangles stay in its registers for the whole image, so the per-patch overlap test reads no memory.
   float rx0[NCW], rx1[NCW], ry0[NCW], ry1[NCW];
@@ -441,13 +441,24 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
     const int s = 32 * wd + lane; const bool in = s < sc.nv; const float* o = vs + VS_W * (in ? s : 0);
     rx0[wd] = in ? o[VS_RECT] : 1e9f; rx1[wd] = in ? o[VS_RECT + 1] : -1e9f; ry0[wd] = in ? o[VS_RECT + 2] : 1e9f; ry1[wd] = in ? o[VS_RECT + 3] : -1e9f;
   }
-  // per-lane constants of the ray direction and of the staged stores
+  // per-lane constants of the ray direction and of the staged stores.  A lane casts TWO rays per patch: pixels (li, lj) and
+  // (li, lj + 4) of the 8 x 8 patch, so that the candidate ballots, the patch bookkeeping and the store addressing are paid once per
+  // 64 pixels.  The patch leaves as 64 128-bit pieces (48 of colour, 16 of depth): two per lane.
   const int li = lane % MT_W, lj = lane / MT_W;
   const float kx = 2.0f * th * aspect / (float)width, ky = 2.0f * th / (float)height, cx0 = th * aspect, cy0 = th;
-  const bool col_lane = lane < 24;
-  const int srow = col_lane ? lane / 6 : (lane - 24) / 2, sc4 = col_lane ? lane % 6 : (lane - 24) % 2;
-  const unsigned off_rgb = (unsigned)(srow * width * 3 + 4 * sc4), off_dep = (unsigned)(srow * width + 4 * sc4);
-  const float* src_rgb = w_rgb + 24 * srow + 4 * sc4; const float* src_dep = w_dep + 8 * srow + 4 * sc4; const float* src_seg = w_seg + 8 * srow + 4 * sc4;
+  // piece t of lane: index lane + 32 t.  NH = 2: < 48 colour (row idx / 6, float4 idx % 6), else depth (row (idx - 48) / 2, float4
+  // (idx - 48) % 2), mask pieces on lanes 0..15.  NH = 1: one piece per lane, 0..23 colour, 24..31 depth and mask.
+  const int row0 = NH == 2 ? lane / 6 : (lane < 24 ? lane / 6 : (lane - 24) / 2), c0 = NH == 2 ? lane % 6 : (lane < 24 ? lane % 6 : (lane - 24) % 2);
+  const bool col0 = NH == 2 || lane < 24;
+  const bool col1 = lane < 16;                                    // t = 1 (NH = 2 only): colour for lanes 0..15, depth for 16..31
+  const int row1 = col1 ? (lane + 32) / 6 : (lane - 16) / 2, c1 = col1 ? (lane + 32) % 6 : (lane - 16) % 2;
+  const int rows = NH == 2 ? lane / 2 : row0, cs = NH == 2 ? lane % 2 : c0;   // mask pieces
+  const bool seg_lane = NH == 2 ? lane < 16 : lane >= 24;
+  const unsigned off0 = col0 ? (unsigned)(row0 * width * 3 + 4 * c0) : (unsigned)(row0 * width + 4 * c0),
+                 off1 = col1 ? (unsigned)(row1 * width * 3 + 4 * c1) : (unsigned)(row1 * width + 4 * c1), offs = (unsigned)(rows * width + 4 * cs);
+  const float* src0 = col0 ? w_rgb + 24 * row0 + 4 * c0 : w_dep + 8 * row0 + 4 * c0;
+  const float* src1 = col1 ? w_rgb + 24 * row1 + 4 * c1 : w_dep + 8 * row1 + 4 * c1;
+  const float* srcs = w_seg + 8 * rows + 4 * cs;
   // patches in row-major order, mt = grp nwarp + warp, then + groups nwarp: column / row kept incrementally (no division per patch)
   const int stride = groups * nwarp, dcol = stride % mtx, drow = stride / mtx;
   int mt = grp * nwarp + warp, pcol = mt % mtx, prow = mt / mtx;
@@ -460,56 +471,63 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
 #pragma unroll
       for (int wd = 0; wd < NCW; wd++) cw[wd] = __ballot_sync(0xffffffffu, rx0[wd] <= fx1 && rx1[wd] >= fx0 && ry0[wd] <= fy1 && ry1[wd] >= fy0);
     }
-    const int i = px0 + li, j = py0 + lj;
-    float r = 1.0f, g = 1.0f, bl = 1.0f, dz = -farp, sid = -1.0f;
-    if (i < width && j < height) {
-      const float dc[3] = {fmaf((float)i + 0.5f, kx, -cx0), fmaf((float)j + 0.5f, -ky, cy0), -1.0f};
-      const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
-      float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
-      bool done = false;
-      auto try_shape = [&](int s) {
-        const float* o = vs + VS_W * s;
-        // the ray parameter IS the eye-space depth (the camera-space direction has z = -1): nothing behind `best` can win
-        if (o[VS_ZMIN] >= best) { done = true; return; }
-        float dl[3]; m_vec(dl, o + 21, dc);
-        const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
-        if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) return;
-        float tt, nn[3];
-        if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
-      };
-#pragma unroll
-      for (int wd = 0; wd < NCW; wd++) {
-        unsigned bits = cw[wd];
-        while (bits && !done) { const int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1; try_shape(s); }
-      }
-      if (NCW == 4) for (int s = 128; s < sc.nv && !done; s++) {  // scenes with more than 128 visual shapes: the rest one by one
-        const float* o = vs + VS_W * s;
-        if (o[VS_RECT] <= (float)i && o[VS_RECT + 1] >= (float)i && o[VS_RECT + 2] <= (float)j && o[VS_RECT + 3] >= (float)j) try_shape(s);
-      }
-      if (hs >= 0) {
-        float hn[3]; m_vec(hn, vs + VS_W * hs, hnl);
-        const float* col = vs + VS_W * hs + 16; const float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
-        r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best; sid = vs[VS_W * hs + VS_BODY];
-      }
-    }
     const int wt = min(MT_W, width - px0), ht = min(MT_H, height - py0);
-    if (vec_ok && wt == MT_W) {
-      __syncwarp();
-      w_rgb[3 * lane] = r; w_rgb[3 * lane + 1] = g; w_rgb[3 * lane + 2] = bl; w_dep[lane] = dz; w_seg[lane] = sid;
-      __syncwarp();
-      // 6 float4 of colour and 2 of depth per patch row: lanes 0..23 colour, 24..31 depth (and mask)
-      const unsigned pb = (unsigned)(py0 * width + px0);
-      if (srow < ht) {
-        if (col_lane) *reinterpret_cast<float4*>(rgb_e + 3u * pb + off_rgb) = *reinterpret_cast<const float4*>(src_rgb);
-        else {
-          *reinterpret_cast<float4*>(dep_e + pb + off_dep) = *reinterpret_cast<const float4*>(src_dep);
-          if (seg_e) *reinterpret_cast<float4*>(seg_e + pb + off_dep) = *reinterpret_cast<const float4*>(src_seg);
+    const bool staged = vec_ok && wt == MT_W;
+    const int i = px0 + li;
+    if (staged) __syncwarp();                                      // the previous patch has left the staging buffers
+#pragma unroll 1
+    for (int half = 0; half < NH; half++) {
+      const int j = py0 + lj + 4 * half, slot = lane + 32 * half;
+      float r = 1.0f, g = 1.0f, bl = 1.0f, dz = -farp, sid = -1.0f;
+      if (i < width && j < height) {
+        const float dc[3] = {fmaf((float)i + 0.5f, kx, -cx0), fmaf((float)j + 0.5f, -ky, cy0), -1.0f};
+        const float dd = v_dot(dc, dc);                            // rotations keep the length of the direction
+        float best = farp; int hs = -1; float hnl[3] = {0, 0, 1};
+        bool done = false;
+        auto try_shape = [&](int s) {
+          const float* o = vs + VS_W * s;
+          // the ray parameter IS the eye-space depth (the camera-space direction has z = -1): nothing behind `best` can win
+          if (o[VS_ZMIN] >= best) { done = true; return; }
+          float dl[3]; m_vec(dl, o + 21, dc);
+          const float b = v_dot(o + 30, dl), c2 = o[33];          // per-ray bounding-sphere reject, in the shape frame
+          if (c2 > 0.f && (b > 0.f || b * b < c2 * dd)) return;
+          float tt, nn[3];
+          if (ray_shape(float_as_int(o[19]), o + 12, o + 30, dl, best, &tt, nn) && tt >= nearp) { best = tt; hs = s; v_cpy(hnl, nn); }
+        };
+#pragma unroll
+        for (int wd = 0; wd < NCW; wd++) {
+          unsigned bits = cw[wd];
+          while (bits && !done) { const int s = 32 * wd + __ffs(bits) - 1; bits &= bits - 1; try_shape(s); }
+        }
+        if (NCW == 4) for (int s = 128; s < sc.nv && !done; s++) {  // scenes with more than 128 visual shapes: the rest one by one
+          const float* o = vs + VS_W * s;
+          if (o[VS_RECT] <= (float)i && o[VS_RECT + 1] >= (float)i && o[VS_RECT + 2] <= (float)j && o[VS_RECT + 3] >= (float)j) try_shape(s);
+        }
+        if (hs >= 0) {
+          float hn[3]; m_vec(hn, vs + VS_W * hs, hnl);
+          const float* col = vs + VS_W * hs + 16; const float nl = fmaxf(v_dot(hn, light), 0.f), sh = 0.4f + 0.6f * nl;
+          r = col[0] * sh; g = col[1] * sh; bl = col[2] * sh; dz = -best; sid = vs[VS_W * hs + VS_BODY];
+        }
+        if (!staged) {
+          const size_t px = (size_t)j * width + i;
+          rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
+          if (seg_e) seg_e[px] = sid;
         }
       }
-    } else if (i < width && j < height) {
-      const size_t px = (size_t)j * width + i;
-      rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
-      if (seg_e) seg_e[px] = sid;
+      if (staged) { w_rgb[3 * slot] = r; w_rgb[3 * slot + 1] = g; w_rgb[3 * slot + 2] = bl; w_dep[slot] = dz; w_seg[slot] = sid; }
+    }
+    if (staged) {
+      __syncwarp();
+      const unsigned pb = (unsigned)(py0 * width + px0);
+      if (row0 < ht) {
+        if (col0) *reinterpret_cast<float4*>(rgb_e + 3u * pb + off0) = *reinterpret_cast<const float4*>(src0);
+        else *reinterpret_cast<float4*>(dep_e + pb + off0) = *reinterpret_cast<const float4*>(src0);
+      }
+      if (NH == 2 && row1 < ht) {
+        if (col1) *reinterpret_cast<float4*>(rgb_e + 3u * pb + off1) = *reinterpret_cast<const float4*>(src1);
+        else *reinterpret_cast<float4*>(dep_e + pb + off1) = *reinterpret_cast<const float4*>(src1);
+      }
+      if (seg_e && seg_lane && rows < ht) *reinterpret_cast<float4*>(seg_e + pb + offs) = *reinterpret_cast<const float4*>(srcs);
     }
   }
 }
@@ -892,14 +910,20 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   if (cam < 0 || cam >= d.ncam) { w->err = "dg_render: no such camera"; return DG_E_ARG; }
   DeviceGuard guard(w->device);
   const int* ci = w->hs.dev.cam_i + DG_CAM_I_W * cam;
-  int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 3) / 4;   // patches of 8 x 4 pixels, one per warp at a time
+  // patches of 8 x 8 pixels (two rays per lane), one per warp at a time; images too small to give every warp of a block a dozen of
+  // those take 8 x 4 patches (measured: 50 x 50 is 14 % slower with the large ones, 200 x 200 12 % faster)
+  const int nh = ((ci[1] + 7) / 8) * ((ci[2] + 7) / 8) >= 96 ? 2 : 1;
+  int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 4 * nh - 1) / (4 * nh);
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)((d.nv + 3) & ~3) + (size_t)(d.nv + 31) / 32 + 8) * sizeof(float);
   const int ncw = (d.nv + 31) / 32;   // candidate words per patch the kernel keeps in registers: 1, 2 or 4 (then a per-shape tail)
-  // resident blocks per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers, the per-block set-up spills a little);
-  // DG_RENDER_MINB selects, for A/B measurements
+  // resident blocks per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers, the per-block set-up spills a little;
+  // measured slower: 1.10 vs 1.03 ms); DG_RENDER_MINB selects, for A/B measurements
   static const int minb = [] { const char* v = getenv("DG_RENDER_MINB"); return v && atoi(v) == 4 ? 4 : 3; }();
-  auto kern = minb == 4 ? (ncw <= 1 ? dg_render_kernel<1, 4> : ncw == 2 ? dg_render_kernel<2, 4> : dg_render_kernel<4, 4>)
-                        : (ncw <= 1 ? dg_render_kernel<1, 3> : ncw == 2 ? dg_render_kernel<2, 3> : dg_render_kernel<4, 3>);
+  using RenderFn = void (*)(DevScene, const float*, const float*, int, float*, float*, float*, int, int, int);
+  static const RenderFn table[2][2][3] = {
+      {{dg_render_kernel<1, 3, 1>, dg_render_kernel<2, 3, 1>, dg_render_kernel<4, 3, 1>}, {dg_render_kernel<1, 3, 2>, dg_render_kernel<2, 3, 2>, dg_render_kernel<4, 3, 2>}},
+      {{dg_render_kernel<1, 4, 1>, dg_render_kernel<2, 4, 1>, dg_render_kernel<4, 4, 1>}, {dg_render_kernel<1, 4, 2>, dg_render_kernel<2, 4, 2>, dg_render_kernel<4, 4, 2>}}};
+  RenderFn kern = table[minb == 4][nh - 1][ncw <= 1 ? 0 : (ncw == 2 ? 1 : 2)];
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
   int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
