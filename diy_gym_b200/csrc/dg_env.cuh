@@ -2017,7 +2017,7 @@ DG_NOINLINE DG_FN void physics_pre(const Env& C, int nt, float h, DG_LANE_ARGS) 
     // environments with contacts: solved in row space (A is built here; swept below by the team, or - deferred - by a warp of the
     // sweep kernel); contact-free ones keep the register-resident per-body sweeps.  (WH_RS_R == 0 with contacts: dv-space sweeps,
     // solver == 0 / too many rows)
-    DG_PHASE(if (HDRV(WH_RS_R) > 0) phase_rs_build(C, ln, nt);
+    DG_PHASE(if (HDRV(WH_RS_R) > 0) { if (HDRV(WH_RS_DEFER) == 0) phase_rs_build(C, ln, nt); }   // (deferred: the sweep kernel builds its own columns of A)
              else if (HDRV(WH_COUPLED) == 0) { if (HDRV(WH_NCROW) > 0) phase_pgs_full(C, ln, nt); else phase_pgs_unit(C, ln, nt, 0, sc.iters); });
     if (sc.solver == 1 && nt > 1 && block_any(HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) == 0, nt)) {
 #if defined(__CUDA_ARCH__)

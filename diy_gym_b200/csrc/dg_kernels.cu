@@ -132,7 +132,7 @@ DG_DEFINE_STEP_X(DG_STEP_T)
 // branches stay uniform (no divergence bookkeeping around the shuffles).
 struct SolveArgs { const float* carry; float* gws; const int* list; const int* count; };
 template <int W>
-__global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
+__global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
   constexpr int K = 2, G = 32 / W, RMAX = W * K;
   constexpr unsigned FULL = 0xffffffffu;
   const int count = *a.count, first = (int)blockIdx.x * G;
@@ -160,7 +160,32 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 8) dg_solve_kernel(const __
     const int P1 = npass > 1 ? Lu.P1 : P1w, P2 = P1 + (npass > 1 ? Lu.P2 - Lu.P1 : N2w), Rp = P2 + (npass > 1 ? Lu.Rp - Lu.P2 : N3w);
     const bool live = first + mine < count;
     float* wg = a.gws + (size_t)es[G > 1 ? mine : 0] * sc.g_total;
-    float* REC = wg + sc.X_RSREC; const float* A = wg + sc.X_RSA; const int cap = sc.rs_cap;
+    float* REC = wg + sc.X_RSREC; float* A = wg + sc.X_RSA; const int cap = sc.rs_cap;
+    // A[p][s] = J_s . (M^-1 J^T)_p, built HERE by the environment's W lanes (the stage launch leaves the dense row vectors of
+    // phase_rs_setup in the cold workspace and skips phase_rs_build for deferred environments): lane per column s, only over the
+    // support of J_s, the same four partial sums as phase_rs_build.  Rolled loops: the update sequence below is what must stay in
+    // the instruction cache.
+    {
+      const int GV = sc.GV; const float* RSV = wg + sc.X_RSV;
+#pragma unroll 1
+      for (int s2 = l; s2 < L.Rp; s2 += W) {
+        const bool rs2 = live && rs_real(L, s2);
+        int c0 = 0, c1 = 0;
+        if (rs2) { const int sup = float_as_int(REC[RR_W * s2 + RR_APPLIED]); c0 = sup & 0xffff; c1 = (sup >> 16) & 0xffff; if (c1 > GV) c1 = GV; }
+        const float* Jd = RSV + (size_t)s2 * 2 * GV;
+#pragma unroll 1
+        for (int p = 0; p < L.Rp; p++) {
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+          if (rs2 && rs_real(L, p)) {
+            const float* Md = RSV + (size_t)p * 2 * GV + GV;
+#pragma unroll 2
+            for (int c = c0; c < c1; c += 4) { const F4 jv = ld4(Jd + c), mv = ld4(Md + c); a0 = fmaf(jv.x, mv.x, a0); a1 = fmaf(jv.y, mv.y, a1); a2 = fmaf(jv.z, mv.z, a2); a3 = fmaf(jv.w, mv.w, a3); }
+          }
+          if (live) A[p * cap + s2] = (a0 + a1) + (a2 + a3);
+        }
+      }
+      __syncwarp();
+    }
     // warp position g -> position q in the environment's own layout (-1: padding)
     auto own_pos = [&](int g) {
       int q;
