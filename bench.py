@@ -328,15 +328,17 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
     rng = np.random.default_rng(99 + rank)
     host_pool = [(lo_np + (hi_np - lo_np) * rng.random((n_envs, w.n_act), dtype=np.float32)) for _ in range(4)] if w.n_act else None
     cam_h = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in w.render(c.cam)) for c in cams]
+    cam_h8 = [tuple(torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in w.render(c.cam, u8=True)) for c in cams]   # colour as bytes (dg_render_u8)
     h2d = n_envs * w.n_act * 4
     d2h = n_envs * (w.n_obs * 4 + w.n_rew * 4 + w.n_term)
     dyn_body = next((b for b in sc.bodies if b.kind != 0), sc.bodies[0])
     o_pose = sc.hdr['S_BPOS'] + 3 * dyn_body.index
     if d2h == 0:
         d2h = n_envs * 3 * 4   # no sensor in this config: read back the robot's base position as the step's result
+    d2h_u8 = d2h + sum(int(t.numel() * t.element_size()) for pair in cam_h8 for t in pair)
     d2h += sum(int(t.numel() * t.element_size()) for pair in cam_h for t in pair)
 
-    def host_step(i):
+    def host_step(i, u8=False):
         if host_pool is not None:
             np.copyto(act_h, host_pool[i % 4])
         for a in user_addons:
@@ -344,8 +346,8 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
         w.step_host(act_h if w.n_act else None, obs_h if w.n_obs else None, rew_h if w.n_rew else None, term_h if w.n_term else None)
         if w.n_obs + w.n_rew + w.n_term == 0:
             extra_h[:, :3].copy_(w.state[:, o_pose:o_pose + 3])
-        for c, hs in zip(cams, cam_h):
-            for t_h, t_d in zip(hs, w.render(c.cam)):
+        for c, hs in zip(cams, cam_h8 if u8 else cam_h):
+            for t_h, t_d in zip(hs, w.render(c.cam, u8=u8)):
                 t_h.copy_(t_d, non_blocking=True)
         if cams:
             torch.cuda.synchronize(dev)
@@ -359,6 +361,16 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
         host_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    e2e_u8_s = 0.0
+    if cams:   # the same with the colour images as bytes (camera key `rgb_uint8`, dg_render_u8): what a host-side consumer would ask for
+        for i in range(2):
+            host_step(i, u8=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            host_step(i, u8=True)
+        barrier()
+        e2e_u8_s = time.perf_counter() - t0
 
     # ---- the same through the public Python API: DIYGym.step(action dict) -> (obs, reward, terminal) dicts, consumed ---------
     api_s, api_bytes = 0.0, (0, 0)
@@ -419,11 +431,11 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
         api_s = time.perf_counter() - t0
 
     # ---- max over ranks --------------------------------------------------------------------------------------------
-    stats = torch.tensor([ms_total, e2e_s, kernel_ms, api_s], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_total, e2e_s, kernel_ms, api_s, e2e_u8_s], dtype=torch.float64, device=dev)
     if world_size > 1:
         import torch.distributed as dist
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_total, e2e_s, kernel_ms, api_s = [float(x) for x in stats.tolist()]
+    ms_total, e2e_s, kernel_ms, api_s, e2e_u8_s = [float(x) for x in stats.tolist()]
     res = {'config_extra': dict(team=w.team, block_threads=w.block_threads, grid_blocks=w.grid_blocks, smem_bytes=w.smem_bytes, split_schedule=bool(getattr(w, 'split', False)),
                                 preroll_steps=ctx['preroll'], l2_policy='L2 flushed (256 MB buffer overwritten) before every timed step; per-step actions cycle through 8 pre-generated batches'),
            'split_schedule': bool(getattr(w, 'split', False))}
@@ -433,6 +445,8 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
     total_envs = n_envs * world_size
     res.update(value=total_envs * steps / (ms_total * 1e-3), ms_per_step=ms_total / steps, kernel_ms=kernel_ms, gpu_launches=int(launches), clocks=clocks,
                e2e={'value': total_envs * steps / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'api': 'dg_step_host (pinned host buffers)' + (' + dg_render, images D2H' if cams else '')})
+    if cams:
+        res['e2e']['rgb_uint8'] = {'value': total_envs * steps / e2e_u8_s, 'unit': UNIT, 'd2h_bytes_per_step': d2h_u8, 'api': 'dg_step_host + dg_render_u8 (colour as bytes, depth fp32), images D2H'}
     if api_leg:
         res['e2e_api'] = {'value': total_envs * steps / api_s, 'unit': UNIT, 'h2d_bytes_per_step': int(api_bytes[0]), 'd2h_bytes_per_step': int(api_bytes[1]),
                           'api': 'DIYGym.step(action dict): pinned host actions H2D, every leaf of the returned obs / reward / terminal trees D2H'}

@@ -215,7 +215,11 @@ class Camera(Addon):
         self.rpy = config.get('rpy', [0., 0., 0.])
         self.use_depth = bool(config.get('use_depth', True))
         self.use_seg_mask = bool(config.get('use_segmentation_mask', False))
-        self.observation_space = spaces.Dict({'rgb': spaces.Box(0., 1., shape=self.resolution + [3], dtype='float32')})
+        # extension key: the colour image as bytes (round(255 c), the renderer's own format - the reference divides it by 255,
+        # camera.py:76-78): a quarter of the colour bytes for a host-side consumer to move
+        self.rgb_uint8 = bool(config.get('rgb_uint8', False))
+        self.observation_space = spaces.Dict({'rgb': spaces.Box(0, 255, shape=self.resolution + [3], dtype='uint8') if self.rgb_uint8
+                                              else spaces.Box(0., 1., shape=self.resolution + [3], dtype='float32')})
         if self.use_depth:
             self.observation_space.spaces['depth'] = spaces.Box(0., 10., shape=self.resolution, dtype='float32')
         if self.use_seg_mask:   # camera.py:54-56
@@ -230,7 +234,7 @@ class Camera(Addon):
         self.env = env
 
     def observe(self):
-        img = self.env.world.render(self.cam, seg=self.use_seg_mask)
+        img = self.env.world.render(self.cam, seg=self.use_seg_mask, u8=self.rgb_uint8)
         out = {'rgb': img[0]}   # [N, H, W, 3]; the reference labels the same buffer (W, H, 3) (camera.py:77)
         if self.use_depth:
             out['depth'] = img[1]

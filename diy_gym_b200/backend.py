@@ -53,6 +53,8 @@ def load_library():
     L.dg_render.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     L.dg_render_seg.restype = ctypes.c_int
     L.dg_render_seg.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
+    L.dg_render_u8.restype = ctypes.c_int
+    L.dg_render_u8.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     L.dg_set_action_mask.restype = ctypes.c_int
     L.dg_set_action_mask.argtypes = [vp, ctypes.POINTER(ctypes.c_uint8), ctypes.c_int]
     L.dg_step_host.restype = ctypes.c_int
@@ -162,21 +164,28 @@ class World:
         m = np.ascontiguousarray(enabled, np.uint8)
         self._check(self.L.dg_set_action_mask(self._h, m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)), m.size))
 
-    def render(self, cam=0, seg=False):
+    def render(self, cam=0, seg=False, u8=False):
+        """Camera `cam` of every environment: (rgb [N, H, W, 3], depth [N, H, W][, mask [N, H, W]]) - views of buffers the next
+        render overwrites.  u8: the colour image as bytes round(255 c) (what the reference divides by 255, camera.py:76-78)."""
         w, hgt = self.cams[cam]
-        if cam not in self._img:
-            self._img[cam] = (torch.empty((self.n_envs, hgt, w, 3), dtype=torch.float32, device=self.device),
+        key = ('u8', cam) if u8 else cam
+        if key not in self._img:
+            self._img[key] = (torch.empty((self.n_envs, hgt, w, 3), dtype=torch.uint8 if u8 else torch.float32, device=self.device),
                               torch.empty((self.n_envs, hgt, w), dtype=torch.float32, device=self.device))
-        rgb, depth = self._img[cam]
+        rgb, depth = self._img[key]
+        mask = None
         if seg:
             if ('seg', cam) not in self._img:
                 self._img[('seg', cam)] = torch.empty((self.n_envs, hgt, w), dtype=torch.float32, device=self.device)
             mask = self._img[('seg', cam)]
-            self._check(self.L.dg_render_seg(self._h, cam, ctypes.c_void_p(rgb.data_ptr()), ctypes.c_void_p(depth.data_ptr()),
-                                             ctypes.c_void_p(mask.data_ptr()), self._stream()))
-            return rgb, depth, mask
-        self._check(self.L.dg_render(self._h, cam, ctypes.c_void_p(rgb.data_ptr()), ctypes.c_void_p(depth.data_ptr()), self._stream()))
-        return rgb, depth
+        p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        if u8:
+            self._check(self.L.dg_render_u8(self._h, cam, p(rgb), p(depth), p(mask), self._stream()))
+        elif seg:
+            self._check(self.L.dg_render_seg(self._h, cam, p(rgb), p(depth), p(mask), self._stream()))
+        else:
+            self._check(self.L.dg_render(self._h, cam, p(rgb), p(depth), self._stream()))
+        return (rgb, depth, mask) if seg else (rgb, depth)
 
     def step_host(self, action_host, obs_host, reward_host, term_host):
         """Host-buffer step: numpy (ideally pinned) in, numpy out, synchronous."""

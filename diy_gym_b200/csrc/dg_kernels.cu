@@ -350,8 +350,8 @@ __device__ __forceinline__ bool ray_shape(int type, const float* d, const float*
 #define VS_ZMIN 34
 #define VS_RECT 35
 #define VS_BODY 39
-template <int NCW, int MINB, int NH>
-__global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
+template <int NCW, int NH, bool U8>
+__global__ void __launch_bounds__(256, 3) dg_render_kernel(const __grid_constant__ DevScene sc, const float* state, const float* param, int cam, float* rgb, float* depth,
                                                         float* seg, int tiles_x, int tiles_y, int groups) {
   // a block = one environment (or the `groups`-th part of its image).  Once per block: world pose, camera-relative constants,
   // screen rectangle and nearest depth of every visual shape, sorted front to back.  Then every warp renders 8 x 8 pixel patches (two rays per lane):
@@ -450,13 +450,17 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
   const float light[3] = {0.4082482904638631f, 0.4082482904638631f, 0.8164965809277261f};
   const int npx = width * height;
   float* rgb_e = rgb + (size_t)e * npx * 3; float* dep_e = depth + (size_t)e * npx; float* seg_e = seg ? seg + (size_t)e * npx : nullptr;
+  // U8: the colour image is [H][W][3] bytes, round(255 c) - what the reference's camera reads from the renderer before it divides by 255
+  // (sensors/camera.py:76-78)
+  unsigned char* rgb8_e = reinterpret_cast<unsigned char*>(rgb) + (size_t)e * npx * 3;
+  auto to_u8 = [](float c) { return (unsigned char)__float2uint_rn(__saturatef(c) * 255.0f); };
   // Every WARP renders patches of MT_W x MT_H = 64 pixels on its own (no block barrier in this loop): the lanes test the shapes'
   // screen rectangles against the patch (ballots -> candidate bits in registers, front to back), every lane casts the ray of its
   // pixel, and the patch goes out as 128-bit pieces of image rows through the warp's slice of the staging buffers.
   constexpr int MT_W = 8, MT_H = 4 * NH;   // NH = 2: 8 x 8 patches, two rays per lane; NH = 1: 8 x 4, one ray (small images)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   const int mtx = (width + MT_W - 1) / MT_W, mty = (height + MT_H - 1) / MT_H, nmt = mtx * mty;
-  const bool vec_ok = (width % 4) == 0;   // image rows and patch offsets keep 16-byte alignment
+  const bool vec_ok = (width % (U8 ? 8 : 4)) == 0;   // image rows and patch offsets keep 16-byte (colour bytes: 8-byte) alignment
   float* w_rgb = t_rgb + 192 * warp; float* w_dep = t_dep + 64 * warp; float* w_seg = t_seg + 64 * warp;
   // NCW candidate words live in registers (32 NCW shapes; beyond 128: see below).  Lane l owns shapes l, 32 + l, ...: their screen
   // rectangles stay in its registers for the whole image, so the per-patch overlap test reads no memory.
@@ -484,6 +488,13 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
   const float* src0 = col0 ? w_rgb + 24 * row0 + 4 * c0 : w_dep + 8 * row0 + 4 * c0;
   const float* src1 = col1 ? w_rgb + 24 * row1 + 4 * c1 : w_dep + 8 * row1 + 4 * c1;
   const float* srcs = w_seg + 8 * rows + 4 * cs;
+  // U8: a patch row of colour is 24 bytes = three 64-bit pieces: lanes 0 .. 3 MT_H - 1; depth pieces (two float4 per row) on the next
+  // 2 MT_H lanes (NH = 1) or in a second round on lanes 0..15 (NH = 2); mask pieces after them
+  unsigned char* w8 = reinterpret_cast<unsigned char*>(w_rgb);
+  const int b_row = lane / 3, b_c = lane % 3;
+  const int d_lane = NH == 2 ? lane : lane - 12, s_lane = NH == 2 ? lane - 16 : lane - 20;
+  const bool d_on = d_lane >= 0 && d_lane < 2 * MT_H, s_on = s_lane >= 0 && s_lane < 2 * MT_H;
+  const unsigned b_off = (unsigned)(b_row * width * 3 + 8 * b_c), d_off = (unsigned)((d_lane / 2) * width + 4 * (d_lane % 2)), s_off = (unsigned)((s_lane / 2) * width + 4 * (s_lane % 2));
   // patches in row-major order, mt = grp nwarp + warp, then + groups nwarp: column / row kept incrementally (no division per patch)
   const int stride = groups * nwarp, dcol = stride % mtx, drow = stride / mtx;
   int mt = grp * nwarp + warp, pcol = mt % mtx, prow = mt / mtx;
@@ -535,13 +546,25 @@ __global__ void __launch_bounds__(256, MINB) dg_render_kernel(const __grid_const
         }
         if (!staged) {
           const size_t px = (size_t)j * width + i;
-          rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; dep_e[px] = dz;
+          if (U8) { rgb8_e[3 * px] = to_u8(r); rgb8_e[3 * px + 1] = to_u8(g); rgb8_e[3 * px + 2] = to_u8(bl); }
+          else { rgb_e[3 * px] = r; rgb_e[3 * px + 1] = g; rgb_e[3 * px + 2] = bl; }
+          dep_e[px] = dz;
           if (seg_e) seg_e[px] = sid;
         }
       }
-      if (staged) { w_rgb[3 * slot] = r; w_rgb[3 * slot + 1] = g; w_rgb[3 * slot + 2] = bl; w_dep[slot] = dz; w_seg[slot] = sid; }
+      if (staged) {
+        if (U8) { w8[3 * slot] = to_u8(r); w8[3 * slot + 1] = to_u8(g); w8[3 * slot + 2] = to_u8(bl); }
+        else { w_rgb[3 * slot] = r; w_rgb[3 * slot + 1] = g; w_rgb[3 * slot + 2] = bl; }
+        w_dep[slot] = dz; w_seg[slot] = sid;
+      }
     }
-    if (staged) {
+    if (staged && U8) {
+      __syncwarp();
+      const unsigned pb = (unsigned)(py0 * width + px0);
+      if (lane < 3 * MT_H && b_row < ht) *reinterpret_cast<uint2*>(rgb8_e + 3u * pb + b_off) = *reinterpret_cast<const uint2*>(w8 + 24 * b_row + 8 * b_c);
+      if (d_on && d_lane / 2 < ht) *reinterpret_cast<float4*>(dep_e + pb + d_off) = *reinterpret_cast<const float4*>(w_dep + 4 * d_lane);
+      if (seg_e && s_on && s_lane / 2 < ht) *reinterpret_cast<float4*>(seg_e + pb + s_off) = *reinterpret_cast<const float4*>(w_seg + 4 * s_lane);
+    } else if (staged) {
       __syncwarp();
       const unsigned pb = (unsigned)(py0 * width + px0);
       if (row0 < ht) {
@@ -928,7 +951,7 @@ int dg_step(DgWorld* w, void* stream) { return run(w, 0, nullptr, stream); }
 int dg_reset(DgWorld* w, const uint8_t* mask_dev, void* stream) { return run(w, 1, mask_dev, stream); }
 int dg_observe(DgWorld* w, void* stream) { return run(w, 2, nullptr, stream); }
 
-int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream) {
+static int render_any(DgWorld* w, int cam, void* rgb_dev, bool u8, float* depth_dev, float* seg_dev, void* stream) {
   if (!w || !rgb_dev || !depth_dev) return DG_E_ARG;
   if (!w->bound) { w->err = "dg_render: buffers not bound"; return DG_E_UNBOUND; }
   const DevScene& d = w->dev;
@@ -941,22 +964,23 @@ int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* 
   int tiles_x = (ci[1] + 7) / 8, tiles_y = (ci[2] + 4 * nh - 1) / (4 * nh);
   size_t smem = ((size_t)std::max(d.nv, 1) * VS_W + (size_t)((d.nv + 3) & ~3) + (size_t)(d.nv + 31) / 32 + 8) * sizeof(float);
   const int ncw = (d.nv + 31) / 32;   // candidate words per patch the kernel keeps in registers: 1, 2 or 4 (then a per-shape tail)
-  // resident blocks per SM the kernel is compiled for: 3 (80 registers) or 4 (64 registers, the per-block set-up spills a little;
-  // measured slower: 1.10 vs 1.03 ms); DG_RENDER_MINB selects, for A/B measurements
-  static const int minb = [] { const char* v = getenv("DG_RENDER_MINB"); return v && atoi(v) == 4 ? 4 : 3; }();
+  // (compiled for 3 resident blocks per SM, 80 registers; 4 blocks / 64 registers spills in the per-block set-up and measured
+  // slower: 1.10 vs 1.03 ms per 4096 x 200 x 200 render)
   using RenderFn = void (*)(DevScene, const float*, const float*, int, float*, float*, float*, int, int, int);
   static const RenderFn table[2][2][3] = {
-      {{dg_render_kernel<1, 3, 1>, dg_render_kernel<2, 3, 1>, dg_render_kernel<4, 3, 1>}, {dg_render_kernel<1, 3, 2>, dg_render_kernel<2, 3, 2>, dg_render_kernel<4, 3, 2>}},
-      {{dg_render_kernel<1, 4, 1>, dg_render_kernel<2, 4, 1>, dg_render_kernel<4, 4, 1>}, {dg_render_kernel<1, 4, 2>, dg_render_kernel<2, 4, 2>, dg_render_kernel<4, 4, 2>}}};
-  RenderFn kern = table[minb == 4][nh - 1][ncw <= 1 ? 0 : (ncw == 2 ? 1 : 2)];
+      {{dg_render_kernel<1, 1, false>, dg_render_kernel<2, 1, false>, dg_render_kernel<4, 1, false>}, {dg_render_kernel<1, 2, false>, dg_render_kernel<2, 2, false>, dg_render_kernel<4, 2, false>}},
+      {{dg_render_kernel<1, 1, true>, dg_render_kernel<2, 1, true>, dg_render_kernel<4, 1, true>}, {dg_render_kernel<1, 2, true>, dg_render_kernel<2, 2, true>, dg_render_kernel<4, 2, true>}}};
+  RenderFn kern = table[u8 ? 1 : 0][nh - 1][ncw <= 1 ? 0 : (ncw == 2 ? 1 : 2)];
   if (smem > 48 * 1024) { CK(w, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->smem_cap)); }
   // blocks per environment: one when the batch alone fills the GPU a few times over, else enough groups of tiles to do so
   int groups = std::max(1, std::min((tiles_x * tiles_y + 7) / 8, (8 * w->sm_count + w->n_envs - 1) / w->n_envs));
   w->launches++;
-  kern<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, cam, rgb_dev, depth_dev, seg_dev, tiles_x, tiles_y, groups);
+  kern<<<w->n_envs * groups, 256, smem, (cudaStream_t)stream>>>(w->dev, w->buf.state, w->buf.param, cam, reinterpret_cast<float*>(rgb_dev), depth_dev, seg_dev, tiles_x, tiles_y, groups);
   CK(w, cudaGetLastError());
   return DG_OK;
 }
+int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream) { return render_any(w, cam, rgb_dev, false, depth_dev, seg_dev, stream); }
+int dg_render_u8(DgWorld* w, int cam, uint8_t* rgb_dev, float* depth_dev, float* seg_dev, void* stream) { return render_any(w, cam, rgb_dev, true, depth_dev, seg_dev, stream); }
 int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* stream) { return dg_render_seg(w, cam, rgb_dev, depth_dev, nullptr, stream); }
 
 int dg_step_host(DgWorld* w, const float* action_host, float* obs_host, float* reward_host, uint8_t* term_host, void* stream) {

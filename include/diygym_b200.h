@@ -97,6 +97,9 @@ int dg_render(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, void* strea
 /* The same with the segmentation mask of sensors/camera.py:54-56,89-90 (`use_segmentation_mask`): seg_dev [n_envs][H][W] gets
  * the unique id (body index in load order) of the body visible in each pixel, -1 for the background; NULL = no mask. */
 int dg_render_seg(DgWorld* w, int cam, float* rgb_dev, float* depth_dev, float* seg_dev, void* stream);
+/* The same with the colour image as bytes: rgb_dev [n_envs][H][W][3] uint8 = round(255 c) - the renderer's own output format,
+ * which the reference divides by 255 (sensors/camera.py:76-78); a quarter of the colour bytes to move.  seg_dev may be NULL. */
+int dg_render_u8(DgWorld* w, int cam, uint8_t* rgb_dev, float* depth_dev, float* seg_dev, void* stream);
 
 /* Host-buffer form of dg_step (the reference-facing call when the caller keeps numpy arrays): copies the actions
  * host->device, steps, copies obs / reward / terminal device->host and waits.  Any output pointer may be NULL. */

@@ -57,7 +57,7 @@ class EmulTorchWorld:
             m = self._m.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
         lib().dge_reset(self.e._w, m, *self._ptrs())
 
-    def render(self, cam=0, seg=False):
+    def render(self, cam=0, seg=False, u8=False):
         if self._oracle is None:
             self._oracle = OracleWorld(self.scene)
         w, hgt = self.cams[cam]
@@ -71,6 +71,8 @@ class EmulTorchWorld:
             rgb[e], depth[e] = out[0], out[1]
             if seg:
                 mask[e] = out[2]
+        if u8:   # round(255 c), as dg_render_u8
+            rgb = np.rint(np.clip(rgb, 0.0, 1.0) * 255.0).astype(np.uint8)
         return (torch.from_numpy(rgb), torch.from_numpy(depth)) + ((torch.from_numpy(mask), ) if seg else ())
 
     def set_action_mask(self, enabled):

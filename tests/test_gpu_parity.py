@@ -241,6 +241,25 @@ def test_camera_kernel_matches_oracle_ray_cast():
         env.close()
 
 
+def test_camera_u8_colour_matches_float_render():
+    """dg_render_u8 (camera key `rgb_uint8`): bytes = round(255 c) of the float render, depth and mask unchanged; both patch sizes
+    (50 x 50: 8 x 4 patches, 200 x 200: 8 x 8) and the unaligned-width scalar path (50 is not a multiple of 8)."""
+    for name in ('basic_env', 'from_the_readme'):
+        env = _env(name, 3)
+        for _ in range(3):
+            env.world.step()
+        rgb, depth = (t.clone() for t in env.world.render(0))
+        rgb8, depth8, seg8 = (t.clone() for t in env.world.render(0, seg=True, u8=True))
+        _, _, seg = env.world.render(0, seg=True)
+        torch.cuda.synchronize()
+        assert rgb8.dtype == torch.uint8 and rgb8.shape == rgb.shape
+        want = torch.round(rgb.clamp(0, 1) * 255.0)
+        diff = (rgb8.float() - want).abs()
+        assert diff.max().item() <= 1.0 and (diff > 0).float().mean().item() < 1e-3   # (ties of the rounding only)
+        assert torch.equal(depth8, depth) and torch.equal(seg8, seg)
+        env.close()
+
+
 def test_drone_pilot_user_addons_on_device():
     import importlib.util
     spec = importlib.util.spec_from_file_location('drone_pilot_example', os.path.join(EX, 'drone_pilot', 'drone_pilot.py'))
