@@ -466,9 +466,10 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
     fp32_peak = measure_fp32_peak(local_rank)
     cpu = cpu_oracle_rate(sc, lo_np, hi_np) if cpu_baseline else None
     flops = cpu['flops_per_env_step'] if cpu else oracle_flops(sc, lo_np, hi_np)
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one step's launches (ncu --set full), tools/ncu_traffic.py
+    traffic = render_traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of one step's launches / of one render launch (ncu, profiles/ncu_traffic.json)
     try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'))).get('%s:%d' % (config, n_envs))
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        traffic, render_traffic = table.get('%s:%d' % (config, n_envs)), table.get('%s:%d:render' % (config, n_envs))
     except Exception:
         pass
     kname = ('dg_step_kernel<%d> stage launches + dg_solve_kernel' % w.team) if res['split_schedule'] else 'dg_step_kernel<%d>' % w.team
@@ -482,10 +483,10 @@ def measure(config, n_envs, ctx, cpu_baseline=True, api_leg=True):
     if cams:
         render_ms = max(ms_total / steps - kernel_ms, 1e-6)
         a = img_bytes * n_envs / (render_ms * 1e-3) / 1e9
-        roofline = {'bound': 'hbm', 'kernel': 'dg_render_kernel', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a / hbm_peak, 'traffic': None,
+        roofline = {'bound': 'hbm', 'kernel': 'dg_render_kernel', 'achieved': a, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': a / hbm_peak, 'traffic': render_traffic,
                     'peak_source': hbm['peak_source'], 'algorithmic_bytes_per_env_step': img_bytes, 'kernel_ms': render_ms,
                     'note': 'the render launch (image bytes written per env-step) is the dominant kernel of this config; the physics launches are under "step"',
-                    'step': dict(fp32, bound='fp32', kernel=kname, kernel_ms=kernel_ms, hbm=hbm)}
+                    'step': dict(fp32, bound='fp32', kernel=kname, kernel_ms=kernel_ms, traffic=traffic, hbm=hbm)}
     else:
         roofline = dict(fp32, bound='fp32', kernel=kname, kernel_ms=kernel_ms, traffic=traffic,
                         note='bound = non-tensor FP32 issue (oracle-counted flops / measured FMA peak): the physics is a chain of small dependent fp32 systems; the HBM bound (algorithmic state bytes / measured copy bandwidth) is three orders of magnitude away and listed under "hbm"',

@@ -88,6 +88,28 @@ def test_camera_segmentation_mask_reports_body_ids():
         os.remove(path)
 
 
+def test_camera_rgb_uint8_key_returns_the_renderers_bytes():
+    """Extension key `rgb_uint8`: the colour observation as bytes round(255 c) - what the reference divides by 255 (camera.py:76-78)."""
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(EX, 'basic_env', 'basic_env.yaml')))
+    path = os.path.join(os.path.dirname(__file__), '_tmp_u8.yaml')
+    try:
+        imgs = {}
+        for u8 in (False, True):
+            cfg['camera']['rgb_uint8'] = u8
+            with open(path, 'w') as f:
+                yaml.safe_dump(cfg, f)
+            env = DIYGym(path, num_envs=1, world_factory=factory())
+            sp = env.observation_space['_tmp_u8']['camera']['rgb']
+            assert sp.dtype == (np.uint8 if u8 else np.float32) and sp.shape == (50, 50, 3)
+            imgs[u8] = env.reset()['_tmp_u8']['camera']['rgb'][0].numpy()
+        assert imgs[True].dtype == np.uint8
+        assert np.array_equal(imgs[True], np.rint(np.clip(imgs[False], 0, 1) * 255).astype(np.uint8))
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+
+
 # ---- reference tests/test_utils.py ----------------------------------------------------------------------------
 def test_flatten_unflatten_round_trip():
     env = make('basic_env')
