@@ -575,8 +575,8 @@ DG_HD bool pair_in_reach(const Env& C, int sa, int sb) {
 DG_FN int point_hull(const float* p, const float* R, const float* pos, const float* planes, int np_, float margin, float* surf, float* n, float* dist) {
   float d[3], pl[3]; v_sub(d, p, pos); mT_vec(pl, R, d);
   float best = -1e30f; int bi = 0;
-  for (int k = 0; k < np_; k++) { const float* q = planes + 4 * k; const float s = q[0] * pl[0] + q[1] * pl[1] + q[2] * pl[2] - q[3]; if (s > best) { best = s; bi = k; } }
-  if (best > margin) return 0;
+  // (a point beyond the margin of ANY plane is outside: leave at the first such plane - most vertices of a pair in reach are)
+  for (int k = 0; k < np_; k++) { const float* q = planes + 4 * k; const float s = q[0] * pl[0] + q[1] * pl[1] + q[2] * pl[2] - q[3]; if (s > margin) return 0; if (s > best) { best = s; bi = k; } }
   m_vec(n, R, planes + 4 * bi); *dist = best;
   surf[0] = p[0] - n[0] * best; surf[1] = p[1] - n[1] * best; surf[2] = p[2] - n[2] * best;
   return 1;
@@ -592,11 +592,13 @@ DG_FN void collide_convex(const Env& C, const int* ia, const float* fa, const fl
     const int* ix = side ? ib : ia; const int* iy = side ? ia : ib; const float* fx = side ? fb : fa; const float* fy = side ? fa : fb;
     const float *Rx = side ? Rb : Ra, *px = side ? pb : pa, *Ry = side ? Ra : Rb, *py = side ? pa : pb;
     const int nvx = ix[5] > 0 ? ix[5] : 8;
+    const float reach2 = (fy[11] + margin) * (fy[11] + margin);   // Y lies inside the ball of radius fy[11] about its origin (compiler/scene.py)
     for (int k = 0; k < nvx; k++) {
       float vl[3], t[3], pt[3], surf[3], n[3], dist;
       if (ix[5] > 0) { const float* v = H + ix[4] + 3 * k; vl[0] = v[0]; vl[1] = v[1]; vl[2] = v[2]; }
       else { vl[0] = (k & 1 ? 1 : -1) * fx[7]; vl[1] = (k & 2 ? 1 : -1) * fx[8]; vl[2] = (k & 4 ? 1 : -1) * fx[9]; }
       m_vec(t, Rx, vl); v_add(pt, px, t);
+      { float dy[3]; v_sub(dy, pt, py); if (v_dot(dy, dy) > reach2) continue; }   // a vertex farther than that cannot be within the margin of Y
       const int hit = iy[5] > 0 ? point_hull(pt, Ry, py, H + iy[6], iy[7], margin, surf, n, &dist) : point_box(pt, Ry, py, fy + 7, margin, surf, n, &dist);
       if (!hit) continue;
       if (side == 0) ct_add(loc, nloc, 16, ia[1], ib[1], pt, surf, n, dist, mu, margin);                       // vertex of A in B: normal of B
