@@ -40,8 +40,8 @@ struct Env {
   unsigned* dropped;              // contacts lost to the max_contacts cap since the world was created (one counter per world), or null
   // split schedule (GPU only): the contact sweeps of this environment may be left to the sweep kernel (dg_solve_kernel)
   int split;                      // 1: environments whose rows fit a warp are deferred to the sweep kernel
-  int* rs_list[2];                // deferred environments: <= 32 row positions | <= 64 (local indices), or null
-  int* rs_count;                  // [2] their counts (atomically incremented)
+  int* rs_lists; int rs_stride;   // deferred environments by sweep-kernel class: class c at rs_lists + c rs_stride (local indices), or null
+  int* rs_count;                  // [RS_NCLS] their counts (atomically incremented)
   int e_local;                    // index of this environment in the launch
   unsigned* rs_used;              // counter of environment sub-steps solved in row space (any schedule), or null
   int no_hot;                     // reset launch without the hot-start steps (they follow as stage launches)
@@ -566,8 +566,24 @@ DG_HD bool pair_in_reach(const Env& C, int sa, int sb) {
   const float *Ra, *pa, *Rb, *pb;
   shape_pose(C, sa, &Ra, &pa); shape_pose(C, sb, &Rb, &pb);
   float dc[3]; v_sub(dc, pa, pb);
-  float reach = gc(SC.shape_f)[DG_SHAPE_F_W * sa + 11] + gc(SC.shape_f)[DG_SHAPE_F_W * sb + 11] + SC.margin;
-  return v_dot(dc, dc) <= reach * reach;
+  const float ra = gc(SC.shape_f)[DG_SHAPE_F_W * sa + 11], rb = gc(SC.shape_f)[DG_SHAPE_F_W * sb + 11];
+  float reach = ra + rb + SC.margin;
+  if (v_dot(dc, dc) > reach * reach) return false;
+  // a true box (no hull) is tested itself, not its bounding ball: the other shape lies inside the ball of its radius about its
+  // origin, so nothing of the pair can be within the margin unless that origin is within radius + margin of the box (a large
+  // table under a robot arm otherwise lets every link of the arm through to the narrow phase)
+  for (int side = 0; side < 2; side++) {
+    const int sx = side ? sa : sb;   // the box
+    const int* ix = gc(SC.shape_i) + DG_SHAPE_I_W * sx;
+    if (ix[2] != SHAPE_BOX || ix[5] > 0) continue;
+    const float *Rx = side ? Ra : Rb, *px = side ? pa : pb, *po = side ? pb : pa; const float* h = gc(SC.shape_f) + DG_SHAPE_F_W * sx + 7;
+    float d[3], pl[3]; v_sub(d, po, px); mT_vec(pl, Rx, d);
+    float d2 = 0.f;
+    for (int i = 0; i < 3; i++) { const float ex = fabsf(pl[i]) - h[i]; if (ex > 0.f) d2 += ex * ex; }
+    const float r = (side ? rb : ra) + SC.margin;
+    if (d2 > r * r) return false;
+  }
+  return true;
 }
 // ---- reduced convex hulls (mesh links; model.py:65 loads them as btConvexHullShape) ----------------------------------------
 // signed distance of world point p to the hull (R, pos; planes n . x <= d in its own frame): the largest plane distance.  Inside or
@@ -731,6 +747,17 @@ DG_FN void phase_broad(const Env& C, int ln, int nt) {
       float dc[3]; v_sub(dc, w + 9, cb);
       float reach = gc(sc.shape_f)[DG_SHAPE_F_W * g[0] + 11] + gc(sc.body_reach)[g[1]] + sc.margin;
       if (v_dot(dc, dc) > reach * reach) continue;
+      {   // a static box (a maze wall, a table top) against the body's sphere: the box itself, not its bounding ball
+        const int* is = gc(sc.shape_i) + DG_SHAPE_I_W * g[0];
+        if (is[2] == SHAPE_BOX && is[5] == 0) {
+          const float* h = gc(sc.shape_f) + DG_SHAPE_F_W * g[0] + 7;
+          float d[3], pl[3]; v_sub(d, cb, w + 9); mT_vec(pl, w, d);
+          float d2 = 0.f;
+          for (int i = 0; i < 3; i++) { const float ex = fabsf(pl[i]) - h[i]; if (ex > 0.f) d2 += ex * ex; }
+          const float r = gc(sc.body_reach)[g[1]] + sc.margin;
+          if (d2 > r * r) continue;
+        }
+      }
       for (int j = 0; j < g[3]; j++) {
         int k = gc(sc.grp_pairs)[g[2] + j];
         if (pair_in_reach(C, gc(sc.pair_i)[2 * k], gc(sc.pair_i)[2 * k + 1])) surv_set(WSIP(C, sc.X_SURV) + (k >> 5), k & 31);
@@ -1192,11 +1219,14 @@ DG_FN void phase_rs_plan(const Env& C, int ln, int nt) {
   hdr[WH_RS_NU] = nu; hdr[WH_RS_R] = 0; hdr[WH_RS_DEFER] = 0;
   int need = want ? rs_kneed(nu, nk, nc, nt, sc.rs_cap) : 0;
   if (want && C.split) {
-    // the sweep kernel gives an environment a half warp (<= 32 row positions) or a whole one (<= 64), two rows per lane: its
-    // layout is the K = 2 one; WH_RS_DEFER = 1 / 2 names the list (dg_kernels.cu, dg_solve_kernel)
-    const int t2 = rs_total(nu, nk, nc, 2);
-    const int cls = t2 > sc.rs_cap ? 0 : (t2 <= RS_WARP_R1 ? 1 : (t2 <= RS_WARP_R2 ? 2 : 0));
-    if (cls) { need = 2; hdr[WH_RS_DEFER] = cls; }
+    // the sweep kernel gives an environment 8, 16 or 32 lanes with 4, 3 or 2 consecutive rows each (DevScene::rs_cls_*): the first
+    // class whose K-padded layout fits; WH_RS_DEFER = 1 + class names the list, WH_RS_NEED the K of its layout
+    for (int c = 0; c < RS_NCLS; c++) {
+      const int kc = sc.rs_cls_k[c], rc = sc.rs_cls_r[c];
+      if (rc <= 0) continue;
+      const int t = rs_total(nu, nk, nc, kc);
+      if (t <= rc && t <= sc.rs_cap) { need = kc; hdr[WH_RS_DEFER] = c + 1; break; }
+    }
   }
   hdr[WH_RS_NEED] = need;
 }
@@ -1220,7 +1250,7 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     hdr[WH_RS_R] = L.Rp; hdr[WH_RS_K] = K;
 #if defined(__CUDA_ARCH__)
     if (C.rs_used) atomicAdd(C.rs_used, 1u);   // how many environment sub-steps needed the row-space solver (steers the schedule)
-    if (defer) { const int cls = hdr[WH_RS_DEFER] - 1; const int slot = atomicAdd(C.rs_count + cls, 1); C.rs_list[cls][slot] = C.e_local; }
+    if (defer) { const int cls = hdr[WH_RS_DEFER] - 1; const int slot = atomicAdd(C.rs_count + cls, 1); C.rs_lists[(size_t)cls * C.rs_stride + slot] = C.e_local; }
 #endif
   }
   float* RSV = WSG(C, sc.X_RSV); float* REC = WSG(C, sc.X_RSREC);

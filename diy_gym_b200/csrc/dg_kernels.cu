@@ -27,7 +27,7 @@ struct LaunchArgs {
   unsigned* dropped;         // contacts lost to the max_contacts cap (one counter per world)
   // split schedule (mode 0 only): which stages of the step this launch runs (ST_*), the per-environment carry of the hot
   // workspace between launches, and the lists of environments left to the sweep kernel
-  int stages; float* carry; int* rs_list0; int* rs_list1; int* rs_count; unsigned* rs_used; int no_hot;
+  int stages; float* carry; int* rs_lists; int* rs_count; unsigned* rs_used; int no_hot;   // rs_lists: [RS_NCLS][n_envs]
 };
 
 template <int T>
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) dg_step_kernel(const __grid_constant__ De
   C.link_i = s_link_i; C.link_f = s_link_f; C.link_x = s_link_x;
   C.sc = &sc; C.ws = smem + (size_t)ei * sc.w_total; C.seed = a.seed;
   C.opmask[0] = a.opmask[0]; C.opmask[1] = a.opmask[1]; C.dbg = a.dbg; C.dropped = a.dropped;
-  C.split = a.stages != ST_ALL ? 1 : 0; C.rs_list[0] = a.rs_list0; C.rs_list[1] = a.rs_list1; C.rs_count = a.rs_count; C.rs_used = a.rs_used; C.no_hot = a.no_hot;
+  C.split = a.stages != ST_ALL ? 1 : 0; C.rs_lists = a.rs_lists; C.rs_stride = a.n_envs; C.rs_count = a.rs_count; C.rs_used = a.rs_used; C.no_hot = a.no_hot;
   { // environments that share a warp once the row-space sweeps remap the threads (thread t -> lane t % T of environment t / T)
     const int G = T >= 32 ? 1 : 32 / T, g0 = ei / G * G;
     C.grp0 = g0 - ei; C.grp1 = (g0 + G < E ? g0 + G : E) - ei;
@@ -118,22 +118,22 @@ DG_DEFINE_STEP_X(DG_STEP_T)
 #endif
 
 #if !defined(DG_STEP_T)
-// The contact sweeps of the environments a stage launch deferred.  An environment gets W = 16 lanes (two environments per
-// warp, <= 32 row positions each) or W = 32 (<= 64 positions); one warp per block.  Lane l of the environment owns the TWO
-// consecutive positions 2 l, 2 l + 1 of the padded layout (dg_env.cuh "row-space team solver") and holds, in registers, their
-// right-hand sides, clamps, accumulated impulses, y = J dv and its two columns of A for EVERY row - the 150 sweeps of a
-// sub-step touch no memory.  One pair of updates: every lane evaluates the clamp of its first slot, the owner's change d0 is
-// broadcast by a shuffle; the owner folds d0 into its second row at once (its own register), evaluates that clamp and
-// broadcasts d1; then every lane folds both broadcasts into its two y.  Only every other update waits for a shuffle.
-// Row order, clamps and friction bounds are those of the in-kernel team sweeps and of the oracle.  The two environments of a
-// warp run one instruction stream: their sections are laid out at common offsets (the larger of the two section sizes; the
-// surplus positions of the smaller one are inert padding); if that common layout does not fit, the warp sweeps its two
-// environments one after the other.  Everything that steers the loops is read through block-uniform addresses, so the loop
-// branches stay uniform (no divergence bookkeeping around the shuffles).
+// The contact sweeps of the environments a stage launch deferred: dg_solve_kernel<W, K>, one warp per block, W lanes per
+// environment (32 / W environments per warp), lane l owns the K CONSECUTIVE positions K l .. K l + K - 1 of the padded layout
+// (dg_env.cuh "row-space team solver") - classes 8 x 4 (<= 32 positions), 16 x 3 (<= 48), 32 x 2 (<= 64).  A lane holds, in
+// registers, the right-hand sides, clamps and accumulated impulses of its rows and its K columns of A for EVERY row: the 150 sweeps
+// of a sub-step touch no memory.  One step = the K rows of lane j: every lane evaluates the clamp of its first slot, the owner's
+// change is broadcast by a shuffle; the owner folds it into its next row at once (its own registers), evaluates that clamp,
+// broadcasts, ...; then every lane folds the K broadcasts into its K rows.  Only one update in K waits for a shuffle.
+// Row order, clamps and friction bounds are those of the in-kernel team sweeps and of the oracle.  The environments of a warp run
+// one instruction stream: their sections are laid out at common offsets (the largest of the section sizes; surplus positions are
+// inert padding); if that common layout does not fit, the warp sweeps its environments one after the other.  Everything that
+// steers the loops is read through block-uniform addresses, so the loop branches stay uniform (no divergence bookkeeping around
+// the shuffles).
 struct SolveArgs { const float* carry; float* gws; const int* list; const int* count; };
-template <int W>
-__global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
-  constexpr int K = 2, G = 32 / W, RMAX = W * K;
+template <int W, int K>
+__global__ void __launch_bounds__(32, (K == 2 ? (W == 16 ? 16 : 12) : 8)) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
+  constexpr int G = 32 / W, RMAX = W * K;
   constexpr unsigned FULL = 0xffffffffu;
   const int count = *a.count, first = (int)blockIdx.x * G;
   if (first >= count) return;
@@ -149,17 +149,24 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const _
     if (first + g >= count) Ls[g] = rs_layout(K, 0, 0, 0);
     P1w = max(P1w, Ls[g].P1); N2w = max(N2w, Ls[g].P2 - Ls[g].P1); N3w = max(N3w, Ls[g].Rp - Ls[g].P2);
   }
-  const bool together = P1w + N2w + N3w <= RMAX;   // else: one environment at a time, both halves of the warp on the same one
+  const bool together = P1w + N2w + N3w <= RMAX;   // else: one environment at a time, every group of the warp on the same one
   const int npass = (G > 1 && !together) ? G : 1;
   for (int pass = 0; pass < npass; pass++) {
     const int mine = npass > 1 ? pass : half;                       // which environment this lane works on
-    const bool writer = npass > 1 ? half == 0 : true;               // (duplicated work: one half writes back)
-    const RsLayout L = Ls[G > 1 ? mine : 0];
-    // loop bounds from block-uniform values only (Ls[pass], not Ls[mine]: the compiler must see that they are uniform)
-    const RsLayout Lu = Ls[G > 1 ? pass : 0];
+    const bool writer = npass > 1 ? half == 0 : true;               // (duplicated work: one group writes back)
+    RsLayout L = Ls[0];
+#pragma unroll
+    for (int g = 1; g < G; g++) if (mine == g) L = Ls[g];
+    // loop bounds from block-uniform values only (the layout of environment `pass`, not `mine`: the compiler must see that they are uniform)
+    RsLayout Lu = Ls[0];
+#pragma unroll
+    for (int g = 1; g < G; g++) if (pass == g) Lu = Ls[g];
     const int P1 = npass > 1 ? Lu.P1 : P1w, P2 = P1 + (npass > 1 ? Lu.P2 - Lu.P1 : N2w), Rp = P2 + (npass > 1 ? Lu.Rp - Lu.P2 : N3w);
     const bool live = first + mine < count;
-    float* wg = a.gws + (size_t)es[G > 1 ? mine : 0] * sc.g_total;
+    int emine = es[0];
+#pragma unroll
+    for (int g = 1; g < G; g++) if (mine == g) emine = es[g];
+    float* wg = a.gws + (size_t)emine * sc.g_total;
     float* REC = wg + sc.X_RSREC; float* A = wg + sc.X_RSA; const int cap = sc.rs_cap;
     // A[p][s] = J_s . (M^-1 J^T)_p, built HERE by the environment's W lanes (the stage launch leaves the dense row vectors of
     // phase_rs_setup in the cold workspace and skips phase_rs_build for deferred environments): lane per column s, only over the
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const _
     // one update is  d = min(max(v, lo'), hi')  - two dependent instructions - and folding a broadcast change d_p of row p is
     // v += g[p] d_p  with  g[p][r] = -dinv_r A[p][r]  (for r = p that is -1 up to rounding: the row's own change leaves v - d).
     // Mathematically the update of the team sweeps / the oracle  (ap' = clamp(ap + rhs - dinv y), d = ap' - ap);  only the
-    // rounding differs.  lo', hi' are re-derived from the exact bounds after every update of the row (no drift).
+    // rounding differs.  lo', hi' are re-derived from the exact bounds once per section (no drift).
     float dinv[K], lo[K], hi[K], ap[K], v[K], lop[K], hip[K], mu[K]; int par[K], qown[K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
@@ -207,9 +214,11 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const _
       if (q >= 0) { const F4 r0 = ld4(REC + RR_W * q), r1 = ld4(REC + RR_W * q + 4); v[k] = r0.x; dinv[k] = r0.y; lo[k] = r0.z; hi[k] = r0.w; mu[k] = r1.x; par[k] = float_as_int(r1.y); }
       lop[k] = lo[k]; hip[k] = hi[k];   // ap = 0, y = 0 at the start
     }
-    // The owner only CAPTURES its two changes in the update sequence (chg); impulses and shifted bounds are brought up to date once
+    // The owner only CAPTURES its changes in the update sequence (chg); impulses and shifted bounds are brought up to date once
     // per section (DG_SETTLE) - a row is updated once per section, and nobody else reads them in between.
-    float chg[K] = {0.f, 0.f};
+    float chg[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) chg[k] = 0.f;
 #define DG_SETTLE { _Pragma("unroll") for (int k = 0; k < K; k++) { ap[k] += chg[k]; chg[k] = 0.f; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; } }
     float g_[RMAX][K];   // g_[p][k] = -dinv[k] A[row at warp position p][this lane's slot k]
 #pragma unroll
@@ -219,71 +228,86 @@ __global__ void __launch_bounds__(32, W == 16 ? 16 : 12) dg_solve_kernel(const _
       for (int k = 0; k < K; k++) g_[p][k] = (q >= 0 && qown[k] >= 0) ? -dinv[k] * A[q * cap + qown[k]] : 0.f;
     }
     const int nrm0 = P1 + 6 * sc.ncons;   // warp position of the normal row of contact 0
-    // rows 2 j and 2 j + 1 (lane j of each environment), ascending (FWD) or descending.  The owner folds its first change into
-    // its second row at once (vf_); the broadcast values are bit-identical to its own changes, so the folds below give it the same v.
-#define DG_STEP2(j, FWD)                                                                         \
-    {                                                                                              \
-      constexpr int k0_ = (FWD) ? 0 : 1, k1_ = (FWD) ? 1 : 0;                                      \
-      const float d0_ = fminf(fmaxf(v[k0_], lop[k0_]), hip[k0_]);                                  \
-      const float b0_ = __shfl_sync(FULL, d0_, (j), W);                                            \
-      const float vf_ = fmaf(g_[K * (j) + k0_][k1_], d0_, v[k1_]);                                   \
-      const float d1_ = fminf(fmaxf(vf_, lop[k1_]), hip[k1_]);                                     \
-      const float b1_ = __shfl_sync(FULL, d1_, (j), W);                                            \
-      chg[k0_] = (l == (j)) ? d0_ : chg[k0_]; chg[k1_] = (l == (j)) ? d1_ : chg[k1_];              \
-      v[0] = fmaf(g_[K * (j) + k0_][0], b0_, v[0]); v[1] = fmaf(g_[K * (j) + k0_][1], b0_, v[1]);       \
-      v[0] = fmaf(g_[K * (j) + k1_][0], b1_, v[0]); v[1] = fmaf(g_[K * (j) + k1_][1], b1_, v[1]);       \
+    // rows K j .. K j + K - 1 (lane j of each environment), ascending (FWD) or descending.  The owner folds its earlier changes into
+    // its next row at once; the broadcast values are bit-identical to its own changes, so the folds at the end give it the same v.
+#define DG_STEPK(j, FWD)                                                                                                      \
+    {                                                                                                                           \
+      float d_[K], b_[K];                                                                                                       \
+      _Pragma("unroll") for (int t_ = 0; t_ < K; t_++) {                                                                        \
+        const int k_ = (FWD) ? t_ : K - 1 - t_;                                                                                 \
+        float vf_ = v[k_];                                                                                                      \
+        _Pragma("unroll") for (int u_ = 0; u_ < t_; u_++) { const int ku_ = (FWD) ? u_ : K - 1 - u_; vf_ = fmaf(g_[K * (j) + ku_][k_], d_[ku_], vf_); } \
+        d_[k_] = fminf(fmaxf(vf_, lop[k_]), hip[k_]);                                                                           \
+        b_[k_] = __shfl_sync(FULL, d_[k_], (j), W);                                                                             \
+        chg[k_] = (l == (j)) ? d_[k_] : chg[k_];                                                                                \
+      }                                                                                                                         \
+      _Pragma("unroll") for (int t_ = 0; t_ < K; t_++) {                                                                        \
+        const int k_ = (FWD) ? t_ : K - 1 - t_;                                                                                 \
+        _Pragma("unroll") for (int r_ = 0; r_ < K; r_++) v[r_] = fmaf(g_[K * (j) + k_][r_], b_[k_], v[r_]);                     \
+      }                                                                                                                         \
     }
     // The sweeps enter the unrolled update sequence through a jump table (switch on a block-uniform index) instead of testing every
-    // position: descending runs fall through to position 0 with no test at all, ascending runs test their end once per pair.
+    // position: descending runs fall through to position 0 with no test at all, ascending runs test their end once per step.
     // ONE ascending sequence serves the three sections (the section loop is kept rolled: a third of the code, see no_inst stalls).
-#define DG_ASC_(j) case (j): DG_STEP2((j), true) if ((j) + 1 >= e_) break;
-#define DG_DSC_(j) case (j) + 1: DG_STEP2((j), false)
-#define DG_ASC16_ DG_ASC_(0) DG_ASC_(1) DG_ASC_(2) DG_ASC_(3) DG_ASC_(4) DG_ASC_(5) DG_ASC_(6) DG_ASC_(7) DG_ASC_(8) DG_ASC_(9) DG_ASC_(10) DG_ASC_(11) DG_ASC_(12) DG_ASC_(13) DG_ASC_(14) DG_ASC_(15)
+#define DG_ASC_(j) case (j): DG_STEPK((j), true) if ((j) + 1 >= e_) break;
+#define DG_DSC_(j) case (j) + 1: DG_STEPK((j), false)
+#define DG_ASC8_ DG_ASC_(0) DG_ASC_(1) DG_ASC_(2) DG_ASC_(3) DG_ASC_(4) DG_ASC_(5) DG_ASC_(6) DG_ASC_(7)
+#define DG_ASC16_ DG_ASC8_ DG_ASC_(8) DG_ASC_(9) DG_ASC_(10) DG_ASC_(11) DG_ASC_(12) DG_ASC_(13) DG_ASC_(14) DG_ASC_(15)
 #define DG_ASC32_ DG_ASC16_ DG_ASC_(16) DG_ASC_(17) DG_ASC_(18) DG_ASC_(19) DG_ASC_(20) DG_ASC_(21) DG_ASC_(22) DG_ASC_(23) DG_ASC_(24) DG_ASC_(25) DG_ASC_(26) DG_ASC_(27) DG_ASC_(28) DG_ASC_(29) DG_ASC_(30) DG_ASC_(31)
-#define DG_DSC16_ DG_DSC_(15) DG_DSC_(14) DG_DSC_(13) DG_DSC_(12) DG_DSC_(11) DG_DSC_(10) DG_DSC_(9) DG_DSC_(8) DG_DSC_(7) DG_DSC_(6) DG_DSC_(5) DG_DSC_(4) DG_DSC_(3) DG_DSC_(2) DG_DSC_(1) DG_DSC_(0)
+#define DG_DSC8_ DG_DSC_(7) DG_DSC_(6) DG_DSC_(5) DG_DSC_(4) DG_DSC_(3) DG_DSC_(2) DG_DSC_(1) DG_DSC_(0)
+#define DG_DSC16_ DG_DSC_(15) DG_DSC_(14) DG_DSC_(13) DG_DSC_(12) DG_DSC_(11) DG_DSC_(10) DG_DSC_(9) DG_DSC_(8) DG_DSC8_
 #define DG_DSC32_ DG_DSC_(31) DG_DSC_(30) DG_DSC_(29) DG_DSC_(28) DG_DSC_(27) DG_DSC_(26) DG_DSC_(25) DG_DSC_(24) DG_DSC_(23) DG_DSC_(22) DG_DSC_(21) DG_DSC_(20) DG_DSC_(19) DG_DSC_(18) DG_DSC_(17) DG_DSC_(16) DG_DSC16_
-    const int n1 = (P1 + K - 1) / K, n2 = (P2 + K - 1) / K, n3 = (Rp + K - 1) / K;   // pair index where a section ends
+    const int n1 = (P1 + K - 1) / K, n2 = (P2 + K - 1) / K, n3 = (Rp + K - 1) / K;   // step index where a section ends
     for (int it = 0; it < sc.iters; it++) {
       const bool fwd1 = (it & 1) != 0;
       if (!fwd1) {
-        if constexpr (W == 32) { switch (n1) { DG_DSC32_ default: break; } } else { switch (n1) { DG_DSC16_ default: break; } }
+        if constexpr (W == 32) { switch (n1) { DG_DSC32_ default: break; } } else if constexpr (W == 16) { switch (n1) { DG_DSC16_ default: break; } } else { switch (n1) { DG_DSC8_ default: break; } }
         DG_SETTLE
       }
 #pragma unroll 1
       for (int sec = fwd1 ? 0 : 1; sec < 3; sec++) {
         const int s_ = sec == 0 ? 0 : (sec == 1 ? n1 : n2), e_ = sec == 0 ? n1 : (sec == 1 ? n2 : n3);
         if (sec == 2) {
-          // friction bounds from the normal impulses this sweep left (the normal of contact c sits at warp position nrm0 + c)
+          // friction bounds from the normal impulses this sweep left (the normal of contact c sits at warp position nrm0 + c: slot
+          // (nrm0 + c) % K of lane (nrm0 + c) / K)
 #pragma unroll
           for (int k = 0; k < K; k++) {
             const int pn = par[k] >= 0 ? nrm0 + par[k] : 0;
-            const float v0 = __shfl_sync(FULL, ap[0], pn / K, W), v1 = __shfl_sync(FULL, ap[1], pn / K, W);
-            const float vn = (pn % K) ? v1 : v0;
+            float vn = 0.f;
+#pragma unroll
+            for (int k2 = 0; k2 < K; k2++) { const float vk = __shfl_sync(FULL, ap[k2], pn / K, W); vn = (pn % K) == k2 ? vk : vn; }
             if (par[k] >= 0) { hi[k] = mu[k] * vn; lo[k] = -hi[k]; lop[k] = lo[k] - ap[k]; hip[k] = hi[k] - ap[k]; }
           }
         }
         if (s_ >= e_) continue;
-        if constexpr (W == 32) { switch (s_) { DG_ASC32_ default: break; } } else { switch (s_) { DG_ASC16_ default: break; } }
+        if constexpr (W == 32) { switch (s_) { DG_ASC32_ default: break; } } else if constexpr (W == 16) { switch (s_) { DG_ASC16_ default: break; } } else { switch (s_) { DG_ASC8_ default: break; } }
         DG_SETTLE
       }
     }
 #undef DG_SETTLE
 #undef DG_ASC_
 #undef DG_DSC_
+#undef DG_ASC8_
 #undef DG_ASC16_
 #undef DG_ASC32_
+#undef DG_DSC8_
 #undef DG_DSC16_
 #undef DG_DSC32_
-#undef DG_STEP2
+#undef DG_STEPK
     if (writer) {
 #pragma unroll
       for (int k = 0; k < K; k++) if (qown[k] >= 0) REC[RR_W * qown[k] + RR_APPLIED] = ap[k];
     }
   }
 }
-// cls 0: environments with <= 32 row positions (two per warp), cls 1: <= 64 (one per warp)
+// class c of the scene (DevScene::rs_cls_k / rs_cls_r): the instantiation with W = positions / K lanes per environment
 static cudaError_t solve_launch(int cls, const DevScene& sc, const SolveArgs& a, int n_envs, cudaStream_t s) {
-  if (cls == 0) dg_solve_kernel<16><<<(n_envs + 1) / 2, 32, 0, s>>>(sc, a); else dg_solve_kernel<32><<<n_envs, 32, 0, s>>>(sc, a);
+  const int K = sc.rs_cls_k[cls], W = sc.rs_cls_r[cls] / std::max(K, 1);
+  if (K == 4 && W == 8) dg_solve_kernel<8, 4><<<(n_envs + 3) / 4, 32, 0, s>>>(sc, a);
+  else if (K == 3 && W == 16) dg_solve_kernel<16, 3><<<(n_envs + 1) / 2, 32, 0, s>>>(sc, a);
+  else if (K == 2 && W == 16) dg_solve_kernel<16, 2><<<(n_envs + 1) / 2, 32, 0, s>>>(sc, a);
+  else if (K == 2 && W == 32) dg_solve_kernel<32, 2><<<n_envs, 32, 0, s>>>(sc, a);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 #endif
@@ -603,7 +627,7 @@ struct DgWorld {
   float* carry = nullptr;              // [n_envs + slack][w_total] hot workspaces between stage launches
   int* rs_lists = nullptr;             // [2][n_envs] environments deferred to the sweep kernel (K = 1 | K = 2)
   int* rs_counts = nullptr;            // [substeps][2]
-  cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // the one-per-warp sweeps run beside the two-per-warp sweeps
+  cudaStream_t aux = nullptr, aux2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;   // the sweep classes run side by side
   // Which schedule a step takes is decided from how many environments actually needed the contact solver lately: the stage
   // launches + carry traffic cost ~0.3 ms per step, which only pays when a good share of the environments is in contact
   // (a drone in the air, an R2D2 still falling: fused launch).  The device counter is copied to pinned memory every
@@ -721,6 +745,16 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
   // at least that many contact rows are solved in row space too (both kept for A/B measurements)
   if (const char* env_solver = getenv("DG_SOLVER")) w->hs.dev.solver = atoi(env_solver) != 0;
   if (const char* env_min = getenv("DG_RS_MIN")) w->hs.dev.rs_min = atoi(env_min);
+  // DG_SWEEP_CLASSES="K:R,K:R,K:R" (rows per lane : row positions; 0:0 = unused) replaces the sweep-kernel classes, e.g. "2:32,0:0,2:64"
+  // = the two-rows-per-lane classes of the first split build (A/B measurements)
+  if (const char* ec = getenv("DG_SWEEP_CLASSES")) {
+    int k[RS_NCLS] = {0, 0, 0}, r[RS_NCLS] = {0, 0, 0};
+    if (sscanf(ec, "%d:%d,%d:%d,%d:%d", &k[0], &r[0], &k[1], &r[1], &k[2], &r[2]) >= 2) {
+      bool ok = true;
+      for (int c = 0; c < RS_NCLS; c++) ok = ok && (r[c] == 0 || (k[c] == 4 && r[c] == 32) || (k[c] == 3 && r[c] == 48) || (k[c] == 2 && (r[c] == 32 || r[c] == 64)));
+      if (ok) for (int c = 0; c < RS_NCLS; c++) { w->hs.dev.rs_cls_k[c] = k[c]; w->hs.dev.rs_cls_r[c] = r[c]; }
+    }
+  }
   if (const char* env_pr = getenv("DG_PRECISE")) w->hs.dev.precise = atoi(env_pr) != 0;   // A/B of the SFU sincos in FK / IK (tools/qd_probe.py)
   {
     size_t per_team = (size_t)w->hs.dev.w_total * sizeof(float);
@@ -759,9 +793,10 @@ int dg_world_create(const int32_t* ibuf, int n_ibuf, const double* fbuf, int n_f
     w->split = w->split_ok && (w->split_mode == 1 || w->hs.dev.ncons > 0);   // welded models always have rows; else start fused and adapt
     if (w->split_ok) {
       const size_t nc = ((size_t)w->n_envs + 256) * (size_t)w->hs.dev.w_total * sizeof(float);
-      bool ok = cudaMalloc(&w->carry, nc) == cudaSuccess && cudaMalloc(&w->rs_lists, 2 * (size_t)w->n_envs * sizeof(int)) == cudaSuccess &&
-                cudaMalloc(&w->rs_counts, 2 * (size_t)std::max(w->hs.dev.substeps, 1) * sizeof(int)) == cudaSuccess &&
-                cudaStreamCreateWithFlags(&w->aux, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&w->cap, cudaStreamNonBlocking) == cudaSuccess &&
+      bool ok = cudaMalloc(&w->carry, nc) == cudaSuccess && cudaMalloc(&w->rs_lists, RS_NCLS * (size_t)w->n_envs * sizeof(int)) == cudaSuccess &&
+                cudaMalloc(&w->rs_counts, RS_NCLS * (size_t)std::max(w->hs.dev.substeps, 1) * sizeof(int)) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&w->aux, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&w->aux2, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaStreamCreateWithFlags(&w->cap, cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&w->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&w->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&w->ev_join, cudaEventDisableTiming) == cudaSuccess &&
                 cudaEventCreateWithFlags(&w->ev_stat, cudaEventDisableTiming) == cudaSuccess && cudaMalloc(&w->rs_used, sizeof(unsigned)) == cudaSuccess &&
                 cudaMemset(w->rs_used, 0, sizeof(unsigned)) == cudaSuccess && cudaMallocHost(&w->h_rs_used, sizeof(unsigned)) == cudaSuccess;
@@ -785,6 +820,8 @@ void dg_world_destroy(DgWorld* w) {
   if (w->rs_lists) cudaFree(w->rs_lists);
   if (w->rs_counts) cudaFree(w->rs_counts);
   if (w->aux) cudaStreamDestroy(w->aux);
+  if (w->aux2) cudaStreamDestroy(w->aux2);
+  if (w->ev_join2) cudaEventDestroy(w->ev_join2);
   if (w->ev_fork) cudaEventDestroy(w->ev_fork);
   if (w->ev_join) cudaEventDestroy(w->ev_join);
   if (w->ev_stat) cudaEventDestroy(w->ev_stat);
@@ -855,7 +892,7 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   DeviceGuard guard(w->device);
   if (!guard.ok) { w->err = "cudaSetDevice failed"; cudaGetLastError(); return DG_E_CUDA; }
   LaunchArgs a{w->buf.state, w->buf.param, w->buf.action, w->buf.obs, w->buf.reward, w->buf.term, mask, w->n_envs, mode, w->seed, w->env_off, {w->opmask[0], w->opmask[1]}, w->gws, w->dbg, w->dropped,
-               ST_ALL, nullptr, nullptr, nullptr, nullptr, mode == 0 ? w->rs_used : nullptr, 0};
+               ST_ALL, nullptr, nullptr, nullptr, mode == 0 ? w->rs_used : nullptr, 0};
   cudaStream_t s = (cudaStream_t)stream;
   if (mode == 0 && w->split_ok && w->split_mode < 0 && w->dev.ncons == 0) {
     // adaptive schedule: share of environment sub-steps that needed the contact solver over the last period
@@ -880,11 +917,11 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
   //   stage launch [add-on update, load | sub-step 0 up to the row-space system] -> sweeps ->
   //   stage launch [impulses + integration of sub-step k-1 | sub-step k up to its system] -> sweeps -> ... ->
   //   stage launch [impulses + integration of the last sub-step | link cache, state rows, sensors / rewards / terminals]
-  // The sweeps of one sub-step are two launches of the sweep kernel: environments with <= 32 row positions (two per warp) on this
-  // stream, those with <= 64 (one per warp) beside them on the world's auxiliary stream (they take longest, so they should not
+  // The sweeps of one sub-step are one launch of the sweep kernel per class: environments with <= 32 row positions (four per warp) on this
+  // stream, the other classes beside them on the world's auxiliary streams (the one-per-warp class takes longest, so it should not
   // queue behind the others).
   const int nsub = std::max(w->dev.substeps, 1);
-  a.carry = w->carry; a.rs_list0 = w->rs_lists; a.rs_list1 = w->rs_lists + w->n_envs;
+  a.carry = w->carry; a.rs_lists = w->rs_lists;
   // (DIYGym.reset of the masked environments: reset hooks + link cache as one fused launch, then every hot-start step takes the
   // same cut as a step, without add-on update; blocks without a masked environment return at once, the sweep kernel only sees
   // the listed ones)
@@ -894,18 +931,25 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
     for (int sub = 0; sub <= nsub; sub++) {
       const int first = mode == 0 ? ST_ACT : ST_LOAD;
       a.stages = (sub == 0 ? first : (ST_LOADC | ST_POST)) | (sub < nsub ? (ST_PRE | ST_SAVEC) : ST_END);
-      a.rs_count = w->rs_counts + 2 * std::min(sub, nsub - 1);
-      if (sub == 0) CK(w, cudaMemsetAsync(w->rs_counts, 0, 2 * (size_t)nsub * sizeof(int), q));
+      a.rs_count = w->rs_counts + RS_NCLS * std::min(sub, nsub - 1);
+      if (sub == 0) CK(w, cudaMemsetAsync(w->rs_counts, 0, RS_NCLS * (size_t)nsub * sizeof(int), q));
       CK(w, launch_any(w, a, q));
       if (sub == nsub) break;
+      // the sweep classes of this sub-step side by side: class 0 on this stream, the others on the world's auxiliary streams
       CK(w, cudaEventRecord(w->ev_fork, q));
-      CK(w, cudaStreamWaitEvent(w->aux, w->ev_fork, 0));
-      const SolveArgs s2{w->carry, w->gws, a.rs_list1, a.rs_count + 1}, s1{w->carry, w->gws, a.rs_list0, a.rs_count};
-      CK(w, solve_launch(1, w->dev, s2, w->n_envs, w->aux));
-      CK(w, cudaEventRecord(w->ev_join, w->aux));
-      CK(w, solve_launch(0, w->dev, s1, w->n_envs, q));
-      CK(w, cudaStreamWaitEvent(q, w->ev_join, 0));
-      w->launches += 2;
+      int nl = 0;
+      for (int c = RS_NCLS - 1; c >= 0; c--) {
+        if (w->dev.rs_cls_r[c] <= 0) continue;
+        const int* list = w->rs_lists + (size_t)c * w->n_envs;
+        const SolveArgs sa{w->carry, w->gws, list, a.rs_count + c};
+        cudaStream_t sq = c == 0 ? q : (c == 1 ? w->aux : w->aux2);
+        if (c > 0) CK(w, cudaStreamWaitEvent(sq, w->ev_fork, 0));
+        CK(w, solve_launch(c, w->dev, sa, w->n_envs, sq));
+        if (c > 0) CK(w, cudaEventRecord(c == 1 ? w->ev_join : w->ev_join2, sq));
+        nl++;
+      }
+      for (int c = 1; c < RS_NCLS; c++) if (w->dev.rs_cls_r[c] > 0) CK(w, cudaStreamWaitEvent(q, c == 1 ? w->ev_join : w->ev_join2, 0));   // (after class 0 is in the queue)
+      w->launches += nl;
     }
     return DG_OK;
   };
@@ -925,7 +969,7 @@ static int run(DgWorld* w, int mode, const uint8_t* mask, void* stream) {
     memcpy(w->graph_key, key, sizeof(key)); w->graph_valid = true;
   }
   CK(w, cudaGraphLaunch(w->graph_exec, s));
-  w->launches += (nsub + 1) + 2 * nsub;
+  { int ncl = 0; for (int c = 0; c < RS_NCLS; c++) ncl += w->dev.rs_cls_r[c] > 0; w->launches += (nsub + 1) + ncl * nsub; }
   return DG_OK;
 }
 // Measurement aid: with `enable`, thread 0 of every block of the step kernel accumulates the cycles of each phase (barrier

@@ -22,8 +22,9 @@ enum { BP_DI = 0, BP_GDIM, BP_GVOFF, BP_MINVOFF, BP_I0OFF, BP_SLOT, BP_UROW, BP_
 enum { WH_NCONTACT = 0, WH_NCROW, WH_NSURV, WH_COUPLED, WH_RS_R, WH_RS_NU, WH_RS_K, WH_RS_NEED, WH_RS_DEFER, WH_SUB, WH_COUNT = 12 };
 // stages of one DIYGym.step when the contact sweeps run in their own kernel (dg_kernels.cu): see dg_env.cuh "the phase schedule"
 enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC = 32, ST_LOAD = 128, ST_ALL = 15 };
-// row capacity of the sweep kernel: a warp per environment, K = 1 (<= 32 rows) or 2 (<= 64 rows) rows per lane, A in registers
-enum { RS_WARP_R1 = 32, RS_WARP_R2 = 64 };
+// classes of the sweep kernel (dg_kernels.cu, dg_solve_kernel<W, K>): W lanes per environment, K consecutive rows per lane, W K row
+// positions; an environment goes to the first class its K-padded layout fits (DevScene::rs_cls_k / rs_cls_r)
+enum { RS_NCLS = 3 };
 // row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j
 enum { RS_CONTACT = 0x40000000, RS_KMAX = 8, RS_GVMAX = 128 };
 // row record of the row-space solver
@@ -75,6 +76,7 @@ struct DevScene {
   const int* cons_i; const float* cons_f;
   int need_react;   // a force / torque sensor op reads the joint reaction wrenches (state section S_JREACT)
   int rs_min;   // contact rows an uncoupled environment needs before the team solves it in row space (fewer: per-body sweeps)
+  int rs_cls_k[RS_NCLS], rs_cls_r[RS_NCLS];   // sweep-kernel classes: rows per lane, row positions (0: class unused)
   int solver;   // 1: contact environments are solved in row space by the whole team (default), 0: per-body dv-space sweeps
   int crow_stride, mscr_stride, ctmp_stride, ik_stride;
   int sem;      // SEM_* switches of the engine semantics that could only be recalled (compiler/scene.py SEMANTICS)
@@ -349,6 +351,11 @@ struct HostScene {
     }
     // every environment with contacts is solved in row space (round 1 kept uncoupled ones on the per-body sweeps: its row-space
     // sweeps were slower, profiles/r1_rs_min_sweep.log; DG_RS_MIN restores that for A/B runs)
+    // sweep-kernel classes (split schedule): 16 lanes x 2 rows (two environments per warp) and 32 x 2 (one per warp).  The kernel
+    // also exists as 8 x 4 (<= 32 positions, four per warp) and 16 x 3 (<= 48): measured on the B200 (profiles/r2_sweep_class_ab.log,
+    // DG_SWEEP_CLASSES) 8 x 4 loses everywhere (250 registers, longer steps), 16 x 3 as a middle class wins 1-4 % where few
+    // environments need it (r2d2_maze, ur_robotiq) and loses 4 % where all do (from_the_readme) - so it is off by default.
+    d.rs_cls_k[0] = 2; d.rs_cls_r[0] = 32; d.rs_cls_k[1] = 0; d.rs_cls_r[1] = 0; d.rs_cls_k[2] = 2; d.rs_cls_r[2] = 64;
     d.solver = 1; d.rs_min = 0;   // every environment with contacts is solved in row space (round 1 kept uncoupled ones on the per-body sweeps: its row-space sweeps were slower, profiles/r1_rs_min_sweep.log; DG_RS_MIN restores that for A/B runs)
     d.rs_ashared = 0; d.X_RSAS = 0; (void)rs_ashared;   // (shared-memory home of A: measured slower, removed)
     phase_take(&d.X_RSA, RC_SCRATCH, 1, d.rs_cap * d.rs_cap + RS_KMAX * team);

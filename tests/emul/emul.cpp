@@ -49,7 +49,7 @@ static Env make_env(EmulWorld* w, int e, const float* act, float* obs, float* re
   const DevScene& d = w->hs.dev; Env C;
   C.sc = &d; C.ws = w->ws.data(); C.wg = w->wg.data(); C.link_i = d.link_i; C.link_f = d.link_f; C.link_x = d.link_x; C.st = w->state.data() + (size_t)e * d.S; C.pr = w->param.data() + (size_t)e * d.P;
   C.act = act ? act + (size_t)e * d.n_act : nullptr; C.obs = obs + (size_t)e * d.n_obs; C.rew = rew + (size_t)e * d.n_rew;
-  C.dbg = nullptr; C.active = true; C.grp0 = 0; C.grp1 = 1; C.dropped = &w->dropped; C.split = 0; C.rs_list[0] = C.rs_list[1] = nullptr; C.rs_count = nullptr; C.e_local = e; C.rs_used = nullptr; C.no_hot = 0; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
+  C.dbg = nullptr; C.active = true; C.grp0 = 0; C.grp1 = 1; C.dropped = &w->dropped; C.split = 0; C.rs_lists = nullptr; C.rs_stride = 0; C.rs_count = nullptr; C.e_local = e; C.rs_used = nullptr; C.no_hot = 0; C.term = term + (size_t)e * d.n_term; C.seed = w->seed; C.env_id = w->env_off + e; C.opmask[0] = w->opmask[0]; C.opmask[1] = w->opmask[1];
   return C;
 }
 // DGE_POISON=<value>: fills both workspaces with that value before every environment, so that a read of workspace memory
