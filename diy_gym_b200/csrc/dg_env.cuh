@@ -2074,7 +2074,7 @@ DG_NOINLINE DG_FN void physics_pre(const Env& C, int nt, float h, DG_LANE_ARGS) 
 }
 // ... and the rest of it: impulses of the deferred environments (swept by the sweep kernel in between) folded into dv, integration
 DG_NOINLINE DG_FN void physics_post(const Env& C, int nt, float h, DG_LANE_ARGS) {
-  if (SC.solver == 1 && nt > 1 && C.split) DG_PHASE(if (HDRV(WH_RS_R) > 0 && HDRV(WH_RS_DEFER) != 0) phase_rs_finish(C, ln, nt));
+  // (deferred environments: the sweep kernel has folded the impulses into dv and the unit-row records of the carried workspace)
   DG_PHASE(phase_integrate(C, ln, nt, h));
   if (SC.sem & SEM_WRENCH_FIRST_SUBSTEP) DG_PHASE(phase_next_substep(C, ln, nt));
 }

@@ -130,7 +130,7 @@ DG_DEFINE_STEP_X(DG_STEP_T)
 // inert padding); if that common layout does not fit, the warp sweeps its environments one after the other.  Everything that
 // steers the loops is read through block-uniform addresses, so the loop branches stay uniform (no divergence bookkeeping around
 // the shuffles).
-struct SolveArgs { const float* carry; float* gws; const int* list; const int* count; };
+struct SolveArgs { float* carry; float* gws; const int* list; const int* count; };
 template <int W, int K>
 __global__ void __launch_bounds__(32, (K == 2 ? (W == 16 ? 16 : 12) : 8)) dg_solve_kernel(const __grid_constant__ DevScene sc, const SolveArgs a) {
   constexpr int G = 32 / W, RMAX = W * K;
@@ -297,6 +297,26 @@ __global__ void __launch_bounds__(32, (K == 2 ? (W == 16 ? 16 : 12) : 8)) dg_sol
     if (writer) {
 #pragma unroll
       for (int k = 0; k < K; k++) if (qown[k] >= 0) REC[RR_W * qown[k] + RR_APPLIED] = ap[k];
+    }
+    __syncwarp();
+    // ... and what phase_rs_finish would do in the next stage launch, with W lanes and the rows still in cache: dv of every
+    // body from the accumulated impulses (dv = sum_rows (M^-1 J^T)_row x applied_row, rows in order - the same sums), motor /
+    // limit impulses back into their unit-row records.  Both live in the hot workspace: written into the environment's carry row.
+    if (writer && live) {
+      const int GV = sc.GV; const float* RSV = wg + sc.X_RSV;
+      float* hot = a.carry + (size_t)emine * sc.w_total;
+#pragma unroll 1
+      for (int i = l; i < GV; i += W) {
+        float sum = 0.f;
+#pragma unroll 1
+        for (int p = 0; p < L.Rp; p++) if (rs_real(L, p)) sum = fmaf(RSV[(size_t)p * 2 * GV + GV + i], REC[RR_W * p + RR_APPLIED], sum);
+        hot[sc.W_DV + i] = sum;
+      }
+#pragma unroll 1
+      for (int r = l; r < L.nu; r += W) {
+        const int id = float_as_int(REC[RR_W * r + RR_ID]); const int* bp = sc.body_plan + BP_W * sc.dyn_body[(id >> 16) & 0x3fff];
+        hot[sc.X_UROW + UR_W * (bp[BP_UROW] + (id & 0xffff)) + UR_APPLIED] = REC[RR_W * r + RR_APPLIED];
+      }
     }
   }
 }
