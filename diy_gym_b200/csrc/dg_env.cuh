@@ -1316,8 +1316,14 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     float* Jd = RSV + (size_t)r2 * 2 * GV; float* Md = Jd + GV;
     for (int i = 0; i < 2 * GV; i += 4) st4(Jd + i, 0.f, 0.f, 0.f, 0.f);
     int off = 0, slo = GV, shi = 0;
-    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[i]; Md[go + i] += M[i]; } off = g; slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
-    if (dib >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
+    // (the row was zeroed just above: plain stores, no read-modify-write of global memory, unless both sides are the same body)
+    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] = 0.f + J[i]; Md[go + i] = 0.f + M[i]; } off = g; slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
+    if (dib >= 0) {
+      const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM];
+      if (dib == dia) { for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } }
+      else { for (int i = 0; i < g; i++) { Jd[go + i] = 0.f + J[off + i]; Md[go + i] = 0.f + M[off + i]; } }
+      slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi;
+    }
     if (shi <= slo) { slo = 0; shi = 0; }
     float* rc = REC + RR_W * r2;
     st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], int_as_float(slo | (shi << 16)), int_as_float(RS_CONTACT | rr));
