@@ -427,7 +427,11 @@ DG_FN void minv_column(const Env& C, int b, int col, float* scr) {
   const int jo = kind == 2 ? 6 : 0;
   float* out = WSH(C, sc.W_MINV) + bp[BP_MINVOFF] + col * gs;
   for (int i = g; i < gs; i++) out[i] = 0.f;
-  float* uu = scr; float* ast = scr + sc.max_nlb;   // a-stack indexed by depth+1 (0 = base)
+  // u of every link and the stack of parent accelerations (indexed by depth + 1, 0 = base) live in THREAD-LOCAL memory: the pass
+  // down reads what it stored a few instructions earlier, and a global store -> load round trip through L2 at every branch of the
+  // tree was the longest stall of this phase (local memory stays in L1).  Caps checked by HostScene::build.
+  (void)scr;
+  float uu[DG_MINV_MAXL], ast[6 * DG_MINV_MAXD];
   for (int k = 0; k < nlb; k++) uu[k] = 0.f;
   float p[6] = {0, 0, 0, 0, 0, 0};
   if (col >= jo) {

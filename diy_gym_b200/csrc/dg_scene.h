@@ -25,6 +25,8 @@ enum { ST_ACT = 1, ST_PRE = 2, ST_POST = 4, ST_END = 8, ST_LOADC = 16, ST_SAVEC 
 // classes of the sweep kernel (dg_kernels.cu, dg_solve_kernel<W, K>): W lanes per environment, K consecutive rows per lane, W K row
 // positions; an environment goes to the first class its K-padded layout fits (DevScene::rs_cls_k / rs_cls_r)
 enum { RS_NCLS = 3 };
+// thread-local scratch of minv_column: links per body, tree depth + 2
+enum { DG_MINV_MAXL = 64, DG_MINV_MAXD = 24 };
 // row table of the row-space team solver: contact row rr = RS_CONTACT | rr, unit row j of dynamic body di = di << 16 | j
 enum { RS_CONTACT = 0x40000000, RS_KMAX = 8, RS_GVMAX = 128 };
 // row record of the row-space solver
@@ -284,6 +286,7 @@ struct HostScene {
     point(d, ints.data(), floats.data());
 
     d.ndyn = (int)dyn_body.size(); d.nslot = nslot; d.nshw = nshw; d.nfloat = nfloat; d.GD = GD; d.GP = GP;
+    if (max_nlb > DG_MINV_MAXL || max_depth + 2 > DG_MINV_MAXD) { error = "a body has more than " + std::to_string((int)DG_MINV_MAXL) + " links or a kinematic tree deeper than " + std::to_string((int)DG_MINV_MAXD - 2); return false; }
     d.max_depth = max_depth; d.max_nlb = max_nlb; d.n_ik = n_ik; d.ngrp = (int)grp_i.size() / 4; d.nloose = (int)loose_pairs.size();
 
     // ---- workspace layout ----
