@@ -1321,11 +1321,22 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     for (int i = 0; i < 2 * GV; i += 4) st4(Jd + i, 0.f, 0.f, 0.f, 0.f);
     int off = 0, slo = GV, shi = 0;
     // (the row was zeroed just above: plain stores, no read-modify-write of global memory, unless both sides are the same body)
-    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; for (int i = 0; i < g; i++) { Jd[go + i] = 0.f + J[i]; Md[go + i] = 0.f + M[i]; } off = g; slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
+    // (loads in batches of four ahead of their stores: the compiler may not move a load of J above a store to Jd - they could
+    // alias for all it knows - so a load / store pair per element waits a full memory latency per element)
+#define DG_COPY_ROW(dstJ, dstM, srcJ, srcM, g_)                                                                                   \
+    { int i_ = 0;                                                                                                                  \
+      for (; i_ + 4 <= (g_); i_ += 4) {                                                                                            \
+        const float j0_ = (srcJ)[i_], j1_ = (srcJ)[i_ + 1], j2_ = (srcJ)[i_ + 2], j3_ = (srcJ)[i_ + 3];                            \
+        const float m0_ = (srcM)[i_], m1_ = (srcM)[i_ + 1], m2_ = (srcM)[i_ + 2], m3_ = (srcM)[i_ + 3];                            \
+        (dstJ)[i_] = 0.f + j0_; (dstJ)[i_ + 1] = 0.f + j1_; (dstJ)[i_ + 2] = 0.f + j2_; (dstJ)[i_ + 3] = 0.f + j3_;                \
+        (dstM)[i_] = 0.f + m0_; (dstM)[i_ + 1] = 0.f + m1_; (dstM)[i_ + 2] = 0.f + m2_; (dstM)[i_ + 3] = 0.f + m3_;                \
+      }                                                                                                                            \
+      for (; i_ < (g_); i_++) { const float j0_ = (srcJ)[i_], m0_ = (srcM)[i_]; (dstJ)[i_] = 0.f + j0_; (dstM)[i_] = 0.f + m0_; } }
+    if (dia >= 0) { const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dia]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM]; DG_COPY_ROW(Jd + go, Md + go, J, M, g) off = g; slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi; }
     if (dib >= 0) {
       const int* bp = gc(sc.body_plan) + BP_W * gc(sc.dyn_body)[dib]; const int go = bp[BP_GVOFF], g = bp[BP_GDIM];
       if (dib == dia) { for (int i = 0; i < g; i++) { Jd[go + i] += J[off + i]; Md[go + i] += M[off + i]; } }
-      else { for (int i = 0; i < g; i++) { Jd[go + i] = 0.f + J[off + i]; Md[go + i] = 0.f + M[off + i]; } }
+      else DG_COPY_ROW(Jd + go, Md + go, J + off, M + off, g)
       slo = go < slo ? go : slo; shi = go + bp[BP_GS] > shi ? go + bp[BP_GS] : shi;
     }
     if (shi <= slo) { slo = 0; shi = 0; }
@@ -1333,6 +1344,7 @@ DG_FN void phase_rs_setup(const Env& C, int ln, int nt) {
     st4(rc, row[CR_RHS], row[CR_DINV], row[CR_LO], row[CR_HI]); st4(rc + 4, row[CR_MU], row[CR_PARENT], int_as_float(slo | (shi << 16)), int_as_float(RS_CONTACT | rr));
   }
 }
+#undef DG_COPY_ROW
 // A[p * cap + s] = J_s M^-1 J_p^T for real positions p, s < Rp; zero rows / columns for the padding positions and for the
 // columns up to K nt that the lanes of the sweeps read
 DG_FN void phase_rs_build(const Env& C, int ln, int nt) {
