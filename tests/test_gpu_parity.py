@@ -241,6 +241,34 @@ def test_camera_kernel_matches_oracle_ray_cast():
         env.close()
 
 
+@pytest.mark.parametrize('classes', ['4:32,3:48,2:64', '2:32,3:48,2:64', '0:0,0:0,2:64'])
+@pytest.mark.parametrize('name,scale', [('r2d2_maze', 10.0), ('from_the_readme', 0.01), ('ur_gripper', 0.01)])
+def test_sweep_kernel_classes_agree(monkeypatch, name, scale, classes):
+    """dg_solve_kernel<W, K> in its other instantiations (8 lanes x 4 rows, 16 x 3; DG_SWEEP_CLASSES) against the default classes
+    (16 x 2, 32 x 2): the same Gauss-Seidel updates in the same row order - only the padding of the sections and the number of rows
+    a lane folds locally differ - so the states agree like the split and the fused schedule do."""
+    n, steps = 96, 12
+    states = {}
+    monkeypatch.setenv('DG_SPLIT', '1')
+    for key, cls in (('default', None), ('other', classes)):
+        if cls is None:
+            monkeypatch.delenv('DG_SWEEP_CLASSES', raising=False)
+        else:
+            monkeypatch.setenv('DG_SWEEP_CLASSES', cls)
+        env = _env(name, n, seed=5)
+        g = torch.Generator(device='cuda').manual_seed(3)
+        for k in range(steps):
+            env.world.action.copy_((torch.rand(env.world.action.shape, device='cuda', generator=g) * 2 - 1) * scale)
+            env.world.step()
+        torch.cuda.synchronize()
+        states[key] = env.world.state.clone()
+        env.close()
+    a, b = states['default'], states['other']
+    assert torch.isfinite(b).all()
+    assert (a - b).abs().max().item() <= 2e-3 * max(1.0, a.abs().max().item())
+    assert torch.isclose(a, b, rtol=1e-4, atol=1e-5).float().mean().item() > 0.99
+
+
 def test_camera_u8_colour_matches_float_render():
     """dg_render_u8 (camera key `rgb_uint8`): bytes = round(255 c) of the float render, depth and mask unchanged; both patch sizes
     (50 x 50: 8 x 4 patches, 200 x 200: 8 x 8) and the unaligned-width scalar path (50 is not a multiple of 8)."""
